@@ -1,0 +1,84 @@
+// common.cuh -- layout constants, error plumbing and sm_100a PTX helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------
+// Device body storage: "blocked SoA".  Bodies are grouped in blocks of BLK = 256; one block is
+//     T x[256], y[256], z[256], m[256]          (4 KiB for float, 8 KiB for double)
+// so (a) a thread reading lane t of a component is perfectly coalesced, (b) a source tile of any
+// whole number of blocks is ONE contiguous range -> one cp.async.bulk (TMA 1-D bulk copy) stages
+// it, and lands in shared memory already in SoA form, where a single LDS.128 yields four
+// consecutive x (or y, z, m) values = two packed f32x2 operands, and (c) a rank's shard is a
+// contiguous byte range -> in-place ncclAllGather.  vel uses the same blocks with (vx,vy,vz,radius),
+// acc with (ax,ay,az,unused).
+// Replaces the reference's 64-byte AoS Body (Body.hpp:6-14), of which the force loop touches 12 B.
+// ---------------------------------------------------------------------------------------------
+constexpr int BLK = 256;                 // bodies per block
+constexpr int BLK_ELEMS = 4 * BLK;       // scalars per block
+
+__host__ __device__ inline size_t blk_index(size_t body, int comp)
+{
+    return (body >> 8) * (size_t)BLK_ELEMS + (size_t)comp * BLK + (body & 255);
+}
+
+// ---- sm_100a PTX helpers: mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; completion is signalled as transaction bytes on `bar`.
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                             uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// MUFU.RSQ, no denormal fix-up code around it
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+} // namespace nb

@@ -1,0 +1,87 @@
+// kernels.h -- launch interface between the C-ABI layer (nbody_gpu.cu) and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace nb {
+
+// Integrator constants (defaults == Simulation.hpp:120-124), shared by the fused epilogue of the
+// force kernel and the stand-alone integrator so both perform identical arithmetic.
+struct IntegParams {
+    float dt;
+    float G;
+    unsigned flags;          // NBODY_INTEG_*
+    float max_velocity;      // MAX_VELOCITY
+    float max_velocity_sq;   // MAX_VELOCITY * MAX_VELOCITY (fp32 product, as the reference forms it)
+    float soft_boundary;     // BOUNDARY_RADIUS * 0.8f
+    float soft_boundary_sq;  // SOFT_BOUNDARY * SOFT_BOUNDARY
+    float boundary_force;    // BOUNDARY_FORCE
+    float damping;           // DAMPING
+};
+
+// One force launch: targets = n_itiles tiles starting at block i_blk0; sources = blocks
+// [j_blk0, j_blk0 + j_nblk) cut into `splits` chunks; CTA (tile, s) writes its partial sum into
+// partial slot slot0 + s.  Slots are summed in index order by the integrator (deterministic).
+struct ForceLaunch {
+    const void *posm;        // blocked (x,y,z,m), float or double
+    void *accp;              // partial accelerations, blocked, [slot][local block]
+    int i_blk0;              // first target block (global block index into posm)
+    int i_blk_local0;        // same block's index inside this GPU's shard (for accp / vel / acc)
+    int n_iblk;              // target blocks in this launch
+    int n_iblk_shard;        // blocks in the whole shard (slot stride of accp)
+    int j_blk0, j_nblk;      // source block range
+    long long j_body_limit;  // sources >= this global body index are padding (refcompat skips them)
+    int splits, slot0;
+    float eps2;
+    double eps2_f64;
+    // fused kick-drift epilogue (fast fp32 kernel, splits == 1, single launch per step)
+    int fuse;
+    void *posm_next;         // blocked, full array (only the target blocks are written)
+    void *vel;               // blocked, shard-local
+    void *acc;               // blocked, shard-local
+    IntegParams ip;
+};
+
+struct IntegLaunch {
+    const void *posm_cur;    // blocked, full array
+    void *posm_next;         // blocked, full array
+    void *vel, *acc;         // blocked, shard-local
+    const void *accp;        // partial slots
+    int nslots;
+    int i_blk0;              // first global block of the shard
+    int n_iblk_shard;
+    int acc_only;            // 1: acc := G * sum(partials), no kick-drift (nbody_gpu_accel_only)
+    long long n_real;        // bodies >= n_real are zero-mass padding: never moved
+    IntegParams ip;
+};
+
+// geometry of each force kernel variant
+constexpr int FAST_THREADS = 256, FAST_I = 4, FAST_TILE_BLKS = FAST_I;       // 1024 targets / CTA
+constexpr int REF_THREADS = 128, REF_TILE_BODIES = 128;                      // refcompat: 1 / thread
+constexpr int F64_THREADS = 128, F64_I = 2, F64_TILE_BLKS = 1;               // 256 targets / CTA
+constexpr int TARGET_GRANULE = FAST_TILE_BLKS * BLK;                         // shard granularity
+
+cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStream_t st);
+cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st);
+cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st);
+int force_f32_fast_ctas_per_sm(bool fuse);
+int force_f32_fast_grid(const ForceLaunch &L);
+
+cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st);
+cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st);
+
+// AoS (reference Body, 64 B) <-> blocked SoA
+cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,
+                        size_t shard_count, void *posm, void *vel, void *acc, bool f64,
+                        cudaStream_t st);
+cudaError_t launch_unpack(void *aos, size_t n, size_t shard_start, size_t shard_count,
+                          const void *posm, const void *vel, const void *acc, bool f64,
+                          cudaStream_t st);
+cudaError_t launch_unpack_f64(double *pos3, double *vel3, double *acc3, size_t n,
+                              size_t shard_start, size_t shard_count, const void *posm,
+                              const void *vel, const void *acc, bool f64, cudaStream_t st);
+
+// fp64 diagnostics: out[0]=K, out[1]=W (pairs counted twice, caller halves), out[2..4]=P
+cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, size_t shard_start,
+                          size_t shard_count, double eps2, bool f64, double *out5, cudaStream_t st);
+
+} // namespace nb

@@ -1,0 +1,175 @@
+// layout.cu -- body storage conversion (host AoS <-> device blocked SoA) and fp64 diagnostics.
+//
+// pack/unpack restate nothing arithmetic: they move the reference's 64-byte `Body` records
+// (Body.hpp:6-14) into the device layout described in common.cuh and back
+// (`SHARED_BODIES = simulation->bodies`, main.cpp:625, is the reference-side analogue).
+#include "kernels.h"
+#include "../../include/nbody_body.h"
+
+namespace nb {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_kernel(const nbody_body_t *__restrict__ aos, size_t n, size_t n_padded, size_t shard_start,
+            size_t shard_count, T *__restrict__ posm, T *__restrict__ vel, T *__restrict__ acc)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    // each thread reads its 64-byte record as four 16-byte vectors (a warp covers 2 KiB contiguous)
+    float4 p = make_float4(0, 0, 0, 0), v = p, a = p, mr = p;
+    if (i < n) {
+        const float4 *r = reinterpret_cast<const float4 *>(aos + i);
+        p = r[0]; v = r[1]; a = r[2]; mr = r[3];
+    }
+    const size_t g = blk_index(i, 0);
+    posm[g] = (T)p.x; posm[g + BLK] = (T)p.y; posm[g + 2 * BLK] = (T)p.z;
+    posm[g + 3 * BLK] = (T)mr.x;   // zero-mass padding beyond n: contributes exactly 0
+    if (i >= shard_start && i < shard_start + shard_count) {
+        const size_t l = blk_index(i - shard_start, 0);
+        vel[l] = (T)v.x; vel[l + BLK] = (T)v.y; vel[l + 2 * BLK] = (T)v.z; vel[l + 3 * BLK] = (T)mr.y;
+        acc[l] = (T)a.x; acc[l + BLK] = (T)a.y; acc[l + 2 * BLK] = (T)a.z; acc[l + 3 * BLK] = (T)0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_kernel(nbody_body_t *__restrict__ aos, size_t n, size_t shard_start, size_t shard_count,
+              const T *__restrict__ posm, const T *__restrict__ vel, const T *__restrict__ acc)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // index inside the shard
+    const size_t i = shard_start + k;
+    if (k >= shard_count || i >= n) return;
+    const size_t g = blk_index(i, 0), l = blk_index(k, 0);
+    float4 *r = reinterpret_cast<float4 *>(aos + k);              // staging holds the shard only
+    r[0] = make_float4((float)posm[g], (float)posm[g + BLK], (float)posm[g + 2 * BLK], 0.f);
+    r[1] = make_float4((float)vel[l], (float)vel[l + BLK], (float)vel[l + 2 * BLK], 0.f);
+    r[2] = make_float4((float)acc[l], (float)acc[l + BLK], (float)acc[l + 2 * BLK], 0.f);
+    r[3] = make_float4((float)posm[g + 3 * BLK], (float)vel[l + 3 * BLK], 0.f, 0.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_f64_kernel(double *__restrict__ pos3, double *__restrict__ vel3, double *__restrict__ acc3,
+                  size_t n, size_t shard_start, size_t shard_count, const T *__restrict__ posm,
+                  const T *__restrict__ vel, const T *__restrict__ acc)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = shard_start + k;
+    if (k >= shard_count || i >= n) return;
+    const size_t g = blk_index(i, 0), l = blk_index(k, 0);
+    if (pos3) { pos3[3 * k] = posm[g]; pos3[3 * k + 1] = posm[g + BLK]; pos3[3 * k + 2] = posm[g + 2 * BLK]; }
+    if (vel3) { vel3[3 * k] = vel[l]; vel3[3 * k + 1] = vel[l + BLK]; vel3[3 * k + 2] = vel[l + 2 * BLK]; }
+    if (acc3) { acc3[3 * k] = acc[l]; acc3[3 * k + 1] = acc[l + BLK]; acc3[3 * k + 2] = acc[l + 2 * BLK]; }
+}
+
+cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,
+                        size_t shard_count, void *posm, void *vel, void *acc, bool f64,
+                        cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((n_padded + 255) / 256);
+    if (f64)
+        pack_kernel<double><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, n, n_padded, shard_start,
+                                                  shard_count, (double *)posm, (double *)vel,
+                                                  (double *)acc);
+    else
+        pack_kernel<float><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, n, n_padded, shard_start,
+                                                 shard_count, (float *)posm, (float *)vel,
+                                                 (float *)acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(void *aos, size_t n, size_t shard_start, size_t shard_count,
+                          const void *posm, const void *vel, const void *acc, bool f64,
+                          cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((shard_count + 255) / 256);
+    if (f64)
+        unpack_kernel<double><<<grid, 256, 0, st>>>((nbody_body_t *)aos, n, shard_start, shard_count,
+                                                    (const double *)posm, (const double *)vel,
+                                                    (const double *)acc);
+    else
+        unpack_kernel<float><<<grid, 256, 0, st>>>((nbody_body_t *)aos, n, shard_start, shard_count,
+                                                   (const float *)posm, (const float *)vel,
+                                                   (const float *)acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_f64(double *pos3, double *vel3, double *acc3, size_t n,
+                              size_t shard_start, size_t shard_count, const void *posm,
+                              const void *vel, const void *acc, bool f64, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((shard_count + 255) / 256);
+    if (f64)
+        unpack_f64_kernel<double><<<grid, 256, 0, st>>>(pos3, vel3, acc3, n, shard_start, shard_count,
+                                                        (const double *)posm, (const double *)vel,
+                                                        (const double *)acc);
+    else
+        unpack_f64_kernel<float><<<grid, 256, 0, st>>>(pos3, vel3, acc3, n, shard_start, shard_count,
+                                                       (const float *)posm, (const float *)vel,
+                                                       (const float *)acc);
+    return cudaGetLastError();
+}
+
+// ---- energy / momentum diagnostic, fp64 arithmetic and accumulation ------------------------------
+// K = sum 1/2 m v^2, P = sum m v over the shard; W2 = - sum_{i in shard} sum_{j != i} m_i m_j
+// rsqrt(r^2 + eps^2) over ALL sources (each pair counted twice over the whole system; the caller
+// halves after summing ranks).  Sources are read straight from the blocked array: all lanes of a
+// warp read the same address (broadcast) and the array is L2-resident.
+template <typename T>
+__global__ void __launch_bounds__(256)
+energy_kernel(const T *__restrict__ posm, const T *__restrict__ vel, size_t n_padded,
+              size_t shard_start, size_t shard_count, double eps2, double *__restrict__ out5)
+{
+    __shared__ double red[5][8];
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double K = 0, W = 0, P0 = 0, P1 = 0, P2 = 0;
+    if (k < shard_count) {
+        const size_t i = shard_start + k;
+        const size_t g = blk_index(i, 0), l = blk_index(k, 0);
+        const double xi = posm[g], yi = posm[g + BLK], zi = posm[g + 2 * BLK], mi = posm[g + 3 * BLK];
+        const double vx = vel[l], vy = vel[l + BLK], vz = vel[l + 2 * BLK];
+        K = 0.5 * mi * (vx * vx + vy * vy + vz * vz);
+        P0 = mi * vx; P1 = mi * vy; P2 = mi * vz;
+        double w = 0;
+        const size_t nblk = n_padded / BLK;
+        for (size_t b = 0; b < nblk; ++b) {
+            const T *sx = posm + b * BLK_ELEMS;
+#pragma unroll 4
+            for (int j = 0; j < BLK; ++j) {
+                const double dx = (double)sx[j] - xi, dy = (double)sx[BLK + j] - yi,
+                             dz = (double)sx[2 * BLK + j] - zi;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const bool self = (b * BLK + j) == i;
+                w += self ? 0.0 : (double)sx[3 * BLK + j] * rsqrt(r2 + eps2);
+            }
+        }
+        W = -mi * w;
+    }
+    double v[5] = {K, W, P0, P1, P2};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+        if ((threadIdx.x & 31) == 0) red[c][threadIdx.x >> 5] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        atomicAdd(&out5[threadIdx.x], s);
+    }
+}
+
+cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, size_t shard_start,
+                          size_t shard_count, double eps2, bool f64, double *out5, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((shard_count + 255) / 256);
+    if (f64)
+        energy_kernel<double><<<grid, 256, 0, st>>>((const double *)posm, (const double *)vel,
+                                                    n_padded, shard_start, shard_count, eps2, out5);
+    else
+        energy_kernel<float><<<grid, 256, 0, st>>>((const float *)posm, (const float *)vel, n_padded,
+                                                   shard_start, shard_count, eps2, out5);
+    return cudaGetLastError();
+}
+
+} // namespace nb

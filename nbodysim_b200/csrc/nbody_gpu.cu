@@ -1,0 +1,714 @@
+// nbody_gpu.cu -- the C ABI (include/nbody_gpu.h) and the per-step driver.
+//
+// Replaces, behind a C boundary, the body of Simulation::step()'s hot path
+// (Simulation.hpp:67-75 -> iterate :116-164 -> attract :176-214 -> Quadtree::acc, Quadtree.hpp:113-155):
+// per step, force accumulation on the current positions, then kick-drift.  The reference's
+// std::async fan-out over target chunks (Simulation.hpp:190-213) becomes (a) a grid of CTAs per GPU
+// and (b) a shard of targets per GPU with an NCCL allgather of the new positions each step,
+// overlapped with the force pass over the locally-owned sources.
+#include "../../include/nbody_gpu.h"
+#include "kernels.h"
+#include "nccl_dyn.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace nb;
+
+namespace {
+
+thread_local char g_init_err[512] = "";
+
+struct Range {          // one force launch of the per-step plan
+    int j_blk0, j_nblk; // source blocks
+    int splits, slot0;
+    bool remote;        // needs the allgather of the previous step to have landed
+};
+
+struct Dev {
+    int device = 0;
+    int rank = 0;                 // global rank of this GPU
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev_integrated = nullptr, ev_gathered = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *posm[2] = {nullptr, nullptr};
+    void *vel = nullptr, *acc = nullptr, *accp = nullptr, *aos = nullptr;
+    double *energy5 = nullptr;
+    ncclComm_t comm = nullptr;
+    size_t shard_start = 0, shard_count = 0; // bodies (padded index space)
+    int cur = 0;
+    bool gathered_pending = false;           // an allgather into posm[cur] may still be in flight
+    std::vector<Range> plan;
+    int nslots = 0;
+    bool fused = false;
+    int force_ctas = 0;
+};
+
+} // namespace
+
+struct nbody_ctx {
+    nbody_params p;
+    size_t n = 0, n_padded = 0;
+    int world = 1;               // total GPUs
+    bool f64 = false;
+    size_t esz = 4;
+    std::vector<Dev> devs;
+    nbody_body_t *h_stage = nullptr; // pinned, n records (download merges / uploads)
+    int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0;
+    unsigned long long launches = 0, interactions = 0;
+    int profile_next = 0;
+    float last_force_ms = 0.f, last_integ_ms = 0.f;
+    char err[512];
+    nbody_ctx() { err[0] = 0; }
+};
+
+namespace {
+
+void set_err(nbody_ctx *c, const char *fmt, ...)
+{
+    char *dst = c ? c->err : g_init_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+}
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_err(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return e_ == cudaErrorMemoryAllocation ? NBODY_ENOMEM : NBODY_ECUDA;               \
+        }                                                                                      \
+    } while (0)
+#define NC(call)                                                                               \
+    do {                                                                                       \
+        int r_ = (call);                                                                       \
+        if (r_ != 0) {                                                                         \
+            set_err(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl().GetErrorString(r_)); \
+            return NBODY_ENCCL;                                                                \
+        }                                                                                      \
+    } while (0)
+
+IntegParams make_ip(const nbody_ctx *c, float dt)
+{
+    IntegParams ip;
+    ip.dt = dt;
+    ip.G = c->p.G;
+    ip.flags = c->p.integ_flags;
+    ip.max_velocity = c->p.max_velocity;
+    ip.max_velocity_sq = c->p.max_velocity * c->p.max_velocity;
+    ip.soft_boundary = c->p.boundary_radius * c->p.soft_boundary;
+    ip.soft_boundary_sq = ip.soft_boundary * ip.soft_boundary;
+    ip.boundary_force = c->p.boundary_force;
+    ip.damping = c->p.damping;
+    return ip;
+}
+
+// Choose the number of source-range splits so that the CTAs of one launch fill whole waves of
+// the GPU (slots = SMs x resident CTAs per SM): wave-quantisation efficiency
+//   eff(S) = units / (ceil(units/slots) * slots),  units = target_tiles * S.
+// Prefer the smallest S within 1 % of the best; each chunk keeps >= min_chunk_blks source blocks.
+int choose_splits(int tiles, int j_nblk, int slots, int min_chunk_blks, int max_splits)
+{
+    if (tiles <= 0 || slots <= 0) return 1;
+    int smax = std::max(1, std::min(max_splits, j_nblk / std::max(1, min_chunk_blks)));
+    double best = -1.0;
+    int best_s = 1;
+    for (int s = 1; s <= smax; ++s) {
+        const long long units = (long long)tiles * s;
+        const long long waves = (units + slots - 1) / slots;
+        double eff = (double)units / (double)(waves * slots);
+        // a launch of very few waves also suffers the imbalance of a dynamic tail: favour >= 4 waves
+        if (waves < 4) eff *= 0.97;
+        if (eff > best + 0.01) { best = eff; best_s = s; }
+    }
+    return best_s;
+}
+
+int plan_device(nbody_ctx *c, Dev &d)
+{
+    const int nblk = (int)(c->n_padded / BLK);
+    const int ib0 = (int)(d.shard_start / BLK), ibn = (int)(d.shard_count / BLK);
+    const bool refc = !c->f64 && c->p.rsqrt_mode == NBODY_RSQRT_REFCOMPAT;
+    d.plan.clear();
+    d.fused = false;
+    int tiles, slots, min_chunk;
+    if (c->f64) { tiles = ibn / F64_TILE_BLKS; slots = c->sm_count * 4; min_chunk = 4; }
+    else if (refc) { tiles = ibn * 2; slots = c->sm_count * 4; min_chunk = 1; }
+    else { tiles = ibn / FAST_TILE_BLKS; slots = c->sm_count * std::max(1, c->ctas_per_sm); min_chunk = 8; }
+
+    struct Seg { int b0, nb; bool remote; };
+    std::vector<Seg> segs;
+    if (c->world == 1 || refc) {
+        segs.push_back({0, nblk, c->world > 1});
+    } else {
+        segs.push_back({ib0, ibn, false});                        // locally owned sources first
+        if (ib0 > 0) segs.push_back({0, ib0, true});
+        if (ib0 + ibn < nblk) segs.push_back({ib0 + ibn, nblk - ib0 - ibn, true});
+    }
+    int slot = 0;
+    for (const Seg &s : segs) {
+        int S = 1;
+        if (!refc) {
+            if (c->p.j_splits > 0) S = std::min(c->p.j_splits, s.nb);
+            else S = choose_splits(tiles, s.nb, slots, min_chunk, 64);
+        }
+        d.plan.push_back({s.b0, s.nb, S, slot, s.remote});
+        slot += S;
+    }
+    d.nslots = slot;
+    if (!c->f64 && !refc && c->world == 1 && d.plan.size() == 1 && d.plan[0].splits == 1) {
+        d.fused = (c->p.fuse_integrator != 0);
+    }
+    if (c->p.fuse_integrator == 1 && !(d.plan.size() == 1 && d.plan[0].splits == 1 && !c->f64 && !refc)) {
+        // explicit request that cannot be honoured with this plan: fall back to separate kernels
+        d.fused = false;
+    }
+    d.force_ctas = 0;
+    for (const Range &r : d.plan) d.force_ctas += tiles * r.splits;
+    return NBODY_OK;
+}
+
+int alloc_device(nbody_ctx *ctx, Dev &d)
+{
+    CU(cudaSetDevice(d.device));
+    const size_t esz = ctx->esz;
+    const size_t full = ctx->n_padded * 4 * esz, shard = d.shard_count * 4 * esz;
+    if (d.own_stream) CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    if (ctx->world > 1) CU(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&d.ev_integrated, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&d.ev_gathered, cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&d.ev_t[k]));
+    CU(cudaMalloc(&d.posm[0], full));
+    CU(cudaMalloc(&d.posm[1], full));
+    CU(cudaMalloc(&d.vel, shard));
+    CU(cudaMalloc(&d.acc, shard));
+    CU(cudaMalloc(&d.accp, shard * (size_t)std::max(1, d.nslots)));
+    CU(cudaMalloc(&d.aos, ctx->n_padded * sizeof(nbody_body_t)));
+    CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
+    return NBODY_OK;
+}
+
+int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies)
+{
+    for (Dev &d : ctx->devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaMemcpyAsync(d.aos, bodies, ctx->n * sizeof(nbody_body_t), cudaMemcpyHostToDevice, d.stream));
+        d.cur = 0;
+        CU(launch_pack(d.aos, ctx->n, ctx->n_padded, d.shard_start, d.shard_count, d.posm[0], d.vel,
+                       d.acc, ctx->f64, d.stream));
+        ctx->launches++;
+        // padding must also be valid in the other buffer (masses are copied by the integrator only
+        // for the shard's own blocks, so seed both buffers with the full packed state)
+        CU(cudaMemcpyAsync(d.posm[1], d.posm[0], ctx->n_padded * 4 * ctx->esz, cudaMemcpyDeviceToDevice, d.stream));
+        d.gathered_pending = false;
+    }
+    for (Dev &d : ctx->devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.stream)); // `bodies` may be pageable and reused by the caller
+    }
+    return NBODY_OK;
+}
+
+ForceLaunch make_force(const nbody_ctx *c, const Dev &d, const Range &r, float dt)
+{
+    ForceLaunch L;
+    memset(&L, 0, sizeof L);
+    L.posm = d.posm[d.cur];
+    L.accp = d.accp;
+    L.i_blk0 = (int)(d.shard_start / BLK);
+    L.i_blk_local0 = 0;
+    L.n_iblk = (int)(d.shard_count / BLK);
+    L.n_iblk_shard = L.n_iblk;
+    L.j_blk0 = r.j_blk0;
+    L.j_nblk = r.j_nblk;
+    L.j_body_limit = (long long)c->n;
+    L.splits = r.splits;
+    L.slot0 = r.slot0;
+    L.eps2 = c->p.eps * c->p.eps;                       // Quadtree ctor: e_sq = eps*eps in fp32
+    L.eps2_f64 = (double)c->p.eps * (double)c->p.eps;
+    L.fuse = 0;
+    L.posm_next = d.posm[d.cur ^ 1];
+    L.vel = d.vel;
+    L.acc = d.acc;
+    L.ip = make_ip(c, dt);
+    return L;
+}
+
+// Enqueue one force evaluation (+ integration unless acc_only) on every local GPU.
+int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
+{
+    const bool refc = !ctx->f64 && ctx->p.rsqrt_mode == NBODY_RSQRT_REFCOMPAT;
+    const bool guard = (ctx->p.eps == 0.0f);
+    for (Dev &d : ctx->devs) {
+        CU(cudaSetDevice(d.device));
+        const bool prof = profile && (&d == &ctx->devs[0]);
+        if (prof) CU(cudaEventRecord(d.ev_t[0], d.stream));
+        bool waited = false;
+        for (const Range &r : d.plan) {
+            if (r.remote && d.gathered_pending && !waited) {
+                CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0));
+                waited = true;
+            }
+            ForceLaunch L = make_force(ctx, d, r, dt);
+            cudaError_t e;
+            if (ctx->f64) e = launch_force_f64(L, d.stream);
+            else if (refc) e = launch_force_f32_refcompat(L, d.stream);
+            else {
+                L.fuse = (d.fused && !acc_only) ? 1 : 0;
+                e = launch_force_f32_fast(L, guard, d.stream);
+            }
+            CU(e);
+            ctx->launches++;
+        }
+        if (d.gathered_pending && !waited) { // local-only plan cannot happen with world>1, but be safe
+            CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0));
+        }
+        if (prof) CU(cudaEventRecord(d.ev_t[1], d.stream));
+        const bool fused_now = d.fused && !acc_only && !ctx->f64 && !refc;
+        if (!fused_now) {
+            IntegLaunch I;
+            memset(&I, 0, sizeof I);
+            I.posm_cur = d.posm[d.cur];
+            I.posm_next = d.posm[d.cur ^ 1];
+            I.vel = d.vel;
+            I.acc = d.acc;
+            I.accp = d.accp;
+            I.nslots = d.nslots;
+            I.i_blk0 = (int)(d.shard_start / BLK);
+            I.n_iblk_shard = (int)(d.shard_count / BLK);
+            I.acc_only = acc_only ? 1 : 0;
+            I.n_real = (long long)ctx->n;
+            I.ip = make_ip(ctx, dt);
+            if (d.fused && acc_only) {
+                // fused plans own no partial slot buffer semantics beyond slot 0: the non-fused
+                // force launch above wrote slot 0.
+                I.nslots = 1;
+            }
+            CU(ctx->f64 ? launch_integrate_f64(I, d.stream) : launch_integrate_f32(I, d.stream));
+            ctx->launches++;
+        }
+        if (prof) CU(cudaEventRecord(d.ev_t[2], d.stream));
+        if (!acc_only) {
+            size_t real = 0;
+            if (d.shard_start < ctx->n) real = std::min(ctx->n - d.shard_start, d.shard_count);
+            ctx->interactions += (unsigned long long)real * (unsigned long long)ctx->n;
+        }
+    }
+    if (acc_only) return NBODY_OK;
+
+    if (ctx->world > 1) {
+        // new positions of every shard -> every GPU, in place in the next buffer, on the comm stream
+        for (Dev &d : ctx->devs) {
+            CU(cudaSetDevice(d.device));
+            CU(cudaEventRecord(d.ev_integrated, d.stream));
+            CU(cudaStreamWaitEvent(d.comm_stream, d.ev_integrated, 0));
+        }
+        NC(nccl().GroupStart());
+        for (Dev &d : ctx->devs) {
+            const size_t bytes = d.shard_count * 4 * ctx->esz;
+            char *base = (char *)d.posm[d.cur ^ 1];
+            int r = nccl().AllGather(base + (size_t)d.rank * bytes, base, bytes, NCCL_UINT8, d.comm, d.comm_stream);
+            if (r != 0) { nccl().GroupEnd(); NC(r); }
+        }
+        NC(nccl().GroupEnd());
+        for (Dev &d : ctx->devs) {
+            CU(cudaSetDevice(d.device));
+            CU(cudaEventRecord(d.ev_gathered, d.comm_stream));
+            d.gathered_pending = true;
+        }
+    }
+    for (Dev &d : ctx->devs) d.cur ^= 1;
+    return NBODY_OK;
+}
+
+int sync_all(nbody_ctx *ctx)
+{
+    for (Dev &d : ctx->devs) {
+        CU(cudaSetDevice(d.device));
+        if (d.comm_stream) CU(cudaStreamSynchronize(d.comm_stream));
+        CU(cudaStreamSynchronize(d.stream));
+        d.gathered_pending = false;
+    }
+    return NBODY_OK;
+}
+
+void free_all(nbody_ctx *c)
+{
+    for (Dev &d : c->devs) {
+        cudaSetDevice(d.device);
+        if (d.comm && nccl().CommDestroy) nccl().CommDestroy(d.comm);
+        for (int k = 0; k < 2; ++k) if (d.posm[k]) cudaFree(d.posm[k]);
+        if (d.vel) cudaFree(d.vel);
+        if (d.acc) cudaFree(d.acc);
+        if (d.accp) cudaFree(d.accp);
+        if (d.aos) cudaFree(d.aos);
+        if (d.energy5) cudaFree(d.energy5);
+        if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
+        if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
+        for (int k = 0; k < 4; ++k) if (d.ev_t[k]) cudaEventDestroy(d.ev_t[k]);
+        if (d.comm_stream) cudaStreamDestroy(d.comm_stream);
+        if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    delete c;
+}
+
+} // namespace
+
+// ================================================================================================
+extern "C" {
+
+void nbody_params_default(nbody_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->struct_size = (uint32_t)sizeof *p;
+    p->dims = 2;                    // the reference is 2-D (Vec2.hpp:17-20)
+    p->eps = 1.0f;                  // Simulation.hpp:59
+    p->G = 1.0f;
+    p->precision = NBODY_PRECISION_F32;
+    p->rsqrt_mode = NBODY_RSQRT_FAST;
+    p->force_algo = NBODY_FORCE_ALLPAIRS;
+    p->theta = 1.0f;                // Simulation.hpp:59
+    p->integ_flags = 0;
+    p->max_velocity = 1000.0f;      // Simulation.hpp:124
+    p->boundary_radius = 100000.0f; // :120
+    p->soft_boundary = 0.8f;        // :121
+    p->boundary_force = 0.9f;       // :122
+    p->damping = 0.9995f;           // :123
+    p->j_splits = 0;
+    p->fuse_integrator = -1;
+    p->use_graph = -1;
+    p->ngpus = 1;
+    p->world = 1;
+    p->rank = 0;
+    p->stream = nullptr;
+}
+
+int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *bodies, size_t n)
+{
+    nbody_ctx *ctx = nullptr; // for the CU/NC macros before the context exists
+    if (!out) return NBODY_EINVAL;
+    *out = nullptr;
+    if (!p || !bodies || n == 0 || p->struct_size != sizeof(nbody_params)) {
+        set_err(nullptr, "nbody_gpu_init: null argument, n == 0 or nbody_params size mismatch");
+        return NBODY_EINVAL;
+    }
+    if ((p->dims != 2 && p->dims != 3) || !(p->eps >= 0.0f) ||
+        (p->precision != NBODY_PRECISION_F32 && p->precision != NBODY_PRECISION_F64) ||
+        (p->rsqrt_mode != NBODY_RSQRT_FAST && p->rsqrt_mode != NBODY_RSQRT_REFCOMPAT) ||
+        p->ngpus > NBODY_MAX_GPUS || n > ((size_t)1 << 30)) {
+        set_err(nullptr, "nbody_gpu_init: invalid parameter");
+        return NBODY_EINVAL;
+    }
+    if (p->force_algo != NBODY_FORCE_ALLPAIRS) {
+        set_err(nullptr, "nbody_gpu_init: force_algo %d not available in this build", p->force_algo);
+        return NBODY_EINVAL;
+    }
+    const int nlocal = std::max(1, p->ngpus);
+    const bool multiproc = p->world > 1;
+    if (multiproc && nlocal > 1) {
+        set_err(nullptr, "nbody_gpu_init: use either ngpus>1 (one process) or world>1 (one process per GPU)");
+        return NBODY_EINVAL;
+    }
+    const int world = multiproc ? p->world : nlocal;
+    if (multiproc && (p->rank < 0 || p->rank >= p->world)) return NBODY_EINVAL;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_err(nullptr, "nbody_gpu_init: no CUDA device visible");
+        return NBODY_ENODEV;
+    }
+    ctx = new (std::nothrow) nbody_ctx();
+    if (!ctx) return NBODY_ENOMEM;
+    ctx->p = *p;
+    ctx->n = n;
+    ctx->world = world;
+    ctx->f64 = (p->precision == NBODY_PRECISION_F64);
+    ctx->esz = ctx->f64 ? 8 : 4;
+    {
+        const size_t per = (size_t)TARGET_GRANULE * (size_t)world;
+        ctx->n_padded = ((n + per - 1) / per) * per;
+    }
+    int rc = NBODY_OK;
+    auto fail = [&](int code) {
+        memcpy(g_init_err, ctx->err, sizeof g_init_err);
+        free_all(ctx);
+        return code;
+    };
+
+    ctx->devs.resize(nlocal);
+    for (int k = 0; k < nlocal; ++k) {
+        Dev &d = ctx->devs[k];
+        d.device = p->device_ids[k];
+        if (d.device < 0 || d.device >= ndev) {
+            set_err(ctx, "nbody_gpu_init: device ordinal %d out of range (0..%d)", d.device, ndev - 1);
+            return fail(NBODY_ENODEV);
+        }
+        d.rank = multiproc ? p->rank : k;
+        d.shard_count = ctx->n_padded / (size_t)world;
+        d.shard_start = d.shard_count * (size_t)d.rank;
+        if (p->stream && nlocal == 1) { d.stream = (cudaStream_t)p->stream; d.own_stream = false; }
+    }
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->devs[0].device) != cudaSuccess) {
+            set_err(ctx, "cudaGetDeviceProperties failed");
+            return fail(NBODY_ECUDA);
+        }
+        if (prop.major < 10) {
+            set_err(ctx, "device %d is sm_%d%d; this library contains sm_100a code only", ctx->devs[0].device,
+                    prop.major, prop.minor);
+            return fail(NBODY_ENODEV);
+        }
+        ctx->sm_count = prop.multiProcessorCount;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->devs[0].device);
+        ctx->sm_clock_khz = khz;
+        cudaSetDevice(ctx->devs[0].device);
+        ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(false);
+    }
+    for (Dev &d : ctx->devs) {
+        if ((rc = plan_device(ctx, d)) != NBODY_OK) return fail(rc);
+        if ((rc = alloc_device(ctx, d)) != NBODY_OK) return fail(rc);
+    }
+    if (cudaMallocHost(&ctx->h_stage, ctx->n * sizeof(nbody_body_t)) != cudaSuccess) {
+        set_err(ctx, "cudaMallocHost(%zu) failed", ctx->n * sizeof(nbody_body_t));
+        return fail(NBODY_ENOMEM);
+    }
+    if (world > 1) {
+        if (!nccl().load()) {
+            set_err(ctx, "libnccl.so.2 could not be loaded: %s", dlerror());
+            return fail(NBODY_ENCCL);
+        }
+        if (multiproc) {
+            ncclUniqueId id;
+            memcpy(&id, p->nccl_id, sizeof id);
+            cudaSetDevice(ctx->devs[0].device);
+            int r = nccl().CommInitRank(&ctx->devs[0].comm, world, id, p->rank);
+            if (r != 0) { set_err(ctx, "ncclCommInitRank: %s", nccl().GetErrorString(r)); return fail(NBODY_ENCCL); }
+        } else {
+            std::vector<ncclComm_t> comms(nlocal);
+            std::vector<int> ids(nlocal);
+            for (int k = 0; k < nlocal; ++k) ids[k] = ctx->devs[k].device;
+            int r = nccl().CommInitAll(comms.data(), nlocal, ids.data());
+            if (r != 0) { set_err(ctx, "ncclCommInitAll: %s", nccl().GetErrorString(r)); return fail(NBODY_ENCCL); }
+            for (int k = 0; k < nlocal; ++k) ctx->devs[k].comm = comms[k];
+        }
+    }
+    if ((rc = upload_state(ctx, bodies)) != NBODY_OK) return fail(rc);
+    *out = ctx;
+    return NBODY_OK;
+}
+
+int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
+{
+    if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
+    for (int s = 0; s < nsteps; ++s) {
+        const bool prof = ctx->profile_next && s == 0;
+        int rc = enqueue_step(ctx, dt, false, prof);
+        if (rc != NBODY_OK) return rc;
+        if (prof) {
+            Dev &d = ctx->devs[0];
+            CU(cudaSetDevice(d.device));
+            CU(cudaEventSynchronize(d.ev_t[2]));
+            CU(cudaEventElapsedTime(&ctx->last_force_ms, d.ev_t[0], d.ev_t[1]));
+            CU(cudaEventElapsedTime(&ctx->last_integ_ms, d.ev_t[1], d.ev_t[2]));
+            ctx->profile_next = 0;
+        }
+    }
+    return NBODY_OK;
+}
+
+int nbody_gpu_accel_only(nbody_ctx *ctx)
+{
+    if (!ctx) return NBODY_EINVAL;
+    return enqueue_step(ctx, 0.0f, true, false);
+}
+
+int nbody_gpu_sync(nbody_ctx *ctx)
+{
+    if (!ctx) return NBODY_EINVAL;
+    return sync_all(ctx);
+}
+
+int nbody_gpu_download(nbody_ctx *ctx, nbody_body_t *bodies, size_t n, unsigned fields)
+{
+    if (!ctx || !bodies || n != ctx->n || (fields & ~NBODY_FIELD_ALL) || fields == 0) return NBODY_EINVAL;
+    int rc = sync_all(ctx);
+    if (rc != NBODY_OK) return rc;
+    for (Dev &d : ctx->devs) {
+        if (d.shard_start >= ctx->n) continue;
+        const size_t cnt = std::min(ctx->n - d.shard_start, d.shard_count);
+        CU(cudaSetDevice(d.device));
+        CU(launch_unpack(d.aos, ctx->n, d.shard_start, d.shard_count, d.posm[d.cur], d.vel, d.acc, ctx->f64, d.stream));
+        ctx->launches++;
+        nbody_body_t *dst = (fields == NBODY_FIELD_ALL) ? bodies + d.shard_start : ctx->h_stage + d.shard_start;
+        CU(cudaMemcpyAsync(dst, d.aos, cnt * sizeof(nbody_body_t), cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (Dev &d : ctx->devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    if (fields != NBODY_FIELD_ALL) {
+        const bool z = ctx->p.dims == 3;
+        for (Dev &d : ctx->devs) {
+            if (d.shard_start >= ctx->n) continue;
+            const size_t i1 = std::min(ctx->n, d.shard_start + d.shard_count);
+            for (size_t i = d.shard_start; i < i1; ++i) {
+                const nbody_body_t &s = ctx->h_stage[i];
+                nbody_body_t &t = bodies[i];
+                if (fields & NBODY_FIELD_POS) { t.pos[0] = s.pos[0]; t.pos[1] = s.pos[1]; if (z) t.pos_z = s.pos_z; }
+                if (fields & NBODY_FIELD_VEL) { t.vel[0] = s.vel[0]; t.vel[1] = s.vel[1]; if (z) t.vel_z = s.vel_z; }
+                if (fields & NBODY_FIELD_ACC) { t.acc[0] = s.acc[0]; t.acc[1] = s.acc[1]; if (z) t.acc_z = s.acc_z; }
+            }
+        }
+    }
+    return NBODY_OK;
+}
+
+int nbody_gpu_upload(nbody_ctx *ctx, const nbody_body_t *bodies, size_t n)
+{
+    if (!ctx || !bodies || n != ctx->n) return NBODY_EINVAL;
+    int rc = sync_all(ctx);
+    if (rc != NBODY_OK) return rc;
+    return upload_state(ctx, bodies);
+}
+
+int nbody_gpu_download_f64(nbody_ctx *ctx, double *pos3, double *vel3, double *acc3, size_t n)
+{
+    if (!ctx || n != ctx->n) return NBODY_EINVAL;
+    int rc = sync_all(ctx);
+    if (rc != NBODY_OK) return rc;
+    for (Dev &d : ctx->devs) {
+        if (d.shard_start >= ctx->n) continue;
+        const size_t cnt = std::min(ctx->n - d.shard_start, d.shard_count);
+        CU(cudaSetDevice(d.device));
+        // reuse the AoS staging area (64 B/body >= 3 x 24 B/body? no: 72 B) -> separate scratch
+        double *scratch = nullptr;
+        CU(cudaMalloc(&scratch, cnt * 9 * sizeof(double)));
+        double *dp = scratch, *dv = scratch + 3 * cnt, *da = scratch + 6 * cnt;
+        cudaError_t e = launch_unpack_f64(pos3 ? dp : nullptr, vel3 ? dv : nullptr, acc3 ? da : nullptr, ctx->n,
+                                          d.shard_start, d.shard_count, d.posm[d.cur], d.vel, d.acc, ctx->f64, d.stream);
+        ctx->launches++;
+        if (e == cudaSuccess && pos3) e = cudaMemcpyAsync(pos3 + 3 * d.shard_start, dp, cnt * 24, cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess && vel3) e = cudaMemcpyAsync(vel3 + 3 * d.shard_start, dv, cnt * 24, cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess && acc3) e = cudaMemcpyAsync(acc3 + 3 * d.shard_start, da, cnt * 24, cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+        cudaFree(scratch);
+        CU(e);
+    }
+    return NBODY_OK;
+}
+
+int nbody_gpu_energy(nbody_ctx *ctx, double *K, double *W, double P[3])
+{
+    if (!ctx) return NBODY_EINVAL;
+    int rc = sync_all(ctx);
+    if (rc != NBODY_OK) return rc;
+    const double eps2 = (double)ctx->p.eps * (double)ctx->p.eps;
+    for (Dev &d : ctx->devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaMemsetAsync(d.energy5, 0, 5 * sizeof(double), d.stream));
+        CU(launch_energy(d.posm[d.cur], d.vel, ctx->n_padded, d.shard_start, d.shard_count, eps2, ctx->f64, d.energy5, d.stream));
+        ctx->launches++;
+    }
+    if (ctx->p.world > 1) { // one process per GPU: sum over ranks on the device
+        Dev &d = ctx->devs[0];
+        CU(cudaSetDevice(d.device));
+        NC(nccl().AllReduce(d.energy5, d.energy5, 5, NCCL_FLOAT64, NCCL_SUM, d.comm, d.stream));
+    }
+    double tot[5] = {0, 0, 0, 0, 0};
+    for (Dev &d : ctx->devs) {
+        double h[5];
+        CU(cudaSetDevice(d.device));
+        CU(cudaMemcpyAsync(h, d.energy5, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        for (int k = 0; k < 5; ++k) tot[k] += h[k];
+    }
+    const double G = (double)ctx->p.G;
+    if (K) *K = tot[0];
+    if (W) *W = 0.5 * G * tot[1];
+    if (P) { P[0] = tot[2]; P[1] = tot[3]; P[2] = tot[4]; }
+    return NBODY_OK;
+}
+
+int nbody_gpu_profile_next_step(nbody_ctx *ctx, int enable)
+{
+    if (!ctx) return NBODY_EINVAL;
+    ctx->profile_next = enable ? 1 : 0;
+    return NBODY_OK;
+}
+
+int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
+{
+    if (!ctx || !info) return NBODY_EINVAL;
+    memset(info, 0, sizeof *info);
+    const Dev &d0 = ctx->devs.front(), &dl = ctx->devs.back();
+    info->n = ctx->n;
+    info->n_padded = ctx->n_padded;
+    info->shard_start = d0.shard_start;
+    info->shard_count = dl.shard_start + dl.shard_count - d0.shard_start;
+    info->world = ctx->world;
+    info->rank = d0.rank;
+    info->ngpus_local = (int)ctx->devs.size();
+    info->sm_count = ctx->sm_count;
+    info->sm_clock_khz = ctx->sm_clock_khz;
+    info->j_splits = d0.plan.empty() ? 0 : d0.plan[0].splits;
+    info->force_ctas = d0.force_ctas;
+    info->ctas_per_sm = ctx->ctas_per_sm;
+    info->fused = d0.fused ? 1 : 0;
+    info->graph = 0;
+    info->kernel_launches = ctx->launches;
+    info->interactions = ctx->interactions;
+    info->last_force_ms = ctx->last_force_ms;
+    info->last_integ_ms = ctx->last_integ_ms;
+    return NBODY_OK;
+}
+
+int nbody_gpu_nccl_unique_id(uint8_t id[NBODY_NCCL_ID_BYTES])
+{
+    if (!id) return NBODY_EINVAL;
+    if (!nccl().load()) { set_err(nullptr, "libnccl.so.2 could not be loaded"); return NBODY_ENCCL; }
+    ncclUniqueId u;
+    if (nccl().GetUniqueId(&u) != 0) return NBODY_ENCCL;
+    memcpy(id, &u, NBODY_NCCL_ID_BYTES);
+    return NBODY_OK;
+}
+
+void nbody_gpu_shutdown(nbody_ctx *ctx)
+{
+    if (!ctx) return;
+    for (Dev &d : ctx->devs) {
+        cudaSetDevice(d.device);
+        if (d.comm_stream) cudaStreamSynchronize(d.comm_stream);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+    }
+    free_all(ctx);
+}
+
+const char *nbody_gpu_strerror(int code)
+{
+    switch (code) {
+    case NBODY_OK: return "ok";
+    case NBODY_EINVAL: return "invalid argument";
+    case NBODY_ECUDA: return "CUDA error";
+    case NBODY_ENOMEM: return "out of memory";
+    case NBODY_ENCCL: return "NCCL error";
+    case NBODY_ENODEV: return "no usable sm_100 device";
+    case NBODY_ESTATE: return "invalid state";
+    default: return "unknown error";
+    }
+}
+
+const char *nbody_gpu_last_error(const nbody_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
+
+const char *nbody_gpu_version(void) { return "nbody_gpu 0.1 (sm_100a; all-pairs f32 fast/refcompat, f64)"; }
+
+} // extern "C"
