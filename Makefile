@@ -6,7 +6,7 @@ ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude
 CSRC    := nbodysim_b200/csrc
 CU      := $(CSRC)/nbody_gpu.cu $(CSRC)/force_f32.cu $(CSRC)/force_f64.cu $(CSRC)/layout.cu
-HDR     := $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/nccl_dyn.h include/nbody_gpu.h include/nbody_body.h
+HDR     := $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/force_f32_fast.cuh $(CSRC)/nccl_dyn.h include/nbody_gpu.h include/nbody_body.h
 OBJ     := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(CU))
 
 all: lib host oracle
@@ -29,7 +29,16 @@ host/_build/nbody_run: host/nbody_main.c host/nbody_ic.c include/nbody_host.h in
 oracle:
 	$(MAKE) -C oracle all
 
+# tuning / microbenchmark harnesses (not part of the product path)
+tools: build/kbench build/ubench
+build/kbench: tools/kbench.cu $(HDR)
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -o $@ $<
+build/ubench: tools/ubench.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -o $@ $<
+
 clean:
 	rm -rf build/obj nbodysim_b200/*.so host/_build
 	$(MAKE) -C oracle clean
-.PHONY: all lib host oracle clean
+.PHONY: all lib host oracle tools clean

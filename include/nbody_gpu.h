@@ -74,6 +74,10 @@ typedef struct nbody_params {
     int32_t  j_splits;        /* 0 = auto; >0 forces the number of source-range splits */
     int32_t  fuse_integrator; /* -1 = auto; 0/1 = separate / fused kick-drift epilogue */
     int32_t  use_graph;       /* -1 = auto; capture multi-step calls in a CUDA graph */
+    int32_t  force_variant;   /* fast fp32 kernel: -1 = auto, 0 = always the general-mass form (12 fp32
+                                 lane-ops per interaction).  auto uses the uniform-mass form (11 lane-ops;
+                                 m factored out of the sum, same per-pair arithmetic otherwise) when
+                                 every body has the same mass. */
     /* --- single-process multi-GPU (C driver): ngpus devices, NCCL comms created internally --- */
     int32_t  ngpus;           /* 0 or 1 = single GPU */
     int32_t  device_ids[NBODY_MAX_GPUS]; /* CUDA ordinals; device_ids[0] is used when ngpus<=1 */
@@ -96,6 +100,7 @@ typedef struct nbody_info {
     int32_t  force_ctas;      /* CTAs per force launch (per GPU) */
     int32_t  ctas_per_sm;     /* resident force CTAs per SM (occupancy query) */
     int32_t  fused;           /* 1 if the kick-drift runs in the force kernel's epilogue */
+    int32_t  uniform_mass;    /* 1 if the fast kernel runs the uniform-mass (11-op) form */
     int32_t  graph;           /* 1 if multi-step calls replay a CUDA graph */
     uint64_t kernel_launches; /* kernels of this library launched so far (all local GPUs) */
     uint64_t interactions;    /* pair interactions evaluated so far by this process */

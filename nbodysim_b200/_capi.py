@@ -42,6 +42,7 @@ class NbodyParams(C.Structure):
         ("j_splits", C.c_int32),
         ("fuse_integrator", C.c_int32),
         ("use_graph", C.c_int32),
+        ("force_variant", C.c_int32),
         ("ngpus", C.c_int32),
         ("device_ids", C.c_int32 * NBODY_MAX_GPUS),
         ("world", C.c_int32),
@@ -66,6 +67,7 @@ class NbodyInfo(C.Structure):
         ("force_ctas", C.c_int32),
         ("ctas_per_sm", C.c_int32),
         ("fused", C.c_int32),
+        ("uniform_mass", C.c_int32),
         ("graph", C.c_int32),
         ("kernel_launches", C.c_uint64),
         ("interactions", C.c_uint64),

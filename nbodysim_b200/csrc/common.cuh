@@ -20,6 +20,7 @@ namespace nb {
 // ---------------------------------------------------------------------------------------------
 constexpr int BLK = 256;                 // bodies per block
 constexpr int BLK_ELEMS = 4 * BLK;       // scalars per block
+constexpr float PAD_POS = 1.0e18f;       // coordinates of the zero-mass padding bodies
 
 __host__ __device__ inline size_t blk_index(size_t body, int comp)
 {

@@ -4,236 +4,28 @@
 // Quadtree::fast_inv_sqrt (Quadtree.hpp:106-111), driven over all targets as Simulation::attract
 // does (Simulation.hpp:203-207).  Two variants:
 //
-//  * force_f32_fast_kernel      headline path.  256 threads, 4 target bodies per thread held in
-//    registers; source tiles (blocked SoA, 8 KiB per stage) are staged into shared memory by 1-D
-//    TMA bulk copies (cp.async.bulk + mbarrier full/empty ring, 4 stages); the inner loop runs on
-//    Blackwell's packed-fp32 instructions (FADD2/FFMA2/FMUL2: two sources per issue slot) with
-//    one MUFU.RSQ per interaction -- 12 fp32-pipe lane-ops + 1 MUFU per interaction and ~0.6 issue
-//    slots per lane-op, so the FP32 datapath, not the issue port, is the limiter.  No tensor
-//    cores: this is not a dense contraction.
-//  * force_f32_refcompat_kernel parity path.  Bit-faithful restatement: unfused IEEE mul/add in
+//  * force_f32_fast_kernel (force_f32_fast.cuh)  headline path.  256 threads, 8 target bodies per
+//    thread held in registers, one CTA per SM; source tiles (blocked SoA, 8 KiB per stage) are
+//    staged into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier full/empty ring,
+//    4 stages); the inner loop runs on Blackwell's packed-fp32 instructions (FADD2/FFMA2/FMUL2:
+//    two sources per issue slot) with one MUFU.RSQ per interaction: 12 fp32-pipe lane-ops per
+//    interaction in general, 11 when all massive bodies share one mass (the multiply by m_j then
+//    factors out of the sum -- the "uniform" form, chosen automatically at upload).  Measured on
+//    B200 (tools/ubench.cu, tools/kbench.cu): an FFMA2 occupies the FP32 pipe for 2 cycles (same
+//    datapath peak as FFMA, half the issue slots), an FFMA2 with three distinct register pairs
+//    costs ~2.6 cycles (register-file read bandwidth) and each MUFU.RSQ steals ~1-2 cycles, which
+//    bounds these instruction mixes at ~73 % / ~79 % of the 20-flop FP32 peak.
+//    No tensor cores: this is not a dense contraction.
+//  * force_f32_refcompat_kernel  parity path.  Bit-faithful restatement: unfused IEEE mul/add in
 //    the reference's expression order, the 0x5f3759df bit trick + one Newton step, the r_sq > 0
 //    guard, and accumulation over sources in index order 0..n-1 by a single thread per target,
 //    so accelerations equal the reference's (strict build) bit for bit.
-#include "kernels.h"
+#include "force_f32_fast.cuh"
 
 namespace nb {
 
-constexpr int STAGE_BLKS = 2;                       // source blocks per pipeline stage (512 bodies)
-constexpr int NSTAGE = 4;                           // ring depth
-constexpr int STAGE_FLOATS = STAGE_BLKS * BLK_ELEMS;
-constexpr int STAGE_BYTES = STAGE_FLOATS * 4;       // 8 KiB
-constexpr size_t F32_SMEM = (size_t)NSTAGE * STAGE_BYTES + 2 * NSTAGE * sizeof(uint64_t);
-
-// ---- the one place the integrator arithmetic lives (device side, fp32) -----------------------
-// Body::update (Body.hpp:34-38): vel += acc*dt ; pos += vel*dt, as unfused mul-then-add (two
-// roundings each) exactly like the strict build of the reference; plus the optional extras of
-// Simulation::iterate (Simulation.hpp:129-155).
-__device__ __forceinline__ void integrate_body_f32(float &px, float &py, float &pz, float &vx,
-                                                   float &vy, float &vz, float ax, float ay,
-                                                   float az, const IntegParams &ip)
-{
-    const float dt = ip.dt;
-    vx = __fadd_rn(vx, __fmul_rn(ax, dt));
-    vy = __fadd_rn(vy, __fmul_rn(ay, dt));
-    vz = __fadd_rn(vz, __fmul_rn(az, dt));
-    if (ip.flags & 1u) { // Simulation.hpp:133-137
-        float v2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
-        if (v2 > ip.max_velocity_sq) {
-            float scale = __fdiv_rn(ip.max_velocity, __fsqrt_rn(v2));
-            vx = __fmul_rn(vx, scale);
-            vy = __fmul_rn(vy, scale);
-            vz = __fmul_rn(vz, scale);
-        }
-    }
-    if (ip.flags & 2u) { // Simulation.hpp:142-155
-        float d2 = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
-        if (d2 > ip.soft_boundary_sq) {
-            float dist = __fsqrt_rn(d2);
-            float ratio = __fdiv_rn(dist, ip.soft_boundary);
-            float force = __fmul_rn(ip.boundary_force, expf(__fsub_rn(ratio, 1.0f)));
-            float k = __fdiv_rn(-1.0f, dist);
-            float fd = __fmul_rn(force, dt);
-            vx = __fadd_rn(vx, __fmul_rn(__fmul_rn(px, k), fd));
-            vy = __fadd_rn(vy, __fmul_rn(__fmul_rn(py, k), fd));
-            vz = __fadd_rn(vz, __fmul_rn(__fmul_rn(pz, k), fd));
-            vx = __fmul_rn(vx, ip.damping);
-            vy = __fmul_rn(vy, ip.damping);
-            vz = __fmul_rn(vz, ip.damping);
-        }
-    }
-    px = __fadd_rn(px, __fmul_rn(vx, dt));
-    py = __fadd_rn(py, __fmul_rn(vy, dt));
-    pz = __fadd_rn(pz, __fmul_rn(vz, dt));
-}
-
-// ---- TMA source-tile ring -----------------------------------------------------------------------
-struct Ring {
-    float *stage;        // NSTAGE * STAGE_FLOATS
-    uint64_t *full;      // NSTAGE, tx-count barriers armed by the producer thread
-    uint64_t *empty;     // NSTAGE, one arrival per consumer warp
-};
-
-__device__ __forceinline__ void ring_issue(const Ring &r, const float *src_blocks, int t,
-                                           int chunk_blks)
-{
-    const int s = t % NSTAGE;
-    const int nb = min(STAGE_BLKS, chunk_blks - t * STAGE_BLKS);
-    const uint32_t bytes = (uint32_t)nb * BLK_ELEMS * 4u;
-    mbar_expect_tx(&r.full[s], bytes);
-    tma_bulk_g2s(r.stage + (size_t)s * STAGE_FLOATS,
-                 src_blocks + (size_t)t * STAGE_BLKS * BLK_ELEMS, bytes, &r.full[s]);
-}
-
-__device__ __forceinline__ Ring ring_setup(unsigned char *smem_raw, int nwarps)
-{
-    Ring r;
-    r.stage = reinterpret_cast<float *>(smem_raw);
-    r.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
-    r.empty = r.full + NSTAGE;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&r.full[s], 1);
-            mbar_init(&r.empty[s], nwarps);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    return r;
-}
-
-// ---- fast kernel --------------------------------------------------------------------------------
-// 4 sources (two f32x2 pairs) against this thread's I targets.
-template <int I, bool GUARD>
-__device__ __forceinline__ void interact4(const float4 X, const float4 Y, const float4 Z,
-                                          const float4 M, const float2 (&nxi)[I],
-                                          const float2 (&nyi)[I], const float2 (&nzi)[I],
-                                          float2 (&ax)[I], float2 (&ay)[I], float2 (&az)[I],
-                                          const float2 e2)
-{
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const float2 xj = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
-        const float2 yj = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
-        const float2 zj = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
-        const float2 mj = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
-#pragma unroll
-        for (int k = 0; k < I; ++k) {
-            const float2 dx = __fadd2_rn(xj, nxi[k]);            // r = p_j - p_i   (FADD2)
-            const float2 dy = __fadd2_rn(yj, nyi[k]);
-            const float2 dz = __fadd2_rn(zj, nzi[k]);
-            float2 r2 = __ffma2_rn(dx, dx, e2);                  // r^2 + eps^2     (3 FFMA2)
-            r2 = __ffma2_rn(dy, dy, r2);
-            r2 = __ffma2_rn(dz, dz, r2);
-            float2 ri = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y)); // 2 MUFU.RSQ
-            if (GUARD) { // eps == 0: self / coincident pairs contribute nothing (Quadtree.hpp:139)
-                ri.x = (r2.x > 0.0f) ? ri.x : 0.0f;
-                ri.y = (r2.y > 0.0f) ? ri.y : 0.0f;
-            }
-            const float2 ri2 = __fmul2_rn(ri, ri);
-            const float2 mr = __fmul2_rn(mj, ri);
-            const float2 s = __fmul2_rn(mr, ri2);                // m / (r^2+eps^2)^(3/2)
-            ax[k] = __ffma2_rn(dx, s, ax[k]);                    // acc += r * s    (3 FFMA2)
-            ay[k] = __ffma2_rn(dy, s, ay[k]);
-            az[k] = __ffma2_rn(dz, s, az[k]);
-        }
-    }
-}
-
-template <bool GUARD, bool FUSE>
-__global__ void __launch_bounds__(FAST_THREADS, 2)
-force_f32_fast_kernel(const float *__restrict__ posm, float *__restrict__ accp, int i_blk0,
-                      int i_blk_local0, int n_iblk_shard, int j_blk0, int j_nblk, int splits,
-                      int slot0, float eps2, long long n_real, float *__restrict__ posm_next,
-                      float *__restrict__ vel, float *__restrict__ acc, IntegParams ip)
-{
-    constexpr int I = FAST_I;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const Ring ring = ring_setup(smem_raw, FAST_THREADS / 32);
-
-    const int tile = blockIdx.x / splits;
-    const int split = blockIdx.x - tile * splits;
-    const int tid = threadIdx.x;
-
-    // source chunk of this CTA: whole blocks, balanced to within one block
-    const int jb0 = j_blk0 + (int)(((long long)j_nblk * split) / splits);
-    const int jb1 = j_blk0 + (int)(((long long)j_nblk * (split + 1)) / splits);
-    const int chunk_blks = jb1 - jb0;
-    const int nst = (chunk_blks + STAGE_BLKS - 1) / STAGE_BLKS;
-    const float *src = posm + (size_t)jb0 * BLK_ELEMS;
-
-    if (tid == 0) {
-        const int pre = min(NSTAGE, nst);
-        for (int t = 0; t < pre; ++t) ring_issue(ring, src, t, chunk_blks);
-    }
-
-    // targets: body (tile*I + k)*256 + tid of the launch, k = 0..I-1 -> coalesced block reads.
-    // Keep -p_i broadcast over both packed lanes so that r = p_j + (-p_i) is one FADD2.
-    float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
-#pragma unroll
-    for (int k = 0; k < I; ++k) {
-        const float *b = posm + (size_t)(i_blk0 + tile * I + k) * BLK_ELEMS + tid;
-        const float x = b[0], y = b[BLK], z = b[2 * BLK];
-        nxi[k] = make_float2(-x, -x);
-        nyi[k] = make_float2(-y, -y);
-        nzi[k] = make_float2(-z, -z);
-        ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
-    }
-    const float2 e2 = make_float2(eps2, eps2);
-
-    for (int t = 0; t < nst; ++t) {
-        const int s = t % NSTAGE;
-        mbar_wait(&ring.full[s], (uint32_t)(t / NSTAGE) & 1u);
-        const float *st = ring.stage + (size_t)s * STAGE_FLOATS;
-        const int nb = min(STAGE_BLKS, chunk_blks - t * STAGE_BLKS);
-        for (int b = 0; b < nb; ++b) {
-            const float *sx = st + b * BLK_ELEMS;
-#pragma unroll 2
-            for (int j = 0; j < BLK; j += 4) {
-                const float4 X = *reinterpret_cast<const float4 *>(sx + j);
-                const float4 Y = *reinterpret_cast<const float4 *>(sx + BLK + j);
-                const float4 Z = *reinterpret_cast<const float4 *>(sx + 2 * BLK + j);
-                const float4 M = *reinterpret_cast<const float4 *>(sx + 3 * BLK + j);
-                interact4<I, GUARD>(X, Y, Z, M, nxi, nyi, nzi, ax, ay, az, e2);
-            }
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&ring.empty[s]);
-        // refill the buffer of the PREVIOUS stage (all warps have almost surely left it by now)
-        if (tid == 0 && t >= 1 && (t - 1 + NSTAGE) < nst) {
-            const int tp = t - 1;
-            mbar_wait(&ring.empty[tp % NSTAGE], (uint32_t)(tp / NSTAGE) & 1u);
-            ring_issue(ring, src, tp + NSTAGE, chunk_blks);
-        }
-    }
-
-    // epilogue: fold the two packed lanes (even/odd sources)
-#pragma unroll
-    for (int k = 0; k < I; ++k) {
-        const float fx = ax[k].x + ax[k].y, fy = ay[k].x + ay[k].y, fz = az[k].x + az[k].y;
-        const int lb = i_blk_local0 + tile * I + k; // block inside the shard
-        if (FUSE) {
-            if ((long long)(i_blk0 + tile * I + k) * BLK + tid >= n_real) continue; // padding stays put
-            // fused kick-drift: the new positions go to the other posm buffer, so CTAs still
-            // reading the current one are undisturbed (race-free by construction).
-            const float gx = fx * ip.G, gy = fy * ip.G, gz = fz * ip.G;
-            const float *pb = posm + (size_t)(i_blk0 + tile * I + k) * BLK_ELEMS + tid;
-            float *vb = vel + (size_t)lb * BLK_ELEMS + tid;
-            float *ab = acc + (size_t)lb * BLK_ELEMS + tid;
-            float *nb_ = posm_next + (size_t)(i_blk0 + tile * I + k) * BLK_ELEMS + tid;
-            float px = pb[0], py = pb[BLK], pz = pb[2 * BLK];
-            const float m = pb[3 * BLK];
-            float vx = vb[0], vy = vb[BLK], vz = vb[2 * BLK];
-            integrate_body_f32(px, py, pz, vx, vy, vz, gx, gy, gz, ip);
-            nb_[0] = px; nb_[BLK] = py; nb_[2 * BLK] = pz; nb_[3 * BLK] = m;
-            vb[0] = vx; vb[BLK] = vy; vb[2 * BLK] = vz;
-            ab[0] = gx; ab[BLK] = gy; ab[2 * BLK] = gz;
-        } else {
-            float *o = accp + ((size_t)(slot0 + split) * n_iblk_shard + lb) * BLK_ELEMS + tid;
-            o[0] = fx; o[BLK] = fy; o[2 * BLK] = fz;
-        }
-    }
-}
+using RefRing = Ring<BLK_ELEMS, 2>;
+constexpr int STAGE_BLKS = 2;
 
 // ---- refcompat kernel ---------------------------------------------------------------------------
 // Quadtree.hpp:106-111, every operation individually rounded (no FMA contraction).
@@ -267,14 +59,15 @@ force_f32_refcompat_kernel(const float *__restrict__ posm, float *__restrict__ a
                            long long j_body_limit, int slot0, float eps2)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const Ring ring = ring_setup(smem_raw, REF_THREADS / 32);
+    RefRing ring;
+    ring.setup(smem_raw, REF_THREADS / 32);
     const int tid = threadIdx.x;
     const int chunk_blks = j_nblk;
     const int nst = (chunk_blks + STAGE_BLKS - 1) / STAGE_BLKS;
     const float *src = posm + (size_t)j_blk0 * BLK_ELEMS;
     if (tid == 0) {
         const int pre = min(NSTAGE, nst);
-        for (int t = 0; t < pre; ++t) ring_issue(ring, src, t, chunk_blks);
+        for (int t = 0; t < pre; ++t) ring.issue(src, t, chunk_blks);
     }
     // 128 targets per CTA: half a block
     const int half = blockIdx.x;                      // half-block index inside the launch
@@ -287,7 +80,7 @@ force_f32_refcompat_kernel(const float *__restrict__ posm, float *__restrict__ a
     for (int t = 0; t < nst; ++t) {
         const int s = t % NSTAGE;
         mbar_wait(&ring.full[s], (uint32_t)(t / NSTAGE) & 1u);
-        const float *st = ring.stage + (size_t)s * STAGE_FLOATS;
+        const float *st = ring.stage + (size_t)s * RefRing::STAGE_FLOATS;
         const int nb = min(STAGE_BLKS, chunk_blks - t * STAGE_BLKS);
         for (int bb = 0; bb < nb; ++bb) {
             const float *sx = st + bb * BLK_ELEMS;
@@ -309,13 +102,7 @@ force_f32_refcompat_kernel(const float *__restrict__ posm, float *__restrict__ a
                 ref_pair(sx[j], sx[BLK + j], sx[2 * BLK + j], sx[3 * BLK + j], xi, yi, zi, eps2, ax,
                          ay, az);
         }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&ring.empty[s]);
-        if (tid == 0 && t >= 1 && (t - 1 + NSTAGE) < nst) {
-            const int tp = t - 1;
-            mbar_wait(&ring.empty[tp % NSTAGE], (uint32_t)(tp / NSTAGE) & 1u);
-            ring_issue(ring, src, tp + NSTAGE, chunk_blks);
-        }
+        ring.release_and_refill(src, t, nst, chunk_blks);
     }
     const int lb = i_blk_local0 + (half >> 1);
     float *o = accp + ((size_t)slot0 * n_iblk_shard + lb) * BLK_ELEMS + lane;
@@ -323,22 +110,26 @@ force_f32_refcompat_kernel(const float *__restrict__ posm, float *__restrict__ a
 }
 
 // ---- host-side launchers ------------------------------------------------------------------------
-template <bool GUARD, bool FUSE>
+using FastRing = Ring<BLK_ELEMS, FAST_STAGE_BLKS>;
+
+template <int FORM, bool GUARD, bool FUSE>
 static cudaError_t launch_fast_t(const ForceLaunch &L, cudaStream_t st)
 {
-    auto kern = force_f32_fast_kernel<GUARD, FUSE>;
+    auto kern = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM, GUARD, FUSE>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)F32_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int grid = force_f32_fast_grid(L);
-    kern<<<grid, FAST_THREADS, F32_SMEM, st>>>(
-        (const float *)L.posm, (float *)L.accp, L.i_blk0, L.i_blk_local0, L.n_iblk_shard, L.j_blk0,
-        L.j_nblk, L.splits, L.slot0, L.eps2, L.j_body_limit, (float *)L.posm_next, (float *)L.vel,
-        (float *)L.acc, L.ip);
+    FastArgs a;
+    a.posm = (const float *)L.posm;
+    a.accp = (float *)L.accp;
+    a.i_blk0 = L.i_blk0; a.i_blk_local0 = L.i_blk_local0; a.n_iblk_shard = L.n_iblk_shard;
+    a.j_blk0 = L.j_blk0; a.j_nblk = L.j_nblk; a.splits = L.splits; a.slot0 = L.slot0;
+    a.eps2 = L.eps2; a.acc_scale = L.acc_scale; a.n_real = L.j_body_limit;
+    a.posm_next = (float *)L.posm_next; a.vel = (float *)L.vel; a.acc = (float *)L.acc; a.ip = L.ip;
+    kern<<<force_f32_fast_grid(L), FAST_THREADS, FastRing::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -349,20 +140,32 @@ cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStr
     if (L.n_iblk % FAST_TILE_BLKS != 0 || L.splits < 1 || L.j_nblk < L.splits)
         return cudaErrorInvalidValue;
     if (L.fuse && L.splits != 1) return cudaErrorInvalidValue;
-    if (guard_zero) return L.fuse ? launch_fast_t<true, true>(L, st) : launch_fast_t<true, false>(L, st);
-    return L.fuse ? launch_fast_t<false, true>(L, st) : launch_fast_t<false, false>(L, st);
+    const int v = (L.uniform_mass ? 4 : 0) | (guard_zero ? 2 : 0) | (L.fuse ? 1 : 0);
+    switch (v) {
+    case 0: return launch_fast_t<FORM_PLAIN, false, false>(L, st);
+    case 1: return launch_fast_t<FORM_PLAIN, false, true>(L, st);
+    case 2: return launch_fast_t<FORM_PLAIN, true, false>(L, st);
+    case 3: return launch_fast_t<FORM_PLAIN, true, true>(L, st);
+    case 4: return launch_fast_t<FORM_UNIFORM, false, false>(L, st);
+    case 5: return launch_fast_t<FORM_UNIFORM, false, true>(L, st);
+    case 6: return launch_fast_t<FORM_UNIFORM, true, false>(L, st);
+    default: return launch_fast_t<FORM_UNIFORM, true, true>(L, st);
+    }
 }
 
-int force_f32_fast_ctas_per_sm(bool fuse)
+int force_f32_fast_ctas_per_sm(bool uniform_mass)
 {
     int n = 0;
     cudaError_t e;
-    if (fuse)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_fast_kernel<false, true>,
-                                                          FAST_THREADS, F32_SMEM);
-    else
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_fast_kernel<false, false>,
-                                                          FAST_THREADS, F32_SMEM);
+    if (uniform_mass) {
+        auto k = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_UNIFORM, false, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, FAST_THREADS, FastRing::SMEM);
+    } else {
+        auto k = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_PLAIN, false, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, FAST_THREADS, FastRing::SMEM);
+    }
     return e == cudaSuccess ? n : 0;
 }
 
@@ -370,7 +173,7 @@ cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st)
 {
     if (L.splits != 1 || L.j_nblk < 1) return cudaErrorInvalidValue;
     const int grid = L.n_iblk * (BLK / REF_TILE_BODIES);
-    force_f32_refcompat_kernel<<<grid, REF_THREADS, F32_SMEM, st>>>(
+    force_f32_refcompat_kernel<<<grid, REF_THREADS, RefRing::SMEM, st>>>(
         (const float *)L.posm, (float *)L.accp, L.i_blk0, L.i_blk_local0, L.n_iblk_shard, L.j_blk0,
         L.j_nblk, L.j_body_limit, L.slot0, L.eps2);
     return cudaGetLastError();
@@ -383,8 +186,8 @@ cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st)
 __global__ void __launch_bounds__(256)
 integrate_f32_kernel(const float *__restrict__ posm_cur, float *__restrict__ posm_next,
                      float *__restrict__ vel, float *__restrict__ acc,
-                     const float *__restrict__ accp, int nslots, int i_blk0, int n_iblk_shard,
-                     int acc_only, long long n_real, IntegParams ip)
+                     const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                     int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // one per 4 bodies
     const int lb = gid >> 6;                                 // 64 float4 groups per block
@@ -404,7 +207,7 @@ integrate_f32_kernel(const float *__restrict__ posm_cur, float *__restrict__ pos
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        A[c].x *= ip.G; A[c].y *= ip.G; A[c].z *= ip.G; A[c].w *= ip.G;
+        A[c].x *= acc_scale; A[c].y *= acc_scale; A[c].z *= acc_scale; A[c].w *= acc_scale;
         *reinterpret_cast<float4 *>(acc + loff + c * BLK) = A[c];
     }
     if (acc_only) return;
@@ -435,7 +238,7 @@ cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st)
     const int grid = (threads + 255) / 256;
     integrate_f32_kernel<<<grid, 256, 0, st>>>((const float *)L.posm_cur, (float *)L.posm_next,
                                                (float *)L.vel, (float *)L.acc,
-                                               (const float *)L.accp, L.nslots, L.i_blk0,
+                                               (const float *)L.accp, L.acc_scale, L.nslots, L.i_blk0,
                                                L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
     return cudaGetLastError();
 }

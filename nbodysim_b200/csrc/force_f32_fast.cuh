@@ -1,0 +1,280 @@
+// force_f32_fast.cuh -- the headline all-pairs kernel (template), shared by the product library
+// (force_f32.cu) and the tuning harness (tools/kbench.cu).  See force_f32.cu for the design notes.
+#pragma once
+#include "kernels.h"
+
+namespace nb {
+
+constexpr int NSTAGE = 4;                           // ring depth of the TMA source pipeline
+
+// ---- the one place the integrator arithmetic lives (device side, fp32) -----------------------
+// Body::update (Body.hpp:34-38): vel += acc*dt ; pos += vel*dt, as unfused mul-then-add (two
+// roundings each) exactly like the strict build of the reference; plus the optional extras of
+// Simulation::iterate (Simulation.hpp:129-155).
+__device__ __forceinline__ void integrate_body_f32(float &px, float &py, float &pz, float &vx,
+                                                   float &vy, float &vz, float ax, float ay,
+                                                   float az, const IntegParams &ip)
+{
+    const float dt = ip.dt;
+    vx = __fadd_rn(vx, __fmul_rn(ax, dt));
+    vy = __fadd_rn(vy, __fmul_rn(ay, dt));
+    vz = __fadd_rn(vz, __fmul_rn(az, dt));
+    if (ip.flags & 1u) { // Simulation.hpp:133-137
+        float v2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        if (v2 > ip.max_velocity_sq) {
+            float scale = __fdiv_rn(ip.max_velocity, __fsqrt_rn(v2));
+            vx = __fmul_rn(vx, scale);
+            vy = __fmul_rn(vy, scale);
+            vz = __fmul_rn(vz, scale);
+        }
+    }
+    if (ip.flags & 2u) { // Simulation.hpp:142-155
+        float d2 = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
+        if (d2 > ip.soft_boundary_sq) {
+            float dist = __fsqrt_rn(d2);
+            float ratio = __fdiv_rn(dist, ip.soft_boundary);
+            float force = __fmul_rn(ip.boundary_force, expf(__fsub_rn(ratio, 1.0f)));
+            float k = __fdiv_rn(-1.0f, dist);
+            float fd = __fmul_rn(force, dt);
+            vx = __fadd_rn(vx, __fmul_rn(__fmul_rn(px, k), fd));
+            vy = __fadd_rn(vy, __fmul_rn(__fmul_rn(py, k), fd));
+            vz = __fadd_rn(vz, __fmul_rn(__fmul_rn(pz, k), fd));
+            vx = __fmul_rn(vx, ip.damping);
+            vy = __fmul_rn(vy, ip.damping);
+            vz = __fmul_rn(vz, ip.damping);
+        }
+    }
+    px = __fadd_rn(px, __fmul_rn(vx, dt));
+    py = __fadd_rn(py, __fmul_rn(vy, dt));
+    pz = __fadd_rn(pz, __fmul_rn(vz, dt));
+}
+
+// ---- TMA source-tile ring -----------------------------------------------------------------------
+// SRC_BLK_ELEMS floats per source block (4 or 5 component arrays of 256), STAGE_BLKS blocks per stage.
+template <int SRC_BLK_ELEMS, int STAGE_BLKS>
+struct Ring {
+    static constexpr int STAGE_FLOATS = STAGE_BLKS * SRC_BLK_ELEMS;
+    static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+    static constexpr size_t SMEM = (size_t)NSTAGE * STAGE_BYTES + 2 * NSTAGE * sizeof(uint64_t);
+    float *stage;        // NSTAGE * STAGE_FLOATS
+    uint64_t *full;      // NSTAGE, tx-count barriers armed by the producer thread
+    uint64_t *empty;     // NSTAGE, one arrival per consumer warp
+
+    __device__ __forceinline__ void setup(unsigned char *smem_raw, int nwarps)
+    {
+        stage = reinterpret_cast<float *>(smem_raw);
+        full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
+        empty = full + NSTAGE;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NSTAGE; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], nwarps);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void issue(const float *src_blocks, int t, int chunk_blks) const
+    {
+        const int s = t % NSTAGE;
+        const int nb = min(STAGE_BLKS, chunk_blks - t * STAGE_BLKS);
+        const uint32_t bytes = (uint32_t)nb * SRC_BLK_ELEMS * 4u;
+        mbar_expect_tx(&full[s], bytes);
+        tma_bulk_g2s(stage + (size_t)s * STAGE_FLOATS,
+                     src_blocks + (size_t)t * STAGE_BLKS * SRC_BLK_ELEMS, bytes, &full[s]);
+    }
+    // consumer side of stage t is done; thread 0 refills the buffer of the PREVIOUS stage
+    __device__ __forceinline__ void release_and_refill(const float *src_blocks, int t, int nst,
+                                                       int chunk_blks) const
+    {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[t % NSTAGE]);
+        if (threadIdx.x == 0 && t >= 1 && (t - 1 + NSTAGE) < nst) {
+            const int tp = t - 1;
+            mbar_wait(&empty[tp % NSTAGE], (uint32_t)(tp / NSTAGE) & 1u);
+            issue(src_blocks, tp + NSTAGE, chunk_blks);
+        }
+    }
+};
+
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+
+// Plain formulation, 12 fp32-pipe lane-ops + 1 MUFU per interaction:
+//   d = p_j - p_i (3 FADD) ; r2 = d.d + eps^2 (3 FFMA) ; ri = rsqrt(r2) ; s = m_j ri^3 (3 FMUL) ;
+//   acc += d s (3 FFMA)
+template <int I, bool GUARD>
+__device__ __forceinline__ void interact_pair_plain(const float2 xj, const float2 yj,
+                                                    const float2 zj, const float2 mj,
+                                                    const float2 (&nxi)[I], const float2 (&nyi)[I],
+                                                    const float2 (&nzi)[I], float2 (&ax)[I],
+                                                    float2 (&ay)[I], float2 (&az)[I], const float2 e2)
+{
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+        const float2 dx = __fadd2_rn(xj, nxi[k]);
+        const float2 dy = __fadd2_rn(yj, nyi[k]);
+        const float2 dz = __fadd2_rn(zj, nzi[k]);
+        float2 r2 = __ffma2_rn(dx, dx, e2);
+        r2 = __ffma2_rn(dy, dy, r2);
+        r2 = __ffma2_rn(dz, dz, r2);
+        float2 ri = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+        if (GUARD) { // eps == 0: self / coincident pairs contribute nothing (Quadtree.hpp:139)
+            ri.x = (r2.x > 0.0f) ? ri.x : 0.0f;
+            ri.y = (r2.y > 0.0f) ? ri.y : 0.0f;
+        }
+        const float2 ri2 = __fmul2_rn(ri, ri);
+        const float2 mr = __fmul2_rn(mj, ri);
+        const float2 s = __fmul2_rn(mr, ri2);
+        ax[k] = __ffma2_rn(dx, s, ax[k]);
+        ay[k] = __ffma2_rn(dy, s, ay[k]);
+        az[k] = __ffma2_rn(dz, s, az[k]);
+    }
+}
+
+// Uniform-mass formulation, 11 lane-ops + 1 MUFU, exact displacements: when every massive source has
+// the same mass the multiply by m_j factors out of the sum (applied once per target afterwards):
+//   d = p_j - p_i (3 FADD) ; r2 = d.d + eps^2 (3 FFMA) ; ri = rsqrt(r2) ; s = ri^3 (2 FMUL) ; acc += d s
+// Padding sources sit at 1e18 (pack kernel): ri^3 underflows to exactly 0 there.
+template <int I, bool GUARD>
+__device__ __forceinline__ void interact_pair_uniform(const float2 xj, const float2 yj,
+                                                      const float2 zj, const float2 (&nxi)[I],
+                                                      const float2 (&nyi)[I], const float2 (&nzi)[I],
+                                                      float2 (&ax)[I], float2 (&ay)[I], float2 (&az)[I],
+                                                      const float2 e2)
+{
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+        const float2 dx = __fadd2_rn(xj, nxi[k]);
+        const float2 dy = __fadd2_rn(yj, nyi[k]);
+        const float2 dz = __fadd2_rn(zj, nzi[k]);
+        float2 r2 = __ffma2_rn(dx, dx, e2);
+        r2 = __ffma2_rn(dy, dy, r2);
+        r2 = __ffma2_rn(dz, dz, r2);
+        float2 ri = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+        if (GUARD) {
+            ri.x = (r2.x > 0.0f) ? ri.x : 0.0f;
+            ri.y = (r2.y > 0.0f) ? ri.y : 0.0f;
+        }
+        const float2 ri2 = __fmul2_rn(ri, ri);
+        const float2 s = __fmul2_rn(ri2, ri);
+        ax[k] = __ffma2_rn(dx, s, ax[k]);
+        ay[k] = __ffma2_rn(dy, s, ay[k]);
+        az[k] = __ffma2_rn(dz, s, az[k]);
+    }
+}
+
+enum { FORM_PLAIN = 0, FORM_UNIFORM = 1 };
+
+struct FastArgs {
+    const float *posm;       // blocked (x,y,z,m): sources and targets
+    float *accp;
+    int i_blk0, i_blk_local0, n_iblk_shard, j_blk0, j_nblk, splits, slot0;
+    float eps2;
+    float acc_scale;         // fused epilogue factor: G (plain) or G*m (uniform)
+    long long n_real;
+    float *posm_next, *vel, *acc;   // fused epilogue only
+    IntegParams ip;
+};
+
+template <int I, int THREADS, int MINB, int UNROLL, int STAGE_BLKS, int FORM, bool GUARD, bool FUSE>
+__global__ void __launch_bounds__(THREADS, MINB) force_f32_fast_kernel(const FastArgs a)
+{
+    constexpr int SRC_ELEMS = BLK_ELEMS;
+    using RingT = Ring<SRC_ELEMS, STAGE_BLKS>;
+    constexpr int LANES_PER_BLK = BLK / THREADS;          // 1 (256 threads) or 2 (128 threads)
+    static_assert(BLK % THREADS == 0 && I % LANES_PER_BLK == 0, "tile shape");
+    constexpr int TILE_BLKS = I / LANES_PER_BLK;           // target blocks per CTA
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RingT ring;
+    ring.setup(smem_raw, THREADS / 32);
+
+    const int tile = blockIdx.x / a.splits;
+    const int split = blockIdx.x - tile * a.splits;
+    const int tid = threadIdx.x;
+
+    // source chunk of this CTA: whole blocks, balanced to within one block
+    const int jb0 = a.j_blk0 + (int)(((long long)a.j_nblk * split) / a.splits);
+    const int jb1 = a.j_blk0 + (int)(((long long)a.j_nblk * (split + 1)) / a.splits);
+    const int chunk_blks = jb1 - jb0;
+    const int nst = (chunk_blks + STAGE_BLKS - 1) / STAGE_BLKS;
+    const float *src = a.posm + (size_t)jb0 * SRC_ELEMS;
+
+    if (tid == 0) {
+        const int pre = min(NSTAGE, nst);
+        for (int t = 0; t < pre; ++t) ring.issue(src, t, chunk_blks);
+    }
+
+    // targets: I bodies per thread, coalesced block reads.  Keep -p_i broadcast over both packed
+    // lanes so that r = p_j + (-p_i) is one FADD2 (ptxas folds the pair into a .F32 operand).
+    float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
+    size_t tgt_off[I];
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+        const int blk = tile * TILE_BLKS + k / LANES_PER_BLK;
+        const int lane = (k % LANES_PER_BLK) * THREADS + tid;
+        tgt_off[k] = (size_t)blk * BLK_ELEMS + lane;
+        const float *b = a.posm + (size_t)a.i_blk0 * BLK_ELEMS + tgt_off[k];
+        const float x = b[0], y = b[BLK], z = b[2 * BLK];
+        nxi[k] = make_float2(-x, -x);
+        nyi[k] = make_float2(-y, -y);
+        nzi[k] = make_float2(-z, -z);
+        ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+    }
+    const float2 e2 = make_float2(a.eps2, a.eps2);
+
+    for (int t = 0; t < nst; ++t) {
+        const int s = t % NSTAGE;
+        mbar_wait(&ring.full[s], (uint32_t)(t / NSTAGE) & 1u);
+        const float *st = ring.stage + (size_t)s * RingT::STAGE_FLOATS;
+        const int nb = min(STAGE_BLKS, chunk_blks - t * STAGE_BLKS);
+        for (int b = 0; b < nb; ++b) {
+            const float *sx = st + b * SRC_ELEMS;
+#pragma unroll UNROLL
+            for (int j = 0; j < BLK; j += 4) {
+                const float4 X = *reinterpret_cast<const float4 *>(sx + j);
+                const float4 Y = *reinterpret_cast<const float4 *>(sx + BLK + j);
+                const float4 Z = *reinterpret_cast<const float4 *>(sx + 2 * BLK + j);
+                if (FORM == FORM_UNIFORM) {
+                    interact_pair_uniform<I, GUARD>(lo2(X), lo2(Y), lo2(Z), nxi, nyi, nzi, ax, ay, az, e2);
+                    interact_pair_uniform<I, GUARD>(hi2(X), hi2(Y), hi2(Z), nxi, nyi, nzi, ax, ay, az, e2);
+                    continue;
+                }
+                const float4 M = *reinterpret_cast<const float4 *>(sx + 3 * BLK + j);
+                interact_pair_plain<I, GUARD>(lo2(X), lo2(Y), lo2(Z), lo2(M), nxi, nyi, nzi, ax, ay, az, e2);
+                interact_pair_plain<I, GUARD>(hi2(X), hi2(Y), hi2(Z), hi2(M), nxi, nyi, nzi, ax, ay, az, e2);
+            }
+        }
+        ring.release_and_refill(src, t, nst, chunk_blks);
+    }
+
+    // epilogue: fold the two packed lanes (even/odd sources)
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+        const float fx = ax[k].x + ax[k].y, fy = ay[k].x + ay[k].y, fz = az[k].x + az[k].y;
+        const size_t loff = (size_t)a.i_blk_local0 * BLK_ELEMS + tgt_off[k];   // inside the shard
+        if (FUSE) {
+            const size_t goff = (size_t)a.i_blk0 * BLK_ELEMS + tgt_off[k];
+            const long long body = (long long)(goff / BLK_ELEMS) * BLK + (long long)(goff % BLK);
+            if (body >= a.n_real) continue;                      // padding stays put
+            // fused kick-drift: the new positions go to the other posm buffer, so CTAs still
+            // reading the current one are undisturbed (race-free by construction).
+            const float g = a.acc_scale;
+            const float gx = fx * g, gy = fy * g, gz = fz * g;
+            const float *pb = a.posm + goff;
+            float *vb = a.vel + loff, *ab = a.acc + loff, *nb_ = a.posm_next + goff;
+            float px = pb[0], py = pb[BLK], pz = pb[2 * BLK];
+            const float m = pb[3 * BLK];
+            float vx = vb[0], vy = vb[BLK], vz = vb[2 * BLK];
+            integrate_body_f32(px, py, pz, vx, vy, vz, gx, gy, gz, a.ip);
+            nb_[0] = px; nb_[BLK] = py; nb_[2 * BLK] = pz; nb_[3 * BLK] = m;
+            vb[0] = vx; vb[BLK] = vy; vb[2 * BLK] = vz;
+            ab[0] = gx; ab[BLK] = gy; ab[2 * BLK] = gz;
+        } else {
+            float *o = a.accp + (size_t)(a.slot0 + split) * a.n_iblk_shard * BLK_ELEMS + loff;
+            o[0] = fx; o[BLK] = fy; o[2 * BLK] = fz;
+        }
+    }
+}
+
+} // namespace nb

@@ -145,8 +145,8 @@ cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st)
 __global__ void __launch_bounds__(256)
 integrate_f64_kernel(const double *__restrict__ posm_cur, double *__restrict__ posm_next,
                      double *__restrict__ vel, double *__restrict__ acc,
-                     const double *__restrict__ accp, int nslots, int i_blk0, int n_iblk_shard,
-                     int acc_only, long long n_real, IntegParams ip)
+                     const double *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                     int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x; // one body
     const int lb = gid >> 8;
@@ -159,7 +159,7 @@ integrate_f64_kernel(const double *__restrict__ posm_cur, double *__restrict__ p
         const double *p = accp + (size_t)s * n_iblk_shard * BLK_ELEMS + loff;
         a[0] += p[0]; a[1] += p[BLK]; a[2] += p[2 * BLK];
     }
-    const double G = (double)ip.G;
+    const double G = (double)acc_scale;
     a[0] *= G; a[1] *= G; a[2] *= G;
     acc[loff] = a[0]; acc[loff + BLK] = a[1]; acc[loff + 2 * BLK] = a[2];
     if (acc_only || (long long)(i_blk0 + lb) * BLK + q >= n_real) return;
@@ -177,7 +177,7 @@ cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st)
     const int threads = L.n_iblk_shard * BLK;
     integrate_f64_kernel<<<(threads + 255) / 256, 256, 0, st>>>(
         (const double *)L.posm_cur, (double *)L.posm_next, (double *)L.vel, (double *)L.acc,
-        (const double *)L.accp, L.nslots, L.i_blk0, L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
+        (const double *)L.accp, L.acc_scale, L.nslots, L.i_blk0, L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,8 @@ struct IntegParams {
 // [j_blk0, j_blk0 + j_nblk) cut into `splits` chunks; CTA (tile, s) writes its partial sum into
 // partial slot slot0 + s.  Slots are summed in index order by the integrator (deterministic).
 struct ForceLaunch {
+    int uniform_mass;        // fast kernel: 1 = every massive source has the same mass (11-op form)
+    float acc_scale;         // fused epilogue: G (plain) or G*m (uniform)
     const void *posm;        // blocked (x,y,z,m), float or double
     void *accp;              // partial accelerations, blocked, [slot][local block]
     int i_blk0;              // first target block (global block index into posm)
@@ -46,6 +48,7 @@ struct IntegLaunch {
     void *posm_next;         // blocked, full array
     void *vel, *acc;         // blocked, shard-local
     const void *accp;        // partial slots
+    float acc_scale;         // G, or G*m when the uniform-mass force kernel summed unit masses
     int nslots;
     int i_blk0;              // first global block of the shard
     int n_iblk_shard;
@@ -54,8 +57,10 @@ struct IntegLaunch {
     IntegParams ip;
 };
 
-// geometry of each force kernel variant
-constexpr int FAST_THREADS = 256, FAST_I = 4, FAST_TILE_BLKS = FAST_I;       // 1024 targets / CTA
+// geometry of each force kernel variant (fast: chosen by the tools/kbench.cu sweeps on B200 --
+// 8 targets per thread, 256 threads, one CTA of 8 warps per SM, ~228 registers per thread)
+constexpr int FAST_THREADS = 256, FAST_I = 8, FAST_MINB = 1, FAST_UNROLL = 1, FAST_STAGE_BLKS = 2;
+constexpr int FAST_TILE_BLKS = FAST_I / (BLK / FAST_THREADS);                // 8 blocks = 2048 targets / CTA
 constexpr int REF_THREADS = 128, REF_TILE_BODIES = 128;                      // refcompat: 1 / thread
 constexpr int F64_THREADS = 128, F64_I = 2, F64_TILE_BLKS = 1;               // 256 targets / CTA
 constexpr int TARGET_GRANULE = FAST_TILE_BLKS * BLK;                         // shard granularity
@@ -63,7 +68,7 @@ constexpr int TARGET_GRANULE = FAST_TILE_BLKS * BLK;                         // 
 cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStream_t st);
 cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st);
 cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st);
-int force_f32_fast_ctas_per_sm(bool fuse);
+int force_f32_fast_ctas_per_sm(bool uniform_mass);
 int force_f32_fast_grid(const ForceLaunch &L);
 
 cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st);

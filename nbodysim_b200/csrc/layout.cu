@@ -16,14 +16,16 @@ pack_kernel(const nbody_body_t *__restrict__ aos, size_t n, size_t n_padded, siz
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_padded) return;
     // each thread reads its 64-byte record as four 16-byte vectors (a warp covers 2 KiB contiguous)
-    float4 p = make_float4(0, 0, 0, 0), v = p, a = p, mr = p;
+    // zero-mass padding beyond n sits far away (1e18): it contributes exactly 0 to every sum, also in
+    // the uniform-mass kernel, where (r^2)^-3/2 underflows to 0 instead of being multiplied by m = 0
+    float4 p = make_float4(PAD_POS, PAD_POS, PAD_POS, 0), v = make_float4(0, 0, 0, 0), a = v, mr = v;
     if (i < n) {
         const float4 *r = reinterpret_cast<const float4 *>(aos + i);
         p = r[0]; v = r[1]; a = r[2]; mr = r[3];
     }
     const size_t g = blk_index(i, 0);
     posm[g] = (T)p.x; posm[g + BLK] = (T)p.y; posm[g + 2 * BLK] = (T)p.z;
-    posm[g + 3 * BLK] = (T)mr.x;   // zero-mass padding beyond n: contributes exactly 0
+    posm[g + 3 * BLK] = (T)mr.x;
     if (i >= shard_start && i < shard_start + shard_count) {
         const size_t l = blk_index(i - shard_start, 0);
         vel[l] = (T)v.x; vel[l + BLK] = (T)v.y; vel[l + 2 * BLK] = (T)v.z; vel[l + 3 * BLK] = (T)mr.y;

@@ -55,6 +55,8 @@ struct nbody_ctx {
     size_t n = 0, n_padded = 0;
     int world = 1;               // total GPUs
     bool f64 = false;
+    bool uniform = false;        // every massive body has the same mass: 11-op force kernel
+    float uniform_mass = 0.f;
     size_t esz = 4;
     std::vector<Dev> devs;
     nbody_body_t *h_stage = nullptr; // pinned, n records (download merges / uploads)
@@ -220,6 +222,8 @@ ForceLaunch make_force(const nbody_ctx *c, const Dev &d, const Range &r, float d
     ForceLaunch L;
     memset(&L, 0, sizeof L);
     L.posm = d.posm[d.cur];
+    L.uniform_mass = c->uniform ? 1 : 0;
+    L.acc_scale = c->uniform ? c->p.G * c->uniform_mass : c->p.G;
     L.accp = d.accp;
     L.i_blk0 = (int)(d.shard_start / BLK);
     L.i_blk_local0 = 0;
@@ -284,6 +288,8 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             I.n_iblk_shard = (int)(d.shard_count / BLK);
             I.acc_only = acc_only ? 1 : 0;
             I.n_real = (long long)ctx->n;
+            const bool fastpath = !ctx->f64 && !refc;
+            I.acc_scale = (fastpath && ctx->uniform) ? ctx->p.G * ctx->uniform_mass : ctx->p.G;
             I.ip = make_ip(ctx, dt);
             if (d.fused && acc_only) {
                 // fused plans own no partial slot buffer semantics beyond slot 0: the non-fused
@@ -385,6 +391,7 @@ void nbody_params_default(nbody_params *p)
     p->j_splits = 0;
     p->fuse_integrator = -1;
     p->use_graph = -1;
+    p->force_variant = -1;
     p->ngpus = 1;
     p->world = 1;
     p->rank = 0;
@@ -436,6 +443,15 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         const size_t per = (size_t)TARGET_GRANULE * (size_t)world;
         ctx->n_padded = ((n + per - 1) / per) * per;
     }
+    if (!ctx->f64 && p->rsqrt_mode == NBODY_RSQRT_FAST && p->force_variant != 0) {
+        // uniform-mass form: valid when every body has the same positive mass (bit-equal), so that
+        // sum_j m_j f(r_ij) == m * sum_j f(r_ij) term for term.  force_variant = 0 disables it.
+        const float m0 = bodies[0].mass;
+        bool same = m0 > 0.0f;
+        for (size_t i = 1; i < n && same; ++i) same = (bodies[i].mass == m0);
+        ctx->uniform = same;
+        ctx->uniform_mass = same ? m0 : 0.0f;
+    }
     int rc = NBODY_OK;
     auto fail = [&](int code) {
         memcpy(g_init_err, ctx->err, sizeof g_init_err);
@@ -472,7 +488,7 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->devs[0].device);
         ctx->sm_clock_khz = khz;
         cudaSetDevice(ctx->devs[0].device);
-        ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(false);
+        ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(ctx->uniform);
     }
     for (Dev &d : ctx->devs) {
         if ((rc = plan_device(ctx, d)) != NBODY_OK) return fail(rc);
@@ -578,6 +594,13 @@ int nbody_gpu_upload(nbody_ctx *ctx, const nbody_body_t *bodies, size_t n)
     if (!ctx || !bodies || n != ctx->n) return NBODY_EINVAL;
     int rc = sync_all(ctx);
     if (rc != NBODY_OK) return rc;
+    if (ctx->uniform) { // the uniform-mass kernel stays valid only while the masses stay as uploaded
+        for (size_t i = 0; i < n; ++i)
+            if (bodies[i].mass != ctx->uniform_mass) {
+                set_err(ctx, "nbody_gpu_upload: masses changed; re-create the context (uniform-mass kernel in use)");
+                return NBODY_ESTATE;
+            }
+    }
     return upload_state(ctx, bodies);
 }
 
@@ -664,6 +687,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->force_ctas = d0.force_ctas;
     info->ctas_per_sm = ctx->ctas_per_sm;
     info->fused = d0.fused ? 1 : 0;
+    info->uniform_mass = ctx->uniform ? 1 : 0;
     info->graph = 0;
     info->kernel_launches = ctx->launches;
     info->interactions = ctx->interactions;
@@ -709,6 +733,6 @@ const char *nbody_gpu_strerror(int code)
 
 const char *nbody_gpu_last_error(const nbody_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
 
-const char *nbody_gpu_version(void) { return "nbody_gpu 0.1 (sm_100a; all-pairs f32 fast/refcompat, f64)"; }
+const char *nbody_gpu_version(void) { return "nbody_gpu 0.2 (sm_100a; all-pairs f32 fast[plain|uniform-mass]/refcompat, f64)"; }
 
 } // extern "C"

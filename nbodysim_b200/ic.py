@@ -44,7 +44,10 @@ def rescale(b, lscale=1.0, vscale=1.0, mscale=1.0):
     return b
 
 
-def shard_plan(n, world, rank, granule=1024):
+TARGET_GRANULE = 2048  # == nb::TARGET_GRANULE (csrc/kernels.h): 8 blocks of 256 targets per force CTA
+
+
+def shard_plan(n, world, rank, granule=TARGET_GRANULE):
     """(n_padded, start, count) of the multi-GPU driver's target shard for `rank`."""
     npad, start, count = C.c_size_t(), C.c_size_t(), C.c_size_t()
     _check(host_lib().nbody_shard_plan(n, world, rank, granule, C.byref(npad), C.byref(start), C.byref(count)),

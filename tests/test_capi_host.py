@@ -130,9 +130,9 @@ def test_snapshot_roundtrip(tmp_path):
 def test_shard_plan_covers_everything_once(n, world):
     spans = [ic.shard_plan(n, world, r) for r in range(world)]
     npad = spans[0][0]
-    assert npad >= n and npad % (1024 * world) == 0 and npad - n < 1024 * world
+    assert npad >= n and npad % (2048 * world) == 0 and npad - n < 2048 * world
     pos = 0
     for (np_, start, count) in spans:
-        assert np_ == npad and start == pos and count == npad // world and count % 1024 == 0
+        assert np_ == npad and start == pos and count == npad // world and count % 2048 == 0
         pos += count
     assert pos == npad
