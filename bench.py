@@ -111,6 +111,19 @@ def pinned_bodies(n):
     return t, t.numpy().view(BODY_DTYPE)
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes per force launch from the committed ncu capture (None if absent)."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r1_force_uniform_ncu.txt")):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def fp32_peak_tflops(info, sm_max_mhz):
     """B200 non-tensor FP32 peak: SMs x 128 FP32 lanes x 2 flop (FMA) x SM clock."""
     mhz = sm_max_mhz if sm_max_mhz else info["sm_clock_khz"] / 1e3
@@ -301,6 +314,12 @@ def native_arm(args):
         "flop_per_interaction": FLOP_PER_INTERACTION, "interactions_per_launch_set": per_gpu_inter,
         "kernel_ms": f_ms, "traffic": None,
     }
+    tr = ncu_traffic_bytes()
+    if tr is not None and n == 1048576 and world == 1:
+        roof["traffic"] = tr
+        roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this N from the committed "
+                                  "ncu --set full capture profiles/r1_force_uniform_ncu.txt")
+    roof["algorithmic_bytes"] = n * 16 / world * 0 + n * 16 + (n / world) * 12 * max(1, i1["j_splits"])
     if clocks and clocks.get("sm_mhz"):
         roof["frac_at_observed_clock"] = achieved_tf / (peak_tf * clocks["sm_mhz"] / peak_mhz)
     try:

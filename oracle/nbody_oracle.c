@@ -217,3 +217,179 @@ void orc_energy_f64(const orc_body_t *b, size_t n, double eps, double G, int dim
     P[1] = p1;
     P[2] = p2;
 }
+
+/* ============================================================================ Barnes-Hut path */
+#include <stdlib.h>
+
+typedef struct { orc_node_t *v; size_t n, cap; } nodevec_t;
+typedef struct { size_t *v; size_t n, cap; } idxvec_t;
+
+static void nv_push(nodevec_t *a, orc_node_t x)
+{
+    if (a->n == a->cap) {
+        a->cap = a->cap ? a->cap * 2 : 1024;
+        a->v = (orc_node_t *)realloc(a->v, a->cap * sizeof *a->v);
+    }
+    a->v[a->n++] = x;
+}
+static void iv_push(idxvec_t *a, size_t x)
+{
+    if (a->n == a->cap) {
+        a->cap = a->cap ? a->cap * 2 : 1024;
+        a->v = (size_t *)realloc(a->v, a->cap * sizeof *a->v);
+    }
+    a->v[a->n++] = x;
+}
+
+/* Node(next, quad, depth): data{Vec2::zero(), 0.0f, quad}, children 0.   Node.hpp:47-48 */
+static orc_node_t make_node(uint64_t next, float cx, float cy, float size, uint64_t depth)
+{
+    orc_node_t nd;
+    nd.px = 0.0f; nd.py = 0.0f; nd.mass = 0.0f;
+    nd.cx = cx; nd.cy = cy; nd.size = size;
+    nd.children = 0; nd.next = next; nd.depth = depth;
+    return nd;
+}
+
+/* Quad::find_quadrant, Quad.hpp:47-49 */
+static size_t find_quadrant(const orc_node_t *nd, float x, float y)
+{
+    return ((size_t)(y > nd->cy) << 1) | (size_t)(x > nd->cx);
+}
+
+/* Quad::into_quadrant, Quad.hpp:51-57: new_size = size*0.5f; offset = unit_x*((q&1)-0.5f) +
+ * unit_y*((q>>1)-0.5f); new_center = center + offset*new_size. */
+static void into_quadrant(const orc_node_t *nd, size_t q, float *cx, float *cy, float *size)
+{
+    const float new_size = nd->size * 0.5f;
+    const float fx = (float)(q & 1) - 0.5f, fy = (float)(q >> 1) - 0.5f;
+    const float ox = 1.0f * fx + 0.0f * fy; /* unit_x()*fx + unit_y()*fy, component-wise */
+    const float oy = 0.0f * fx + 1.0f * fy;
+    *cx = nd->cx + ox * new_size;
+    *cy = nd->cy + oy * new_size;
+    *size = new_size;
+}
+
+/* Quadtree::insert, Quadtree.hpp:35-93 */
+static void bh_insert(nodevec_t *nodes, idxvec_t *parents, float x, float y, float mass)
+{
+    size_t node = 0;
+    while (nodes->v[node].children != 0) {
+        size_t q = find_quadrant(&nodes->v[node], x, y);
+        node = nodes->v[node].children + q;
+    }
+    if (nodes->v[node].mass == 0.0f) { /* is_empty */
+        nodes->v[node].px = x; nodes->v[node].py = y; nodes->v[node].mass = mass;
+        return;
+    }
+    const float ex = nodes->v[node].px, ey = nodes->v[node].py, em = nodes->v[node].mass;
+    if (x == ex && y == ey) { /* coincident: merge, :56-60 */
+        nodes->v[node].mass += mass;
+        return;
+    }
+    for (;;) {
+        const size_t children = nodes->n;
+        nodes->v[node].children = children;
+        iv_push(parents, node);
+        for (size_t i = 0; i < 4; ++i) {
+            float cx, cy, sz;
+            const orc_node_t parent = nodes->v[node]; /* copy: the vector may reallocate */
+            into_quadrant(&parent, i, &cx, &cy, &sz);
+            nv_push(nodes, make_node((i < 3) ? children + i + 1 : parent.next, cx, cy, sz, parent.depth + 1));
+        }
+        const size_t q1 = find_quadrant(&nodes->v[node], ex, ey);
+        const size_t q2 = find_quadrant(&nodes->v[node], x, y);
+        if (q1 == q2) {
+            node = children + q1;
+        } else {
+            nodes->v[children + q1].px = ex; nodes->v[children + q1].py = ey; nodes->v[children + q1].mass = em;
+            nodes->v[children + q2].px = x; nodes->v[children + q2].py = y; nodes->v[children + q2].mass = mass;
+            return;
+        }
+    }
+}
+
+size_t orc_bh_build(const orc_body_t *b, size_t n, orc_node_t **nodes_out)
+{
+    nodevec_t nodes = {0, 0, 0};
+    idxvec_t parents = {0, 0, 0};
+    /* Quad::new_containing, Quad.hpp:31-45 */
+    float minx = 3.402823466e+38f, miny = 3.402823466e+38f, maxx = -3.402823466e+38f, maxy = -3.402823466e+38f;
+    for (size_t i = 0; i < n; ++i) {
+        minx = b[i].px < minx ? b[i].px : minx; /* std::min(a,b) = (b<a)?b:a */
+        miny = b[i].py < miny ? b[i].py : miny;
+        maxx = maxx < b[i].px ? b[i].px : maxx; /* std::max(a,b) = (a<b)?b:a */
+        maxy = maxy < b[i].py ? b[i].py : maxy;
+    }
+    const float cx = (minx + maxx) * 0.5f, cy = (miny + maxy) * 0.5f;
+    const float sx = maxx - minx, sy = maxy - miny;
+    const float size = sx < sy ? sy : sx; /* std::max(x, y) */
+    nv_push(&nodes, make_node(0, cx, cy, size, 0)); /* clear(): Node(0, quad) */
+    for (size_t i = 0; i < n; ++i) bh_insert(&nodes, &parents, b[i].px, b[i].py, b[i].mass);
+    /* propagate, Quadtree.hpp:236-258 */
+    for (size_t k = parents.n; k-- > 0;) {
+        const size_t node = parents.v[k], child = nodes.v[node].children;
+        float px = 0.0f, py = 0.0f, m = 0.0f;
+        for (size_t i = 0; i < 4; ++i) {
+            const orc_node_t *c = &nodes.v[child + i];
+            px += c->px * c->mass;
+            py += c->py * c->mass;
+            m += c->mass;
+        }
+        if (m > 0) { /* Vec2::operator/=: inv = 1/scalar; x *= inv; y *= inv */
+            const float inv = 1.0f / m;
+            px *= inv;
+            py *= inv;
+        }
+        nodes.v[node].px = px; nodes.v[node].py = py; nodes.v[node].mass = m;
+    }
+    free(parents.v);
+    *nodes_out = nodes.v;
+    return nodes.n;
+}
+
+/* Quadtree::acc, Quadtree.hpp:113-155 */
+void orc_bh_acc(const orc_node_t *nodes, size_t nnodes, float theta, float eps, const orc_body_t *b,
+                size_t i0, size_t i1, int fix_near_leaves, float *acc_out)
+{
+    (void)nnodes;
+    const float t_sq = theta * theta, e_sq = eps * eps;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long ii = (long long)i0; ii < (long long)i1; ++ii) {
+        const float px = b[ii].px, py = b[ii].py;
+        float ax = 0.0f, ay = 0.0f;
+        size_t node = 0;
+        for (;;) {
+            const orc_node_t *n = &nodes[node];
+            const float dx = n->px - px, dy = n->py - py;
+            const float d_sq = dx * dx + dy * dy;
+            if (n->size * n->size < d_sq * t_sq) {
+                if (d_sq > 0) {
+                    const float inv = orc_fast_inv_sqrt(d_sq + e_sq);
+                    const float inv3 = inv * inv * inv;
+                    const float s = n->mass * inv3;
+                    ax += dx * s;
+                    ay += dy * s;
+                }
+                if (n->next == 0) break;
+                node = n->next;
+            } else if (n->children == 0) {
+                /* near leaf: the reference loops over an EMPTY body range here */
+                if (fix_near_leaves && d_sq > 0 && n->mass != 0.0f) {
+                    const float inv = orc_fast_inv_sqrt(d_sq + e_sq);
+                    const float s = n->mass * (inv * inv * inv);
+                    ax += dx * s;
+                    ay += dy * s;
+                }
+                if (n->next == 0) break;
+                node = n->next;
+            } else {
+                node = n->children;
+            }
+        }
+        acc_out[2 * (ii - (long long)i0)] = ax;
+        acc_out[2 * (ii - (long long)i0) + 1] = ay;
+    }
+}
+
+void orc_free(void *p) { free(p); }

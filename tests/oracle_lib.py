@@ -47,9 +47,10 @@ def oracle():
         L.orc_iterate_after_attract.argtypes = [_vp, _sz, _f, C.c_uint, _i]
         L.orc_exact_acc_f64.argtypes = [_vp, _sz, _d, _d, _i, _sz, _sz, _vp]
         L.orc_energy_f64.argtypes = [_vp, _sz, _d, _d, _i, _vp, _vp, _vp]
-        for name in ("orc_bh_acc", "orc_bh_build"):
-            if hasattr(L, name):
-                pass
+        L.orc_bh_build.restype = _sz
+        L.orc_bh_build.argtypes = [_vp, _sz, C.POINTER(_vp)]
+        L.orc_bh_acc.argtypes = [_vp, _sz, _f, _f, _vp, _sz, _sz, _i, _vp]
+        L.orc_free.argtypes = [_vp]
         _oracle = L
     return _oracle
 
@@ -128,3 +129,43 @@ def ref_step_clean(b, eps, dt, nsteps, nthreads=0, kind="strict"):
     b = b.copy()
     reference(kind).ref_step_clean(b.ctypes.data, b.shape[0], eps, dt, nsteps, nthreads)
     return b
+
+
+ORC_NODE_DTYPE = np.dtype([("px", "<f4"), ("py", "<f4"), ("mass", "<f4"), ("cx", "<f4"), ("cy", "<f4"), ("size", "<f4"),
+                           ("children", "<u8"), ("next", "<u8"), ("depth", "<u8")])
+assert ORC_NODE_DTYPE.itemsize == 48
+
+
+def orc_bh_build(b):
+    """Oracle restatement of Quadtree::build -> structured array of nodes."""
+    ptr = _vp()
+    m = oracle().orc_bh_build(b.ctypes.data, b.shape[0], C.byref(ptr))
+    buf = (C.c_char * (m * ORC_NODE_DTYPE.itemsize)).from_address(ptr.value)
+    nodes = np.frombuffer(buf, dtype=ORC_NODE_DTYPE, count=m).copy()
+    oracle().orc_free(ptr)
+    return nodes
+
+
+def orc_bh_acc(b, theta, eps, nodes=None, i0=0, i1=None, fix_near_leaves=False):
+    n = b.shape[0]
+    i1 = n if i1 is None else i1
+    nodes = orc_bh_build(b) if nodes is None else nodes
+    out = np.zeros((i1 - i0, 2), dtype=np.float32)
+    oracle().orc_bh_acc(nodes.ctypes.data, nodes.shape[0], theta, eps, b.ctypes.data, i0, i1,
+                        1 if fix_near_leaves else 0, out.ctypes.data)
+    return out
+
+
+def ref_bh_acc(b, theta, eps, kind="strict"):
+    out = np.zeros((b.shape[0], 2), dtype=np.float32)
+    m = reference(kind).ref_bh_acc(b.ctypes.data, b.shape[0], theta, eps, out.ctypes.data)
+    return out, m
+
+
+def ref_bh_nodes(b, theta=1.0, eps=1.0, kind="strict"):
+    cap = 8 * b.shape[0] + 64
+    f = np.zeros((cap, 6), dtype=np.float32)
+    u = np.zeros((cap, 3), dtype=np.uint64)
+    m = reference(kind).ref_bh_nodes(b.ctypes.data, b.shape[0], theta, eps, f.ctypes.data, u.ctypes.data, cap)
+    assert m <= cap
+    return f[:m], u[:m]
