@@ -319,7 +319,8 @@ def native_arm(args):
         roof["traffic"] = tr
         roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this N from the committed "
                                   "ncu --set full capture profiles/r1_force_uniform_ncu.txt")
-    roof["algorithmic_bytes"] = n * 16 / world * 0 + n * 16 + (n / world) * 12 * max(1, i1["j_splits"])
+    # bytes the kernel must move per launch: every source once (16 B) + one 12-byte partial per target and split
+    roof["algorithmic_bytes"] = n * 16 + (n / world) * 12 * max(1, i1["j_splits"])
     if clocks and clocks.get("sm_mhz"):
         roof["frac_at_observed_clock"] = achieved_tf / (peak_tf * clocks["sm_mhz"] / peak_mhz)
     try:

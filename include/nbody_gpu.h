@@ -78,6 +78,9 @@ typedef struct nbody_params {
                                  lane-ops per interaction).  auto uses the uniform-mass form (11 lane-ops;
                                  m factored out of the sum, same per-pair arithmetic otherwise) when
                                  every body has the same mass. */
+    int32_t  bh_fix_near_leaves; /* Barnes-Hut only.  0 = the reference's behaviour: a NEAR leaf contributes
+                                 nothing (insert() leaves every body Range empty, Quadtree.hpp:133-147);
+                                 1 = add the leaf's body for near leaves (self excluded) */
     /* --- single-process multi-GPU (C driver): ngpus devices, NCCL comms created internally --- */
     int32_t  ngpus;           /* 0 or 1 = single GPU */
     int32_t  device_ids[NBODY_MAX_GPUS]; /* CUDA ordinals; device_ids[0] is used when ngpus<=1 */
@@ -102,6 +105,8 @@ typedef struct nbody_info {
     int32_t  fused;           /* 1 if the kick-drift runs in the force kernel's epilogue */
     int32_t  uniform_mass;    /* 1 if the fast kernel runs the uniform-mass (11-op) form */
     int32_t  graph;           /* 1 if multi-step calls replay a CUDA graph */
+    uint32_t bh_nodes;        /* Barnes-Hut: non-empty cells of the last tree built */
+    uint32_t reserved0;
     uint64_t kernel_launches; /* kernels of this library launched so far (all local GPUs) */
     uint64_t interactions;    /* pair interactions evaluated so far by this process */
     float    last_force_ms;   /* device time of the force kernel(s) of the last profiled step */
@@ -155,6 +160,13 @@ int nbody_gpu_energy(nbody_ctx *ctx, double *K, double *W, double P[3]);
 int nbody_gpu_profile_next_step(nbody_ctx *ctx, int enable);
 
 int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info);
+
+/* Barnes-Hut diagnostics / parity: the node array of the last tree built, in walk (depth-first,
+ * quadrant) order, WITHOUT the reference's empty leaves.  f6 = 6 floats per node: position (body or
+ * centre of mass) x,y ; mass ; quad centre x,y ; quad size  (Node::data, Node.hpp:35-40).
+ * u2 = 2 words per node: next (skip pointer, 0 = end of walk; Node::next) ; depth | is_leaf << 8.
+ * Writes min(cap, count) nodes; *count receives the total. */
+int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f6, uint32_t *u2, size_t cap, size_t *count);
 
 /* rank 0 creates the NCCL id that every rank passes in nbody_params.nccl_id. */
 int nbody_gpu_nccl_unique_id(uint8_t id[NBODY_NCCL_ID_BYTES]);

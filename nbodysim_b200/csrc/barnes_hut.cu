@@ -1,0 +1,367 @@
+// barnes_hut.cu -- the reference's shipped force algorithm, rebuilt for the GPU (2-D, like the reference).
+//
+// Restates Quadtree::build / insert / propagate (Quadtree.hpp:28-93,157-170,236-258), Quad
+// (Quad.hpp:31-57) and the stackless walk Quadtree::acc (Quadtree.hpp:113-155) so that, in refcompat
+// arithmetic, accelerations equal the reference's BIT FOR BIT -- including its quirks: one body per
+// leaf, COM-distance opening test `size^2 < d^2 theta^2`, far ancestors that contain the target keep
+// the target's own mass, and NEAR LEAVES CONTRIBUTE NOTHING (insert() leaves every body Range empty,
+// so the leaf loop :133-144 never runs).  `fix_near_leaves` adds the leaf body for near leaves.
+//
+// Why a parallel build can be bit-faithful to a serial pointer-chasing insert: the reference's tree,
+// as a SET of cells, does not depend on insertion order -- a cell exists iff its parent holds >= 2
+// distinct positions, child quads come from the fp32 recursion `center + (+-0.5) * size/2`, leaf data
+// is the body itself and branch data is sum(child.pos * child.mass) / sum(child.mass) over children
+// in quadrant order.  Only the node numbering depends on insertion order, and acc() visits nodes in
+// depth-first quadrant order regardless of numbering.  So:
+//   1. bounding box -> root quad                                       (Quad::new_containing)
+//   2. per body, the quadrant path by the SAME fp32 recursion -> 64-bit key, 2 bits per level,
+//      32 levels (Z-order == find_quadrant bit order, Quad.hpp:47-49)
+//   3. stable radix sort of (key, body)                                (cub::DeviceRadixSort)
+//   4. cells owned by each sorted body = the path cells that first appear with it; exclusive scan
+//      -> depth-first pre-order node array WITHOUT the reference's empty leaves (they contribute +-0)
+//   5. skip pointers (`next`) by binary search on the sorted keys; first child = index + 1
+//   6. centres of mass bottom-up, one launch per level, children summed in quadrant order
+//   7. walk: one thread per target (targets in Z-order for coherence), node records from L2.
+// Limits: bodies whose positions agree in all 32 levels are merged like the reference's coincident
+// bodies (`pos == existing_pos`, masses added in index order); the reference would subdivide
+// further if their positions differ beyond that depth.
+#include "kernels.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace nb {
+
+constexpr int BH_LEVELS = 32;
+
+struct BhRoot { float cx, cy, size; int pad; };
+
+// ---- 1. bounding box -------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bh_bbox_kernel(const float *__restrict__ posm, size_t n, BhRoot *root)
+{
+    float minx = 3.402823466e+38f, miny = minx, maxx = -minx, maxy = -minx;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const size_t g = blk_index(i, 0);
+        const float x = posm[g], y = posm[g + BLK];
+        minx = fminf(minx, x); maxx = fmaxf(maxx, x);
+        miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+    }
+    __shared__ float s[4][32];
+    for (int o = 16; o > 0; o >>= 1) {
+        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+        maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+        maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s[0][threadIdx.x >> 5] = minx; s[1][threadIdx.x >> 5] = miny;
+        s[2][threadIdx.x >> 5] = maxx; s[3][threadIdx.x >> 5] = maxy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            minx = fminf(minx, s[0][w]); miny = fminf(miny, s[1][w]);
+            maxx = fmaxf(maxx, s[2][w]); maxy = fmaxf(maxy, s[3][w]);
+        }
+        // Quad::new_containing, Quad.hpp:40-44: center = (min+max)*0.5f ; size = max(extent.x, extent.y)
+        root->cx = __fmul_rn(__fadd_rn(minx, maxx), 0.5f);
+        root->cy = __fmul_rn(__fadd_rn(miny, maxy), 0.5f);
+        root->size = fmaxf(__fsub_rn(maxx, minx), __fsub_rn(maxy, miny));
+    }
+}
+
+// Quad::find_quadrant (Quad.hpp:47-49) and Quad::into_quadrant (Quad.hpp:51-57), one level down.
+__device__ __forceinline__ unsigned bh_descend(float x, float y, float &cx, float &cy, float &size)
+{
+    const unsigned q = ((unsigned)(y > cy) << 1) | (unsigned)(x > cx);
+    const float ns = __fmul_rn(size, 0.5f);
+    cx = __fadd_rn(cx, __fmul_rn((q & 1u) ? 0.5f : -0.5f, ns));
+    cy = __fadd_rn(cy, __fmul_rn((q & 2u) ? 0.5f : -0.5f, ns));
+    size = ns;
+    return q;
+}
+
+// ---- 2. quadrant-path keys -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bh_keys_kernel(const float *__restrict__ posm, size_t n, const BhRoot *__restrict__ root,
+               unsigned long long *__restrict__ keys, unsigned *__restrict__ idx)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t g = blk_index(i, 0);
+    const float x = posm[g], y = posm[g + BLK];
+    float cx = root->cx, cy = root->cy, size = root->size;
+    unsigned long long k = 0;
+#pragma unroll 4
+    for (int l = 0; l < BH_LEVELS; ++l) k = (k << 2) | bh_descend(x, y, cx, cy, size);
+    keys[i] = k;
+    idx[i] = (unsigned)i;
+}
+
+__device__ __forceinline__ int lcp_levels(unsigned long long a, unsigned long long b)
+{
+    return a == b ? BH_LEVELS : (__clzll((long long)(a ^ b)) >> 1);
+}
+
+// ---- 4. cells owned by each sorted body ------------------------------------------------------------
+// first[s]..leaf[s] are the depths of the cells that first appear with sorted body s; duplicates
+// (identical key as the previous body) own nothing.
+__global__ void __launch_bounds__(256)
+bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned *__restrict__ count,
+                unsigned char *__restrict__ first, unsigned char *__restrict__ leaf)
+{
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const unsigned long long k = keys[s];
+    if (s > 0 && keys[s - 1] == k) { count[s] = 0; first[s] = 0; leaf[s] = 0; return; }
+    const int lp = (s > 0) ? lcp_levels(keys[s - 1], k) : -1;
+    size_t t = s + 1;
+    while (t < n && keys[t] == k) ++t;                       // skip the run of coincident bodies
+    const int ln = (t < n) ? lcp_levels(k, keys[t]) : -1;
+    const int leafd = (lp < 0 && ln < 0) ? 0 : max(lp, ln) + 1;   // a lone body is the root leaf
+    const int firstd = lp + 1;                                // s == 0 -> 0: owns the root
+    count[s] = (unsigned)(leafd - firstd + 1);
+    first[s] = (unsigned char)firstd;
+    leaf[s] = (unsigned char)leafd;
+}
+
+// node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag
+struct BhNodes {
+    float4 *data;        // x, y, mass, size*size
+    float4 *quad;        // cx, cy, size, unused (diagnostics / parity tests)
+    unsigned *next;
+    unsigned *meta;      // depth (low 8 bits) | leaf << 8
+};
+
+// ---- 5. emit the pre-order node array -------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restrict__ keys,
+               const unsigned *__restrict__ idx, size_t n, const BhRoot *__restrict__ root,
+               const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
+               const unsigned char *__restrict__ first, const unsigned char *__restrict__ leaf,
+               BhNodes nodes, unsigned cap)
+{
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || count[s] == 0) return;
+    const unsigned long long k = keys[s];
+    const unsigned body = idx[s];
+    const size_t g = blk_index(body, 0);
+    const float x = posm[g], y = posm[g + BLK];
+    // merged mass of coincident bodies, added in body-index order (stable sort) like insert() :56-60
+    float mass = posm[g + 3 * BLK];
+    for (size_t t = s + 1; t < n && keys[t] == k; ++t) mass = __fadd_rn(mass, posm[blk_index(idx[t], 0) + 3 * BLK]);
+    const int firstd = first[s], leafd = leaf[s];
+    const unsigned off = offs[s];
+    float cx = root->cx, cy = root->cy, size = root->size;
+    for (int d = 0; d <= leafd; ++d) {
+        if (d >= firstd) {
+            const unsigned c = off + (unsigned)(d - firstd);
+            if (c < cap) {
+                const bool is_leaf = (d == leafd);
+                nodes.data[c] = make_float4(is_leaf ? x : 0.f, is_leaf ? y : 0.f, is_leaf ? mass : 0.f, __fmul_rn(size, size));
+                nodes.quad[c] = make_float4(cx, cy, size, 0.f);
+                nodes.meta[c] = (unsigned)d | (is_leaf ? 256u : 0u);
+                // skip pointer: first sorted body after s whose depth-d prefix differs
+                unsigned nx = 0;
+                if (d > 0) {
+                    const int sh = 2 * (BH_LEVELS - d);
+                    const unsigned long long p = k >> sh;
+                    size_t lo = s + 1, hi = n;           // first j in (s, n) with (keys[j] >> sh) > p
+                    while (lo < hi) {
+                        const size_t mid = (lo + hi) >> 1;
+                        if ((keys[mid] >> sh) > p) hi = mid; else lo = mid + 1;
+                    }
+                    nx = (lo < n) ? offs[lo] : 0u;
+                }
+                nodes.next[c] = nx;
+            }
+        }
+        if (d < leafd) {
+            const unsigned q = (unsigned)(k >> (2 * (BH_LEVELS - 1 - d))) & 3u;
+            const float ns = __fmul_rn(size, 0.5f);
+            cx = __fadd_rn(cx, __fmul_rn((q & 1u) ? 0.5f : -0.5f, ns));
+            cy = __fadd_rn(cy, __fmul_rn((q & 2u) ? 0.5f : -0.5f, ns));
+            size = ns;
+        }
+    }
+}
+
+// ---- 6. centres of mass, one level per launch (Quadtree::propagate, :236-258) --------------------------
+__global__ void __launch_bounds__(256) bh_propagate_kernel(BhNodes nodes, unsigned m, int level)
+{
+    const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const unsigned meta = nodes.meta[c];
+    if ((meta & 255u) != (unsigned)level || (meta & 256u)) return;
+    const unsigned end = nodes.next[c];
+    float px = 0.f, py = 0.f, mass = 0.f;
+    unsigned ch = c + 1;                                   // children in quadrant order
+    for (int i = 0; i < 4 && ch != end && ch < m; ++i) {
+        if ((nodes.meta[ch] & 255u) != (unsigned)level + 1u) break;
+        const float4 d = nodes.data[ch];
+        px = __fadd_rn(px, __fmul_rn(d.x, d.z));
+        py = __fadd_rn(py, __fmul_rn(d.y, d.z));
+        mass = __fadd_rn(mass, d.z);
+        const unsigned nx = nodes.next[ch];
+        if (nx == 0) break;
+        ch = nx;
+    }
+    if (mass > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
+        const float inv = __fdiv_rn(1.0f, mass);
+        px = __fmul_rn(px, inv);
+        py = __fmul_rn(py, inv);
+    }
+    float4 d = nodes.data[c];
+    d.x = px; d.y = py; d.z = mass;
+    nodes.data[c] = d;
+}
+
+__device__ __forceinline__ float bh_quake(float number)
+{
+    const float y = __uint_as_float(0x5f3759dfu - (__float_as_uint(number) >> 1));
+    return __fmul_rn(y, __fsub_rn(1.5f, __fmul_rn(__fmul_rn(__fmul_rn(number, 0.5f), y), y)));
+}
+
+// ---- 7. walk (Quadtree::acc, :113-155) ------------------------------------------------------------------
+template <bool REFCOMPAT>
+__global__ void __launch_bounds__(128)
+bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
+               float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
+               float *__restrict__ accp)
+{
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const unsigned body = idx[s];                           // targets in Z-order: neighbouring threads walk alike
+    if (body < shard_start || body >= shard_start + shard_count) return;
+    const size_t g = blk_index(body, 0);
+    const float px = posm[g], py = posm[g + BLK];
+    float ax = 0.f, ay = 0.f;
+    unsigned i = 0;
+    do {
+        const float4 nd = nodes.data[i];
+        const float dx = __fsub_rn(nd.x, px), dy = __fsub_rn(nd.y, py);
+        const float d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const bool far = nd.w < __fmul_rn(d_sq, t_sq);
+        const bool is_leaf = (nodes.meta[i] & 256u) != 0u;
+        if (far || is_leaf) {
+            if ((far || fix_near_leaves) && d_sq > 0.f) {
+                float s3;
+                if (REFCOMPAT) {
+                    const float inv = bh_quake(__fadd_rn(d_sq, e_sq));
+                    s3 = __fmul_rn(nd.z, __fmul_rn(__fmul_rn(inv, inv), inv));
+                } else {
+                    const float inv = rsqrt_approx(d_sq + e_sq);
+                    s3 = nd.z * inv * inv * inv;
+                }
+                ax = __fadd_rn(ax, __fmul_rn(dx, s3));
+                ay = __fadd_rn(ay, __fmul_rn(dy, s3));
+            }
+            i = nodes.next[i];
+        } else {
+            i = i + 1;
+        }
+    } while (i != 0);
+    const size_t l = blk_index(body - shard_start, 0);
+    accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = 0.f;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+cudaError_t BhWorkspace::alloc(size_t n)
+{
+    cudaError_t e;
+    n_cap = n;
+    node_cap = (unsigned)std::min<size_t>(4 * n + 1024, 0x7fffffffu);
+#define BH_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
+    BH_ALLOC(root, sizeof(BhRoot))
+    BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
+    BH_ALLOC(count, (n + 1) * 4) BH_ALLOC(offs, (n + 1) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
+    BH_ALLOC(node_data, (size_t)node_cap * 16) BH_ALLOC(node_quad, (size_t)node_cap * 16)
+    BH_ALLOC(node_next, (size_t)node_cap * 4) BH_ALLOC(node_meta, (size_t)node_cap * 4)
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
+    temp_bytes = std::max(t1, t2);
+    BH_ALLOC(temp, temp_bytes)
+#undef BH_ALLOC
+    return cudaSuccess;
+}
+
+void BhWorkspace::release()
+{
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_next, node_meta, temp};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    *this = BhWorkspace();
+}
+
+static BhNodes bh_nodes(const BhWorkspace &w)
+{
+    BhNodes nd;
+    nd.data = (float4 *)w.node_data; nd.quad = (float4 *)w.node_quad;
+    nd.next = (unsigned *)w.node_next; nd.meta = (unsigned *)w.node_meta;
+    return nd;
+}
+
+// Build the tree of the first n bodies of `posm`.  Synchronises once (node count read-back).
+cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int *launches)
+{
+    if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
+    cudaError_t e;
+    const unsigned g256 = (unsigned)((n + 255) / 256), g128 = (unsigned)((n + 127) / 128);
+    bh_bbox_kernel<<<1, 1024, 0, st>>>(posm, n, (BhRoot *)root);
+    bh_keys_kernel<<<g256, 256, 0, st>>>(posm, n, (const BhRoot *)root, (unsigned long long *)keys_in, (unsigned *)idx_in);
+    size_t tb = temp_bytes;
+    if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
+                                             (const unsigned *)idx_in, (unsigned *)idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
+    bh_count_kernel<<<g256, 256, 0, st>>>((const unsigned long long *)keys, n, (unsigned *)count, (unsigned char *)first, (unsigned char *)leaf);
+    if ((e = cudaMemsetAsync((unsigned *)count + n, 0, 4, st)) != cudaSuccess) return e;
+    tb = temp_bytes;
+    if ((e = cub::DeviceScan::ExclusiveSum(temp, tb, (const unsigned *)count, (unsigned *)offs, (int)n + 1, st)) != cudaSuccess) return e;
+    unsigned m = 0;
+    if ((e = cudaMemcpyAsync(&m, (unsigned *)offs + n, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (m > node_cap) return cudaErrorMemoryAllocation;      // pathological depth: more cells than reserved
+    n_nodes = m;
+    bh_emit_kernel<<<g128, 128, 0, st>>>(posm, (const unsigned long long *)keys, (const unsigned *)idx, n, (const BhRoot *)root,
+                                         (const unsigned *)offs, (const unsigned *)count, (const unsigned char *)first,
+                                         (const unsigned char *)leaf, bh_nodes(*this), node_cap);
+    const unsigned gm = (m + 255) / 256;
+    for (int level = BH_LEVELS - 1; level >= 0; --level) bh_propagate_kernel<<<gm, 256, 0, st>>>(bh_nodes(*this), m, level);
+    if (launches) *launches += 5 + BH_LEVELS + 3;            // own kernels + the sort/scan passes (counted as 3)
+    return cudaGetLastError();
+}
+
+cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
+                              size_t shard_start, size_t shard_count, float *accp, cudaStream_t st)
+{
+    const unsigned g = (unsigned)((n + 127) / 128);
+    const float t_sq = theta * theta, e_sq = eps * eps;       // Quadtree ctor, Quadtree.hpp:19
+    if (refcompat)
+        bh_walk_kernel<true><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
+                                                fix_near_leaves ? 1 : 0, shard_start, shard_count, accp);
+    else
+        bh_walk_kernel<false><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
+                                                 fix_near_leaves ? 1 : 0, shard_start, shard_count, accp);
+    return cudaGetLastError();
+}
+
+// node array in walk order for the parity tests: f6 = (x, y, mass, cx, cy, size), u2 = (next, depth | leaf<<8)
+cudaError_t BhWorkspace::download_nodes(float *f6, unsigned *u2, size_t cap, cudaStream_t st)
+{
+    const size_t m = std::min<size_t>(cap, n_nodes);
+    std::vector<float4> d(m), q(m);
+    std::vector<unsigned> nx(m), me(m);
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d.data(), node_data, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(q.data(), node_quad, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(nx.data(), node_next, m * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(me.data(), node_meta, m * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    for (size_t i = 0; i < m; ++i) {
+        f6[6 * i + 0] = d[i].x; f6[6 * i + 1] = d[i].y; f6[6 * i + 2] = d[i].z;
+        f6[6 * i + 3] = q[i].x; f6[6 * i + 4] = q[i].y; f6[6 * i + 5] = q[i].z;
+        u2[2 * i + 0] = nx[i]; u2[2 * i + 1] = me[i];
+    }
+    return cudaSuccess;
+}
+
+} // namespace nb

@@ -1,6 +1,8 @@
 // kernels.h -- launch interface between the C-ABI layer (nbody_gpu.cu) and the kernel files.
 #pragma once
 #include "common.cuh"
+#include <algorithm>
+#include <vector>
 
 namespace nb {
 
@@ -88,5 +90,22 @@ cudaError_t launch_unpack_f64(double *pos3, double *vel3, double *acc3, size_t n
 // fp64 diagnostics: out[0]=K, out[1]=W (pairs counted twice, caller halves), out[2..4]=P
 cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, size_t shard_start,
                           size_t shard_count, double eps2, bool f64, double *out5, cudaStream_t st);
+
+// Barnes-Hut path (barnes_hut.cu): per-GPU workspace holding sorted keys and the pre-order node array
+struct BhWorkspace {
+    size_t n_cap = 0;
+    unsigned node_cap = 0, n_nodes = 0;
+    void *root = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
+    void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
+    void *node_data = nullptr, *node_quad = nullptr, *node_next = nullptr, *node_meta = nullptr;
+    void *temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t alloc(size_t n);
+    void release();
+    cudaError_t build(const float *posm, size_t n, cudaStream_t st, int *launches);
+    cudaError_t walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
+                     size_t shard_start, size_t shard_count, float *accp, cudaStream_t st);
+    cudaError_t download_nodes(float *f6, unsigned *u2, size_t cap, cudaStream_t st);
+};
 
 } // namespace nb

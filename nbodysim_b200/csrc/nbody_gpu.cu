@@ -46,6 +46,7 @@ struct Dev {
     int nslots = 0;
     bool fused = false;
     int force_ctas = 0;
+    BhWorkspace bh;               // Barnes-Hut path only
 };
 
 } // namespace
@@ -55,6 +56,7 @@ struct nbody_ctx {
     size_t n = 0, n_padded = 0;
     int world = 1;               // total GPUs
     bool f64 = false;
+    bool bh = false;             // force_algo == NBODY_FORCE_BARNES_HUT
     bool uniform = false;        // every massive body has the same mass: 11-op force kernel
     float uniform_mass = 0.f;
     size_t esz = 4;
@@ -146,6 +148,12 @@ int plan_device(nbody_ctx *c, Dev &d)
 
     struct Seg { int b0, nb; bool remote; };
     std::vector<Seg> segs;
+    if (c->bh) { // one tree over all sources, one walk launch, one partial slot
+        d.plan.push_back({0, nblk, 1, 0, c->world > 1});
+        d.nslots = 1;
+        d.force_ctas = (int)((c->n + 127) / 128);
+        return NBODY_OK;
+    }
     if (c->world == 1 || refc) {
         segs.push_back({0, nblk, c->world > 1});
     } else {
@@ -193,6 +201,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaMalloc(&d.accp, shard * (size_t)std::max(1, d.nslots)));
     CU(cudaMalloc(&d.aos, ctx->n_padded * sizeof(nbody_body_t)));
     CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
+    if (ctx->bh) CU(d.bh.alloc(ctx->n));
     return NBODY_OK;
 }
 
@@ -254,7 +263,16 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         const bool prof = profile && (&d == &ctx->devs[0]);
         if (prof) CU(cudaEventRecord(d.ev_t[0], d.stream));
         bool waited = false;
+        if (ctx->bh) {
+            if (d.gathered_pending) { CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0)); waited = true; }
+            int nl = 0;
+            CU(d.bh.build((const float *)d.posm[d.cur], ctx->n, d.stream, &nl));
+            CU(d.bh.walk((const float *)d.posm[d.cur], ctx->n, ctx->p.theta, ctx->p.eps, refc, ctx->p.bh_fix_near_leaves != 0,
+                         d.shard_start, d.shard_count, (float *)d.accp, d.stream));
+            ctx->launches += (unsigned long long)nl + 1;
+        }
         for (const Range &r : d.plan) {
+            if (ctx->bh) break;
             if (r.remote && d.gathered_pending && !waited) {
                 CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0));
                 waited = true;
@@ -288,7 +306,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             I.n_iblk_shard = (int)(d.shard_count / BLK);
             I.acc_only = acc_only ? 1 : 0;
             I.n_real = (long long)ctx->n;
-            const bool fastpath = !ctx->f64 && !refc;
+            const bool fastpath = !ctx->f64 && !refc && !ctx->bh;
             I.acc_scale = (fastpath && ctx->uniform) ? ctx->p.G * ctx->uniform_mass : ctx->p.G;
             I.ip = make_ip(ctx, dt);
             if (d.fused && acc_only) {
@@ -355,6 +373,7 @@ void free_all(nbody_ctx *c)
         if (d.accp) cudaFree(d.accp);
         if (d.aos) cudaFree(d.aos);
         if (d.energy5) cudaFree(d.energy5);
+        d.bh.release();
         if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
         if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
         for (int k = 0; k < 4; ++k) if (d.ev_t[k]) cudaEventDestroy(d.ev_t[k]);
@@ -414,8 +433,12 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         set_err(nullptr, "nbody_gpu_init: invalid parameter");
         return NBODY_EINVAL;
     }
-    if (p->force_algo != NBODY_FORCE_ALLPAIRS) {
-        set_err(nullptr, "nbody_gpu_init: force_algo %d not available in this build", p->force_algo);
+    if (p->force_algo != NBODY_FORCE_ALLPAIRS && p->force_algo != NBODY_FORCE_BARNES_HUT) {
+        set_err(nullptr, "nbody_gpu_init: unknown force_algo %d", p->force_algo);
+        return NBODY_EINVAL;
+    }
+    if (p->force_algo == NBODY_FORCE_BARNES_HUT && (p->dims != 2 || p->precision != NBODY_PRECISION_F32)) {
+        set_err(nullptr, "nbody_gpu_init: the Barnes-Hut path is the reference's 2-D fp32 quadtree (dims=2, f32)");
         return NBODY_EINVAL;
     }
     const int nlocal = std::max(1, p->ngpus);
@@ -438,12 +461,13 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     ctx->n = n;
     ctx->world = world;
     ctx->f64 = (p->precision == NBODY_PRECISION_F64);
+    ctx->bh = (p->force_algo == NBODY_FORCE_BARNES_HUT);
     ctx->esz = ctx->f64 ? 8 : 4;
     {
         const size_t per = (size_t)TARGET_GRANULE * (size_t)world;
         ctx->n_padded = ((n + per - 1) / per) * per;
     }
-    if (!ctx->f64 && p->rsqrt_mode == NBODY_RSQRT_FAST && p->force_variant != 0) {
+    if (!ctx->f64 && !ctx->bh && p->rsqrt_mode == NBODY_RSQRT_FAST && p->force_variant != 0) {
         // uniform-mass form: valid when every body has the same positive mass (bit-equal), so that
         // sum_j m_j f(r_ij) == m * sum_j f(r_ij) term for term.  force_variant = 0 disables it.
         const float m0 = bodies[0].mass;
@@ -688,11 +712,24 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->ctas_per_sm = ctx->ctas_per_sm;
     info->fused = d0.fused ? 1 : 0;
     info->uniform_mass = ctx->uniform ? 1 : 0;
+    info->bh_nodes = ctx->bh ? d0.bh.n_nodes : 0;
     info->graph = 0;
     info->kernel_launches = ctx->launches;
     info->interactions = ctx->interactions;
     info->last_force_ms = ctx->last_force_ms;
     info->last_integ_ms = ctx->last_integ_ms;
+    return NBODY_OK;
+}
+
+int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f6, uint32_t *u2, size_t cap, size_t *count)
+{
+    if (!ctx || !count) return NBODY_EINVAL;
+    if (!ctx->bh) return NBODY_ESTATE;
+    Dev &d = ctx->devs[0];
+    *count = d.bh.n_nodes;
+    if (cap == 0 || !f6 || !u2) return NBODY_OK;
+    CU(cudaSetDevice(d.device));
+    CU(d.bh.download_nodes(f6, u2, cap, d.stream));
     return NBODY_OK;
 }
 
@@ -733,6 +770,6 @@ const char *nbody_gpu_strerror(int code)
 
 const char *nbody_gpu_last_error(const nbody_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
 
-const char *nbody_gpu_version(void) { return "nbody_gpu 0.2 (sm_100a; all-pairs f32 fast[plain|uniform-mass]/refcompat, f64)"; }
+const char *nbody_gpu_version(void) { return "nbody_gpu 0.3 (sm_100a; all-pairs f32 fast[plain|uniform-mass]/refcompat, f64; Barnes-Hut quadtree)"; }
 
 } // extern "C"

@@ -95,6 +95,18 @@ def main():
     it = clean(it)
     np.savez_compressed(os.path.join(OUT, "iterate_extras256.npz"), bodies=ex, dt=np.float32(0.05), nsteps=3,
                         end_pos=it["pos"], end_vel=it["vel"])
+    # 7. Barnes-Hut: the reference's shipped algorithm (Quadtree::build + acc, theta=1, eps=1) and its
+    #    real step Simulation::iterate (BH + clamp + boundary + drift; radius=0 so collide() is inert).
+    bh = ic.spinning_disc(2000, seed=31, scale=140.0, spin=0.3, mass=1.0)
+    bh["mass"] = np.random.default_rng(31).uniform(0.05, 3.0, 2000).astype(np.float32)
+    acc_bh, nnodes = O.ref_bh_acc(bh, 1.0, 1.0)
+    acc_bh05, _ = O.ref_bh_acc(bh, 0.5, 1.0)
+    it = bh.copy()
+    R.ref_iterate(it.ctypes.data, 2000, 1.0, 1.0, 0.01, 10)
+    it = clean(it)
+    np.savez_compressed(os.path.join(OUT, "bh2000.npz"), bodies=bh, theta=np.float32(1.0), eps=np.float32(1.0),
+                        dt=np.float32(0.01), nsteps=10, acc=acc_bh, acc_theta05=acc_bh05, nnodes=nnodes,
+                        end_pos=it["pos"], end_vel=it["vel"], end_acc=it["acc"])
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")
