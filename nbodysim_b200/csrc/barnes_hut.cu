@@ -26,6 +26,7 @@
 // bodies (`pos == existing_pos`, masses added in index order); the reference would subdivide
 // further if their positions differ beyond that depth.
 #include "kernels.h"
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -36,16 +37,35 @@ constexpr int BH_LEVELS = 32;
 struct BhRoot { float cx, cy, size; int pad; };
 
 // ---- 1. bounding box -------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) bh_bbox_kernel(const float *__restrict__ posm, size_t n, BhRoot *root)
+// floats map to unsigned keys whose integer order equals the float order, so min/max reduce with
+// integer atomics; box[0..3] = min x, min y, max x, max y (encoded), reset by bh_reset_kernel.
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void bh_reset_kernel(unsigned *box, unsigned *count_tail)
+{
+    box[0] = box[1] = 0xffffffffu;   // running minima
+    box[2] = box[3] = 0u;            // running maxima
+    count_tail[0] = 0;               // count[n]   : terminates the exclusive scan
+    count_tail[1] = 0;               // count[n+1] : deepest leaf level
+}
+
+__global__ void __launch_bounds__(256) bh_bbox_kernel(const float *__restrict__ posm, size_t n, unsigned *box)
 {
     float minx = 3.402823466e+38f, miny = minx, maxx = -minx, maxy = -minx;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t g = blk_index(i, 0);
         const float x = posm[g], y = posm[g + BLK];
         minx = fminf(minx, x); maxx = fmaxf(maxx, x);
         miny = fminf(miny, y); maxy = fmaxf(maxy, y);
     }
-    __shared__ float s[4][32];
     for (int o = 16; o > 0; o >>= 1) {
         minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o));
         miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o));
@@ -53,20 +73,18 @@ __global__ void __launch_bounds__(1024) bh_bbox_kernel(const float *__restrict__
         maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        s[0][threadIdx.x >> 5] = minx; s[1][threadIdx.x >> 5] = miny;
-        s[2][threadIdx.x >> 5] = maxx; s[3][threadIdx.x >> 5] = maxy;
+        atomicMin(&box[0], f2ord(minx)); atomicMin(&box[1], f2ord(miny));
+        atomicMax(&box[2], f2ord(maxx)); atomicMax(&box[3], f2ord(maxy));
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-            minx = fminf(minx, s[0][w]); miny = fminf(miny, s[1][w]);
-            maxx = fmaxf(maxx, s[2][w]); maxy = fmaxf(maxy, s[3][w]);
-        }
-        // Quad::new_containing, Quad.hpp:40-44: center = (min+max)*0.5f ; size = max(extent.x, extent.y)
-        root->cx = __fmul_rn(__fadd_rn(minx, maxx), 0.5f);
-        root->cy = __fmul_rn(__fadd_rn(miny, maxy), 0.5f);
-        root->size = fmaxf(__fsub_rn(maxx, minx), __fsub_rn(maxy, miny));
-    }
+}
+
+__global__ void bh_root_kernel(const unsigned *box, BhRoot *root)
+{
+    const float minx = ord2f(box[0]), miny = ord2f(box[1]), maxx = ord2f(box[2]), maxy = ord2f(box[3]);
+    // Quad::new_containing, Quad.hpp:40-44: center = (min+max)*0.5f ; size = max(extent.x, extent.y)
+    root->cx = __fmul_rn(__fadd_rn(minx, maxx), 0.5f);
+    root->cy = __fmul_rn(__fadd_rn(miny, maxy), 0.5f);
+    root->size = fmaxf(__fsub_rn(maxx, minx), __fsub_rn(maxy, miny));
 }
 
 // Quad::find_quadrant (Quad.hpp:47-49) and Quad::into_quadrant (Quad.hpp:51-57), one level down.
@@ -107,7 +125,7 @@ __device__ __forceinline__ int lcp_levels(unsigned long long a, unsigned long lo
 // (identical key as the previous body) own nothing.
 __global__ void __launch_bounds__(256)
 bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned *__restrict__ count,
-                unsigned char *__restrict__ first, unsigned char *__restrict__ leaf)
+                unsigned char *__restrict__ first, unsigned char *__restrict__ leaf, unsigned *__restrict__ max_depth)
 {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -122,6 +140,8 @@ bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned 
     count[s] = (unsigned)(leafd - firstd + 1);
     first[s] = (unsigned char)firstd;
     leaf[s] = (unsigned char)leafd;
+    // deepest leaf of the tree: bounds the number of propagate launches (warp-aggregated atomic)
+    if ((unsigned)leafd > *max_depth) atomicMax(max_depth, (unsigned)leafd);   // racy pre-check only skips no-ops
 }
 
 // node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag
@@ -185,18 +205,17 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
     }
 }
 
-// ---- 6. centres of mass, one level per launch (Quadtree::propagate, :236-258) --------------------------
-__global__ void __launch_bounds__(256) bh_propagate_kernel(BhNodes nodes, unsigned m, int level)
+// ---- 6. centres of mass (Quadtree::propagate, :236-258) -------------------------------------------------
+// One cooperative launch: levels deepest-first with a grid-wide barrier between levels.  Sorted body s
+// owns the consecutive cells offs[s] .. offs[s]+count[s]-1 at depths first[s] .. leaf[s], so the branch
+// cell of level L on its chain is found by index arithmetic -- no per-level node lists.
+__device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned c, unsigned m, unsigned level)
 {
-    const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m) return;
-    const unsigned meta = nodes.meta[c];
-    if ((meta & 255u) != (unsigned)level || (meta & 256u)) return;
     const unsigned end = nodes.next[c];
     float px = 0.f, py = 0.f, mass = 0.f;
     unsigned ch = c + 1;                                   // children in quadrant order
     for (int i = 0; i < 4 && ch != end && ch < m; ++i) {
-        if ((nodes.meta[ch] & 255u) != (unsigned)level + 1u) break;
+        if ((nodes.meta[ch] & 255u) != level + 1u) break;
         const float4 d = nodes.data[ch];
         px = __fadd_rn(px, __fmul_rn(d.x, d.z));
         py = __fadd_rn(py, __fmul_rn(d.y, d.z));
@@ -215,6 +234,26 @@ __global__ void __launch_bounds__(256) bh_propagate_kernel(BhNodes nodes, unsign
     nodes.data[c] = d;
 }
 
+__global__ void __launch_bounds__(256)
+bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned char *__restrict__ first,
+                    const unsigned char *__restrict__ leaf, const unsigned *__restrict__ count, unsigned cap)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const unsigned m = min(offs[n], cap);
+    const int dmax = (int)min(count[n + 1], (unsigned)BH_LEVELS);
+    for (int level = dmax - 1; level >= 0; --level) {
+        for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (size_t)gridDim.x * blockDim.x) {
+            const int f = first[s], l = leaf[s];
+            if (count[s] != 0 && f <= level && level < l) {
+                const unsigned c = offs[s] + (unsigned)(level - f);
+                if (c < m) bh_propagate_cell(nodes, c, m, (unsigned)level);
+            }
+        }
+        __threadfence();
+        grid.sync();
+    }
+}
+
 __device__ __forceinline__ float bh_quake(float number)
 {
     const float y = __uint_as_float(0x5f3759dfu - (__float_as_uint(number) >> 1));
@@ -226,7 +265,7 @@ template <bool REFCOMPAT>
 __global__ void __launch_bounds__(128)
 bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-               float *__restrict__ accp)
+               float *__restrict__ accp, unsigned cap)
 {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -259,7 +298,7 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
         } else {
             i = i + 1;
         }
-    } while (i != 0);
+    } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (reported by node_count)
     const size_t l = blk_index(body - shard_start, 0);
     accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = 0.f;
 }
@@ -271,9 +310,9 @@ cudaError_t BhWorkspace::alloc(size_t n)
     n_cap = n;
     node_cap = (unsigned)std::min<size_t>(4 * n + 1024, 0x7fffffffu);
 #define BH_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
-    BH_ALLOC(root, sizeof(BhRoot))
+    BH_ALLOC(root, sizeof(BhRoot)) BH_ALLOC(box, 16)
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
-    BH_ALLOC(count, (n + 1) * 4) BH_ALLOC(offs, (n + 1) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
+    BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
     BH_ALLOC(node_data, (size_t)node_cap * 16) BH_ALLOC(node_quad, (size_t)node_cap * 16)
     BH_ALLOC(node_next, (size_t)node_cap * 4) BH_ALLOC(node_meta, (size_t)node_cap * 4)
     size_t t1 = 0, t2 = 0;
@@ -282,13 +321,20 @@ cudaError_t BhWorkspace::alloc(size_t n)
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
     temp_bytes = std::max(t1, t2);
     BH_ALLOC(temp, temp_bytes)
+    {   // co-resident grid size for the cooperative propagate kernel
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_propagate_kernel, 256, 0);
+        coop_blocks = std::max(1, sms * std::max(1, std::min(per_sm, 4)));
+    }
 #undef BH_ALLOC
     return cudaSuccess;
 }
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_next, node_meta, temp};
+    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_next, node_meta, temp};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -301,33 +347,56 @@ static BhNodes bh_nodes(const BhWorkspace &w)
     return nd;
 }
 
-// Build the tree of the first n bodies of `posm`.  Synchronises once (node count read-back).
+// Build the tree of the first n bodies of `posm`.  Fully asynchronous (no host read-back): the node count
+// stays on the device (offs[n]); n_nodes is fetched lazily by node_count().
 cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int *launches)
 {
     if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
     cudaError_t e;
     const unsigned g256 = (unsigned)((n + 255) / 256), g128 = (unsigned)((n + 127) / 128);
-    bh_bbox_kernel<<<1, 1024, 0, st>>>(posm, n, (BhRoot *)root);
+    unsigned *cnt = (unsigned *)count;
+    bh_reset_kernel<<<1, 1, 0, st>>>((unsigned *)box, cnt + n);
+    bh_bbox_kernel<<<std::min(g256, 4u * 148u), 256, 0, st>>>(posm, n, (unsigned *)box);
+    bh_root_kernel<<<1, 1, 0, st>>>((const unsigned *)box, (BhRoot *)root);
     bh_keys_kernel<<<g256, 256, 0, st>>>(posm, n, (const BhRoot *)root, (unsigned long long *)keys_in, (unsigned *)idx_in);
     size_t tb = temp_bytes;
     if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
                                              (const unsigned *)idx_in, (unsigned *)idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
-    bh_count_kernel<<<g256, 256, 0, st>>>((const unsigned long long *)keys, n, (unsigned *)count, (unsigned char *)first, (unsigned char *)leaf);
-    if ((e = cudaMemsetAsync((unsigned *)count + n, 0, 4, st)) != cudaSuccess) return e;
+    bh_count_kernel<<<g256, 256, 0, st>>>((const unsigned long long *)keys, n, cnt, (unsigned char *)first,
+                                          (unsigned char *)leaf, cnt + n + 1);
     tb = temp_bytes;
     if ((e = cub::DeviceScan::ExclusiveSum(temp, tb, (const unsigned *)count, (unsigned *)offs, (int)n + 1, st)) != cudaSuccess) return e;
-    unsigned m = 0;
-    if ((e = cudaMemcpyAsync(&m, (unsigned *)offs + n, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    if (m > node_cap) return cudaErrorMemoryAllocation;      // pathological depth: more cells than reserved
-    n_nodes = m;
     bh_emit_kernel<<<g128, 128, 0, st>>>(posm, (const unsigned long long *)keys, (const unsigned *)idx, n, (const BhRoot *)root,
                                          (const unsigned *)offs, (const unsigned *)count, (const unsigned char *)first,
                                          (const unsigned char *)leaf, bh_nodes(*this), node_cap);
-    const unsigned gm = (m + 255) / 256;
-    for (int level = BH_LEVELS - 1; level >= 0; --level) bh_propagate_kernel<<<gm, 256, 0, st>>>(bh_nodes(*this), m, level);
-    if (launches) *launches += 5 + BH_LEVELS + 3;            // own kernels + the sort/scan passes (counted as 3)
+    {
+        BhNodes nd = bh_nodes(*this);
+        size_t nn = n;
+        const unsigned *po = (const unsigned *)offs, *pc = (const unsigned *)count;
+        const unsigned char *pf = (const unsigned char *)first, *pl = (const unsigned char *)leaf;
+        unsigned cap = node_cap;
+        void *args[] = {&nd, &nn, &po, &pf, &pl, &pc, &cap};
+        const unsigned grid = std::min(g256, (unsigned)coop_blocks);
+        if ((e = cudaLaunchCooperativeKernel((void *)bh_propagate_kernel, dim3(grid), dim3(256), args, 0, st)) != cudaSuccess) return e;
+    }
+    count_valid = false;
+    if (launches) *launches += 7 + 3;                        // own kernels + the sort/scan passes (counted as 3)
     return cudaGetLastError();
+}
+
+// number of cells of the last tree (synchronises the stream once, then cached)
+cudaError_t BhWorkspace::node_count(size_t n, cudaStream_t st, unsigned *out)
+{
+    if (!count_valid) {
+        unsigned m = 0;
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(&m, (unsigned *)offs + n, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        n_nodes = m;
+        count_valid = true;
+    }
+    *out = n_nodes;
+    return n_nodes > node_cap ? cudaErrorMemoryAllocation : cudaSuccess;   // pathological depth: more cells than reserved
 }
 
 cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
@@ -337,17 +406,17 @@ cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float ep
     const float t_sq = theta * theta, e_sq = eps * eps;       // Quadtree ctor, Quadtree.hpp:19
     if (refcompat)
         bh_walk_kernel<true><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
-                                                fix_near_leaves ? 1 : 0, shard_start, shard_count, accp);
+                                                fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, node_cap);
     else
         bh_walk_kernel<false><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
-                                                 fix_near_leaves ? 1 : 0, shard_start, shard_count, accp);
+                                                 fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, node_cap);
     return cudaGetLastError();
 }
 
 // node array in walk order for the parity tests: f6 = (x, y, mass, cx, cy, size), u2 = (next, depth | leaf<<8)
 cudaError_t BhWorkspace::download_nodes(float *f6, unsigned *u2, size_t cap, cudaStream_t st)
 {
-    const size_t m = std::min<size_t>(cap, n_nodes);
+    const size_t m = std::min<size_t>(std::min<size_t>(cap, n_nodes), node_cap);
     std::vector<float4> d(m), q(m);
     std::vector<unsigned> nx(m), me(m);
     cudaError_t e;

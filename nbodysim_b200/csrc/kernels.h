@@ -95,12 +95,15 @@ cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, si
 struct BhWorkspace {
     size_t n_cap = 0;
     unsigned node_cap = 0, n_nodes = 0;
-    void *root = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
+    void *root = nullptr, *box = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
     void *node_data = nullptr, *node_quad = nullptr, *node_next = nullptr, *node_meta = nullptr;
     void *temp = nullptr;
     size_t temp_bytes = 0;
+    int coop_blocks = 148;
+    bool count_valid = false;
     cudaError_t alloc(size_t n);
+    cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);
     void release();
     cudaError_t build(const float *posm, size_t n, cudaStream_t st, int *launches);
     cudaError_t walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,

@@ -712,7 +712,12 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->ctas_per_sm = ctx->ctas_per_sm;
     info->fused = d0.fused ? 1 : 0;
     info->uniform_mass = ctx->uniform ? 1 : 0;
-    info->bh_nodes = ctx->bh ? d0.bh.n_nodes : 0;
+    if (ctx->bh) {
+        unsigned m = 0;
+        cudaSetDevice(ctx->devs[0].device);
+        ctx->devs[0].bh.node_count(ctx->n, ctx->devs[0].stream, &m);
+        info->bh_nodes = m;
+    }
     info->graph = 0;
     info->kernel_launches = ctx->launches;
     info->interactions = ctx->interactions;
@@ -726,9 +731,11 @@ int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f6, uint32_t *u2, size_t cap, size
     if (!ctx || !count) return NBODY_EINVAL;
     if (!ctx->bh) return NBODY_ESTATE;
     Dev &d = ctx->devs[0];
-    *count = d.bh.n_nodes;
-    if (cap == 0 || !f6 || !u2) return NBODY_OK;
     CU(cudaSetDevice(d.device));
+    unsigned m = 0;
+    CU(d.bh.node_count(ctx->n, d.stream, &m));
+    *count = m;
+    if (cap == 0 || !f6 || !u2) return NBODY_OK;
     CU(d.bh.download_nodes(f6, u2, cap, d.stream));
     return NBODY_OK;
 }

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Barnes-Hut path: GPU (tree build + walk + integrator, through the C ABI) next to the reference's
+own Simulation::iterate on the host cores (oracle/_ref fast build = the reference's flags), at the
+reference's shipped size N=25,000 and larger.  Not the headline metric (that is all-pairs, bench.py);
+this measures the reference's REAL algorithm.  Prints one JSON line per N."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as O  # noqa: E402
+from nbodysim_b200 import Simulation, capi, ic  # noqa: E402
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [25000, 100000, 1000000]
+    R = O.reference("fast")
+    for n in sizes:
+        b = ic.spinning_disc(n, seed=3, scale=100.0 * np.sqrt(n / 1024.0), spin=0.3 / np.sqrt(n / 1024.0))
+        b["mass"] = np.random.default_rng(3).uniform(0.1, 3.0, n).astype(np.float32)
+        row = {"n": n, "theta": 1.0, "eps": 1.0}
+        for mode, name in ((capi.RSQRT_REFCOMPAT, "refcompat"), (capi.RSQRT_FAST, "fast")):
+            with Simulation(b, dt=0.01, force_algo=capi.FORCE_BARNES_HUT, dims=2, theta=1.0, eps=1.0, rsqrt_mode=mode,
+                            integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
+                s.step(3); s.sync()
+                f, i = [], []
+                for _ in range(10):
+                    s.profile_next_step(True)
+                    s.step(1)
+                    inf = s.info()
+                    f.append(inf["last_force_ms"]); i.append(inf["last_integ_ms"])
+                t0 = time.perf_counter(); s.step(20); s.sync(); wall = (time.perf_counter() - t0) / 20
+                row[f"gpu_{name}_force_ms"] = float(np.median(f))
+                row[f"gpu_{name}_integ_ms"] = float(np.median(i))
+                row[f"gpu_{name}_step_wall_ms"] = 1e3 * wall
+                row["bh_nodes"] = inf["bh_nodes"]
+        if R is not None and n <= 200000:
+            c = b.copy()
+            R.ref_iterate(c.ctypes.data, n, 1.0, 1.0, 0.01, 1)      # constructs the Simulation singleton + warm-up
+            k = 5 if n <= 50000 else 2
+            t0 = time.perf_counter()
+            R.ref_iterate(c.ctypes.data, n, 1.0, 1.0, 0.01, k)
+            row["cpu_reference_iterate_ms"] = 1e3 * (time.perf_counter() - t0) / k
+            row["cpu_threads"] = os.cpu_count()
+            row["speedup_vs_cpu_reference"] = row["cpu_reference_iterate_ms"] / row["gpu_refcompat_step_wall_ms"]
+        print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
