@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
-    ap.add_argument("--n", type=int, default=0, help="override body count (default 1M at 1 GPU, 4M at >1)")
+    ap.add_argument("--bodies", dest="n", type=int, default=0,
+                    help="override body count (default 1M at 1 GPU, 4M at >1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")

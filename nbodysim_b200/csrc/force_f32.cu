@@ -112,10 +112,10 @@ force_f32_refcompat_kernel(const float *__restrict__ posm, float *__restrict__ a
 // ---- host-side launchers ------------------------------------------------------------------------
 using FastRing = Ring<BLK_ELEMS, FAST_STAGE_BLKS>;
 
-template <int FORM, bool GUARD, bool FUSE>
-static cudaError_t launch_fast_t(const ForceLaunch &L, cudaStream_t st)
+template <int FORM, bool GUARD, bool FUSE, int DIMS>
+static cudaError_t launch_fast_d(const ForceLaunch &L, cudaStream_t st)
 {
-    auto kern = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM, GUARD, FUSE>;
+    auto kern = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM, GUARD, FUSE, DIMS>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
@@ -131,6 +131,12 @@ static cudaError_t launch_fast_t(const ForceLaunch &L, cudaStream_t st)
     a.posm_next = (float *)L.posm_next; a.vel = (float *)L.vel; a.acc = (float *)L.acc; a.ip = L.ip;
     kern<<<force_f32_fast_grid(L), FAST_THREADS, FastRing::SMEM, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int FORM, bool GUARD, bool FUSE>
+static cudaError_t launch_fast_t(const ForceLaunch &L, cudaStream_t st)
+{
+    return L.dims == 2 ? launch_fast_d<FORM, GUARD, FUSE, 2>(L, st) : launch_fast_d<FORM, GUARD, FUSE, 3>(L, st);
 }
 
 int force_f32_fast_grid(const ForceLaunch &L) { return (L.n_iblk / FAST_TILE_BLKS) * L.splits; }

@@ -24,6 +24,7 @@ struct IntegParams {
 // [j_blk0, j_blk0 + j_nblk) cut into `splits` chunks; CTA (tile, s) writes its partial sum into
 // partial slot slot0 + s.  Slots are summed in index order by the integrator (deterministic).
 struct ForceLaunch {
+    int dims;                // fast kernel: 2 = planar data (z == 0 everywhere): z operations dropped
     int uniform_mass;        // fast kernel: 1 = every massive source has the same mass (11-op form)
     float acc_scale;         // fused epilogue: G (plain) or G*m (uniform)
     const void *posm;        // blocked (x,y,z,m), float or double
@@ -78,7 +79,7 @@ cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st);
 
 // AoS (reference Body, 64 B) <-> blocked SoA
 cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,
-                        size_t shard_count, void *posm, void *vel, void *acc, bool f64,
+                        size_t shard_count, void *posm, void *vel, void *acc, bool f64, int dims,
                         cudaStream_t st);
 cudaError_t launch_unpack(void *aos, size_t n, size_t shard_start, size_t shard_count,
                           const void *posm, const void *vel, const void *acc, bool f64,

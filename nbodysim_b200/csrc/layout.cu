@@ -11,7 +11,7 @@ namespace nb {
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_kernel(const nbody_body_t *__restrict__ aos, size_t n, size_t n_padded, size_t shard_start,
-            size_t shard_count, T *__restrict__ posm, T *__restrict__ vel, T *__restrict__ acc)
+            size_t shard_count, T *__restrict__ posm, T *__restrict__ vel, T *__restrict__ acc, int dims)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_padded) return;
@@ -22,6 +22,8 @@ pack_kernel(const nbody_body_t *__restrict__ aos, size_t n, size_t n_padded, siz
     if (i < n) {
         const float4 *r = reinterpret_cast<const float4 *>(aos + i);
         p = r[0]; v = r[1]; a = r[2]; mr = r[3];
+        // 2-D callers (the reference) leave the Vec2 tail padding indeterminate: never read z from it
+        if (dims == 2) { p.z = 0.f; v.z = 0.f; a.z = 0.f; }
     }
     const size_t g = blk_index(i, 0);
     posm[g] = (T)p.x; posm[g + BLK] = (T)p.y; posm[g + 2 * BLK] = (T)p.z;
@@ -65,18 +67,18 @@ unpack_f64_kernel(double *__restrict__ pos3, double *__restrict__ vel3, double *
 }
 
 cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,
-                        size_t shard_count, void *posm, void *vel, void *acc, bool f64,
+                        size_t shard_count, void *posm, void *vel, void *acc, bool f64, int dims,
                         cudaStream_t st)
 {
     const unsigned grid = (unsigned)((n_padded + 255) / 256);
     if (f64)
         pack_kernel<double><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, n, n_padded, shard_start,
                                                   shard_count, (double *)posm, (double *)vel,
-                                                  (double *)acc);
+                                                  (double *)acc, dims);
     else
         pack_kernel<float><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, n, n_padded, shard_start,
                                                  shard_count, (float *)posm, (float *)vel,
-                                                 (float *)acc);
+                                                 (float *)acc, dims);
     return cudaGetLastError();
 }
 

@@ -212,7 +212,7 @@ int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies)
         CU(cudaMemcpyAsync(d.aos, bodies, ctx->n * sizeof(nbody_body_t), cudaMemcpyHostToDevice, d.stream));
         d.cur = 0;
         CU(launch_pack(d.aos, ctx->n, ctx->n_padded, d.shard_start, d.shard_count, d.posm[0], d.vel,
-                       d.acc, ctx->f64, d.stream));
+                       d.acc, ctx->f64, ctx->p.dims, d.stream));
         ctx->launches++;
         // padding must also be valid in the other buffer (masses are copied by the integrator only
         // for the shard's own blocks, so seed both buffers with the full packed state)
@@ -231,6 +231,7 @@ ForceLaunch make_force(const nbody_ctx *c, const Dev &d, const Range &r, float d
     ForceLaunch L;
     memset(&L, 0, sizeof L);
     L.posm = d.posm[d.cur];
+    L.dims = c->p.dims;
     L.uniform_mass = c->uniform ? 1 : 0;
     L.acc_scale = c->uniform ? c->p.G * c->uniform_mass : c->p.G;
     L.accp = d.accp;
