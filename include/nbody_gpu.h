@@ -81,6 +81,10 @@ typedef struct nbody_params {
     int32_t  bh_fix_near_leaves; /* Barnes-Hut only.  0 = the reference's behaviour: a NEAR leaf contributes
                                  nothing (insert() leaves every body Range empty, Quadtree.hpp:133-147);
                                  1 = add the leaf's body for near leaves (self excluded) */
+    int32_t  bh_walk;         /* Barnes-Hut only.  0 = one independent walk per thread, targets in Z-order
+                                 (default: measured faster at theta = 1, where walks are ~125 nodes long);
+                                 1 = warp-cooperative walk (each node record loaded once per warp).
+                                 Identical results bit for bit; only the memory access pattern differs. */
     /* --- single-process multi-GPU (C driver): ngpus devices, NCCL comms created internally --- */
     int32_t  ngpus;           /* 0 or 1 = single GPU */
     int32_t  device_ids[NBODY_MAX_GPUS]; /* CUDA ordinals; device_ids[0] is used when ngpus<=1 */

@@ -44,6 +44,7 @@ class NbodyParams(C.Structure):
         ("use_graph", C.c_int32),
         ("force_variant", C.c_int32),
         ("bh_fix_near_leaves", C.c_int32),
+        ("bh_walk", C.c_int32),
         ("ngpus", C.c_int32),
         ("device_ids", C.c_int32 * NBODY_MAX_GPUS),
         ("world", C.c_int32),

@@ -303,6 +303,64 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
     accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = 0.f;
 }
 
+// Warp-cooperative walk.  The 32 lanes of a warp hold 32 targets that are neighbours in Z-order; the
+// warp walks the UNION of their traversals in pre-order index order and every visited node record is
+// loaded once per warp (uniform address -> one broadcast transaction instead of up to 32 divergent
+// ones).  Each lane keeps `resume`, the index of the next node of ITS OWN sequential walk (node+1 when
+// it opens a branch, next[node] when it accepts a far node or passes a leaf); it takes part only at
+// nodes == resume, and the warp advances to the minimum resume over lanes.  A lane's sequence of
+// visited nodes, and therefore its sum term by term, is exactly that of Quadtree::acc -- bit-exact
+// like bh_walk_kernel, only the memory access pattern differs.
+template <bool REFCOMPAT>
+__global__ void __launch_bounds__(128)
+bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
+                    float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
+                    float *__restrict__ accp, unsigned cap)
+{
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < n;
+    const unsigned body = valid ? idx[s] : 0u;
+    const bool mine = valid && body >= shard_start && body < shard_start + shard_count;
+    const size_t g = blk_index(body, 0);
+    const float px = posm[g], py = posm[g + BLK];
+    float ax = 0.f, ay = 0.f;
+    constexpr unsigned DONE = 0xffffffffu;
+    unsigned resume = mine ? 0u : DONE;
+    unsigned i = __reduce_min_sync(0xffffffffu, resume);
+    while (i < cap) {                                        // DONE (and an overflowed tree) end the walk
+        const float4 nd = nodes.data[i];                     // warp-uniform loads
+        const unsigned nx = nodes.next[i];
+        const bool is_leaf = (nodes.meta[i] & 256u) != 0u;
+        if (resume == i) {
+            const float dx = __fsub_rn(nd.x, px), dy = __fsub_rn(nd.y, py);
+            const float d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            const bool far = nd.w < __fmul_rn(d_sq, t_sq);
+            if (far || is_leaf) {
+                if ((far || fix_near_leaves) && d_sq > 0.f) {
+                    float s3;
+                    if (REFCOMPAT) {
+                        const float inv = bh_quake(__fadd_rn(d_sq, e_sq));
+                        s3 = __fmul_rn(nd.z, __fmul_rn(__fmul_rn(inv, inv), inv));
+                    } else {
+                        const float inv = rsqrt_approx(d_sq + e_sq);
+                        s3 = nd.z * inv * inv * inv;
+                    }
+                    ax = __fadd_rn(ax, __fmul_rn(dx, s3));
+                    ay = __fadd_rn(ay, __fmul_rn(dy, s3));
+                }
+                resume = nx ? nx : DONE;
+            } else {
+                resume = i + 1;
+            }
+        }
+        i = __reduce_min_sync(0xffffffffu, resume);
+    }
+    if (mine) {
+        const size_t l = blk_index(body - shard_start, 0);
+        accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = 0.f;
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 cudaError_t BhWorkspace::alloc(size_t n)
 {
@@ -404,6 +462,15 @@ cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float ep
 {
     const unsigned g = (unsigned)((n + 127) / 128);
     const float t_sq = theta * theta, e_sq = eps * eps;       // Quadtree ctor, Quadtree.hpp:19
+    if (warp_walk) {
+        if (refcompat)
+            bh_walk_warp_kernel<true><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
+                                                         fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, node_cap);
+        else
+            bh_walk_warp_kernel<false><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
+                                                          fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, node_cap);
+        return cudaGetLastError();
+    }
     if (refcompat)
         bh_walk_kernel<true><<<g, 128, 0, st>>>(posm, (const unsigned *)idx, n, bh_nodes(*this), t_sq, e_sq,
                                                 fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, node_cap);

@@ -103,6 +103,7 @@ struct BhWorkspace {
     size_t temp_bytes = 0;
     int coop_blocks = 148;
     bool count_valid = false;
+    bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
     cudaError_t alloc(size_t n);
     cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);
     void release();

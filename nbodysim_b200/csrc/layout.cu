@@ -114,41 +114,50 @@ cudaError_t launch_unpack_f64(double *pos3, double *vel3, double *acc3, size_t n
     return cudaGetLastError();
 }
 
-// ---- energy / momentum diagnostic, fp64 arithmetic and accumulation ------------------------------
+// ---- energy / momentum diagnostic -----------------------------------------------------------------
 // K = sum 1/2 m v^2, P = sum m v over the shard; W2 = - sum_{i in shard} sum_{j != i} m_i m_j
 // rsqrt(r^2 + eps^2) over ALL sources (each pair counted twice over the whole system; the caller
-// halves after summing ranks).  Sources are read straight from the blocked array: all lanes of a
-// warp read the same address (broadcast) and the array is L2-resident.
+// halves after summing ranks).  Sources are staged block by block through shared memory.  fp64 state:
+// everything in double.  fp32 state: pair terms in fp32 (positions are floats; rsqrtf <= 2 ulp), summed
+// in fp32 over one 256-source block and then accumulated in double, so the result resolves relative
+// energy changes of ~1e-8 at 1/20 of the fp64 cost.
 template <typename T>
 __global__ void __launch_bounds__(256)
 energy_kernel(const T *__restrict__ posm, const T *__restrict__ vel, size_t n_padded,
               size_t shard_start, size_t shard_count, double eps2, double *__restrict__ out5)
 {
+    __shared__ T tile[BLK_ELEMS];
     __shared__ double red[5][8];
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double K = 0, W = 0, P0 = 0, P1 = 0, P2 = 0;
-    if (k < shard_count) {
-        const size_t i = shard_start + k;
-        const size_t g = blk_index(i, 0), l = blk_index(k, 0);
-        const double xi = posm[g], yi = posm[g + BLK], zi = posm[g + 2 * BLK], mi = posm[g + 3 * BLK];
-        const double vx = vel[l], vy = vel[l + BLK], vz = vel[l + 2 * BLK];
-        K = 0.5 * mi * (vx * vx + vy * vy + vz * vz);
-        P0 = mi * vx; P1 = mi * vy; P2 = mi * vz;
-        double w = 0;
-        const size_t nblk = n_padded / BLK;
-        for (size_t b = 0; b < nblk; ++b) {
-            const T *sx = posm + b * BLK_ELEMS;
-#pragma unroll 4
-            for (int j = 0; j < BLK; ++j) {
-                const double dx = (double)sx[j] - xi, dy = (double)sx[BLK + j] - yi,
-                             dz = (double)sx[2 * BLK + j] - zi;
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const bool self = (b * BLK + j) == i;
-                w += self ? 0.0 : (double)sx[3 * BLK + j] * rsqrt(r2 + eps2);
-            }
+    const bool active = k < shard_count;
+    const size_t i = shard_start + (active ? k : 0);
+    const size_t g = blk_index(i, 0), l = blk_index(active ? k : 0, 0);
+    const T xi = posm[g], yi = posm[g + BLK], zi = posm[g + 2 * BLK];
+    const double mi = active ? (double)posm[g + 3 * BLK] : 0.0;
+    const double vx = vel[l], vy = vel[l + BLK], vz = vel[l + 2 * BLK];
+    double K = 0.5 * mi * (vx * vx + vy * vy + vz * vz);
+    double P0 = mi * vx, P1 = mi * vy, P2 = mi * vz;
+    double w = 0;
+    const T e2 = (T)eps2;
+    const size_t nblk = n_padded / BLK;
+    for (size_t b = 0; b < nblk; ++b) {
+        __syncthreads();
+        const T *src = posm + b * BLK_ELEMS;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tile[c * BLK + threadIdx.x] = src[c * BLK + threadIdx.x];
+        __syncthreads();
+        const long long self = (long long)i - (long long)(b * BLK);   // lane of the target inside this block, if any
+        T wb = 0;
+#pragma unroll 8
+        for (int j = 0; j < BLK; ++j) {
+            const T dx = tile[j] - xi, dy = tile[BLK + j] - yi, dz = tile[2 * BLK + j] - zi;
+            const T r2 = dx * dx + dy * dy + dz * dz + e2;
+            const T t = tile[3 * BLK + j] * (sizeof(T) == 8 ? (T)rsqrt((double)r2) : (T)rsqrtf((float)r2));
+            wb += (j == self) ? (T)0 : t;
         }
-        W = -mi * w;
+        w += (double)wb;
     }
+    double W = -mi * w;
     double v[5] = {K, W, P0, P1, P2};
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
@@ -158,7 +167,7 @@ energy_kernel(const T *__restrict__ posm, const T *__restrict__ vel, size_t n_pa
     __syncthreads();
     if (threadIdx.x < 5) {
         double s = 0;
-        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        for (int q = 0; q < 8; ++q) s += red[threadIdx.x][q];
         atomicAdd(&out5[threadIdx.x], s);
     }
 }

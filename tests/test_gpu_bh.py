@@ -84,6 +84,17 @@ def test_bh_acc_bitexact_vs_oracle_seeded(n, seed, theta):
     assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, theta, 1.0)))
 
 
+@pytest.mark.parametrize("walk", [0, 1])
+def test_bh_both_walks_bitexact(walk):
+    """per-thread (0) and warp-cooperative (1) walks visit each target's nodes in the same order"""
+    b = ic.spinning_disc(30000, seed=21, scale=600.0)
+    b["mass"] = np.random.default_rng(21).uniform(0.1, 3.0, 30000).astype(np.float32)
+    with bh_sim(b, theta=0.8, eps=1.0, bh_walk=walk) as s:
+        s.attract()
+        out = s.download()["acc"].copy()
+    assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, 0.8, 1.0)))
+
+
 def test_bh_coincident_bodies_merge():
     b = ic.spinning_disc(64, seed=8)
     b[10]["pos"] = b[3]["pos"]

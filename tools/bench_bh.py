@@ -24,9 +24,10 @@ def main():
         b = ic.spinning_disc(n, seed=3, scale=100.0 * np.sqrt(n / 1024.0), spin=0.3 / np.sqrt(n / 1024.0))
         b["mass"] = np.random.default_rng(3).uniform(0.1, 3.0, n).astype(np.float32)
         row = {"n": n, "theta": 1.0, "eps": 1.0}
-        for mode, name in ((capi.RSQRT_REFCOMPAT, "refcompat"), (capi.RSQRT_FAST, "fast")):
+        for mode, walk, name in ((capi.RSQRT_REFCOMPAT, 0, "refcompat"), (capi.RSQRT_REFCOMPAT, 1, "refcompat_warpwalk"),
+                                 (capi.RSQRT_FAST, 0, "fast")):
             with Simulation(b, dt=0.01, force_algo=capi.FORCE_BARNES_HUT, dims=2, theta=1.0, eps=1.0, rsqrt_mode=mode,
-                            integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
+                            bh_walk=walk, integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
                 s.step(3); s.sync()
                 f, i = [], []
                 for _ in range(10):
