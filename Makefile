@@ -20,10 +20,10 @@ nbodysim_b200/libnbody_gpu.so: $(OBJ)
 
 host: nbodysim_b200/libnbody_host.so host/_build/nbody_run
 nbodysim_b200/libnbody_host.so: host/nbody_ic.c include/nbody_host.h include/nbody_body.h
-	$(HOSTCC) -std=c11 -O2 -Wall -Wextra -fPIC -shared -Iinclude -o $@ host/nbody_ic.c -lm
+	$(HOSTCC) -std=c11 -O2 -ffp-contract=off -Wall -Wextra -fPIC -shared -Iinclude -o $@ host/nbody_ic.c -lm
 host/_build/nbody_run: host/nbody_main.c host/nbody_ic.c include/nbody_host.h include/nbody_gpu.h nbodysim_b200/libnbody_gpu.so
 	@mkdir -p host/_build
-	$(HOSTCC) -std=c11 -O2 -Wall -Wextra -Iinclude -o $@ host/nbody_main.c host/nbody_ic.c \
+	$(HOSTCC) -std=c11 -O2 -ffp-contract=off -Wall -Wextra -Iinclude -o $@ host/nbody_main.c host/nbody_ic.c \
 	    -Lnbodysim_b200 -lnbody_gpu -Wl,-rpath,'$$ORIGIN/../../nbodysim_b200' -lm
 
 oracle:

@@ -198,6 +198,189 @@ int nbody_ic_spinning_disc(nbody_body_t *b, size_t n, uint64_t seed, float scale
     return 0;
 }
 
+/* ---- Simulation::uniform_disc restated (Simulation.hpp:347-603) ------------------------------------ */
+typedef struct { uint32_t mt[624]; int idx; } mt19937_t;
+static void mt_seed(mt19937_t *g, uint32_t seed)
+{
+    g->mt[0] = seed;
+    for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t)i;
+    g->idx = 624;
+}
+static uint32_t mt_next(mt19937_t *g)
+{
+    if (g->idx >= 624) {
+        for (int i = 0; i < 624; ++i) {
+            uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7fffffffu);
+            g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->idx = 0;
+    }
+    uint32_t y = g->mt[g->idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+/* std::uniform_real_distribution<float>(0,1) over mt19937 as libstdc++ computes it:
+ * generate_canonical<float,24>: one draw, float(draw) / 2^32, clamped below 1. */
+static float mt_canonical(mt19937_t *g)
+{
+    float r = (float)mt_next(g) / 4294967296.0f;
+    if (r >= 1.0f) r = 0.99999994f; /* nextafter(1.0f, 0.0f) */
+    return r;
+}
+/* std::sort is unstable and the scene has a handful of exact ties in |pos|^2 (7 pairs at n=25000), whose
+ * final order then depends on the library's algorithm.  To stay bit-identical with the libstdc++ build
+ * of the reference, the sort below follows libstdc++'s std::sort structure: introsort (median-of-three
+ * to front, unguarded partition, recursion on the right part) down to runs of 16, then one insertion
+ * pass.  The heap-sort fallback of the depth limit (2*log2 n levels) is a plain heap sort here; it is
+ * never reached for this data. */
+static int less_mag_sq(const nbody_body_t *a, const nbody_body_t *b)
+{
+    return (a->pos[0] * a->pos[0] + a->pos[1] * a->pos[1]) < (b->pos[0] * b->pos[0] + b->pos[1] * b->pos[1]);
+}
+static void body_swap(nbody_body_t *a, nbody_body_t *b) { nbody_body_t t = *a; *a = *b; *b = t; }
+static void unguarded_linear_insert(nbody_body_t *last)
+{
+    nbody_body_t val = *last;
+    nbody_body_t *next = last - 1;
+    while (less_mag_sq(&val, next)) { *last = *next; last = next; --next; }
+    *last = val;
+}
+static void insertion_sort(nbody_body_t *first, nbody_body_t *last)
+{
+    if (first == last) return;
+    for (nbody_body_t *i = first + 1; i != last; ++i) {
+        if (less_mag_sq(i, first)) {
+            nbody_body_t val = *i;
+            memmove(first + 1, first, (size_t)(i - first) * sizeof *first);
+            *first = val;
+        } else {
+            unguarded_linear_insert(i);
+        }
+    }
+}
+static void heap_sort_fallback(nbody_body_t *first, nbody_body_t *last)
+{
+    const ptrdiff_t n = last - first;
+    for (ptrdiff_t start = n / 2 - 1; start >= 0; --start)
+        for (ptrdiff_t r = start;;) {
+            ptrdiff_t c = 2 * r + 1;
+            if (c >= n) break;
+            if (c + 1 < n && less_mag_sq(first + c, first + c + 1)) ++c;
+            if (!less_mag_sq(first + r, first + c)) break;
+            body_swap(first + r, first + c); r = c;
+        }
+    for (ptrdiff_t end = n - 1; end > 0; --end) {
+        body_swap(first, first + end);
+        for (ptrdiff_t r = 0;;) {
+            ptrdiff_t c = 2 * r + 1;
+            if (c >= end) break;
+            if (c + 1 < end && less_mag_sq(first + c, first + c + 1)) ++c;
+            if (!less_mag_sq(first + r, first + c)) break;
+            body_swap(first + r, first + c); r = c;
+        }
+    }
+}
+static void introsort_loop(nbody_body_t *first, nbody_body_t *last, int depth_limit)
+{
+    while (last - first > 16) {
+        if (depth_limit == 0) { heap_sort_fallback(first, last); return; }
+        --depth_limit;
+        /* median of (first+1, mid, last-1) moved to *first */
+        nbody_body_t *a = first + 1, *b = first + (last - first) / 2, *c = last - 1;
+        if (less_mag_sq(a, b)) {
+            if (less_mag_sq(b, c)) body_swap(first, b);
+            else if (less_mag_sq(a, c)) body_swap(first, c);
+            else body_swap(first, a);
+        } else if (less_mag_sq(a, c)) body_swap(first, a);
+        else if (less_mag_sq(b, c)) body_swap(first, c);
+        else body_swap(first, b);
+        /* unguarded partition of [first+1, last) around the pivot *first */
+        nbody_body_t *lo = first + 1, *hi = last;
+        for (;;) {
+            while (less_mag_sq(lo, first)) ++lo;
+            --hi;
+            while (less_mag_sq(first, hi)) --hi;
+            if (!(lo < hi)) break;
+            body_swap(lo, hi);
+            ++lo;
+        }
+        introsort_loop(lo, last, depth_limit);
+        last = lo;
+    }
+}
+static void sort_like_libstdcxx(nbody_body_t *first, size_t n)
+{
+    if (n == 0) return;
+    nbody_body_t *last = first + n;
+    int lg = 0;
+    for (size_t t = n; t > 1; t >>= 1) ++lg;
+    introsort_loop(first, last, 2 * lg);
+    if (n > 16) {
+        insertion_sort(first, first + 16);
+        for (nbody_body_t *i = first + 16; i != last; ++i) unguarded_linear_insert(i);
+    } else {
+        insertion_sort(first, last);
+    }
+}
+
+int nbody_ic_reference_disc(nbody_body_t *b, size_t n)
+{
+    if (!b || n == 0) return NBODY_HOST_EINVAL;
+    mt19937_t rng;
+    mt_seed(&rng, 0); /* std::mt19937 rng(0), :349 */
+    const float inner_radius = 200.0f;
+    const float outer_radius = sqrtf((float)n) * 300.7f;
+    zero_body(&b[0]);
+    b[0].mass = 1e9f;
+    b[0].radius = inner_radius;
+    /* mass buckets :372-397: probabilities normalised, then cumulative, all in float */
+    const float mn[3] = {0.00005f, 1.2f, 5.0f}, mx[3] = {0.8f, 2.5f, 50.0f};
+    float pr[3] = {0.825f, 0.125f, 0.025f};
+    float total = 0.0f;
+    for (int i = 0; i < 3; ++i) total += pr[i];
+    for (int i = 0; i < 3; ++i) pr[i] /= total;
+    float cum[3], c = 0.0f;
+    for (int i = 0; i < 3; ++i) { c += pr[i]; cum[i] = c; }
+    /* Lorenz attractor :399-405, :523-535 */
+    const float sigma = 10.0f, rho = 28.0f, beta = 8.0f / 3.0f;
+    float x = 0.1f, y = 0.0f, z = 0.0f;
+    for (size_t k = 1; k < n; ++k) {
+        const float dt = 0.01f;
+        const float dx = sigma * (y - x);
+        const float dy = x * (rho - z) - y;
+        const float dz = x * y - beta * z;
+        x += dx * dt;
+        y += dy * dt;
+        z += dz * dt;
+        const float scale = outer_radius / 10.0f;
+        const float px = x * scale, py = y * scale;
+        float vx = -py, vy = px;
+        const float m = sqrtf(vx * vx + vy * vy); /* Vec2::normalize: x is divided TWICE (Vec2.hpp:231-232) */
+        if (m > 0.0f) { vx /= m; vx /= m; vy /= m; }
+        const float rp = mt_canonical(&rng);
+        size_t sel = 0;
+        for (size_t i = 0; i < 3; ++i)
+            if (rp <= cum[i]) { sel = i; break; }
+        const float mass = mt_canonical(&rng) * (mx[sel] - mn[sel]) + mn[sel];
+        zero_body(&b[k]);
+        b[k].pos[0] = px; b[k].pos[1] = py;
+        b[k].vel[0] = vx; b[k].vel[1] = vy;
+        b[k].mass = mass;
+        b[k].radius = cbrtf(mass);
+    }
+    sort_like_libstdcxx(b, n); /* std::sort by |pos|^2, :585-590 */
+    float total_mass = 0.0f;
+    for (size_t i = 0; i < n; ++i) { /* :592-600 */
+        total_mass += b[i].mass;
+        if (b[i].pos[0] == 0.0f && b[i].pos[1] == 0.0f) continue;
+        const float r = sqrtf(b[i].pos[0] * b[i].pos[0] + b[i].pos[1] * b[i].pos[1]);
+        const float v = sqrtf(total_mass / r);
+        b[i].vel[0] *= v;
+        b[i].vel[1] *= v;
+    }
+    return 0;
+}
+
 void nbody_ic_rescale(nbody_body_t *b, size_t n, float ls, float vs, float ms)
 {
     for (size_t i = 0; i < n; ++i) {

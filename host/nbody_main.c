@@ -26,7 +26,7 @@ static double now_s(void)
 static void usage(const char *a0)
 {
     fprintf(stderr,
-            "usage: %s [--n N] [--steps K] [--dt DT] [--eps E] [--ic plummer|sphere|galaxy|disc]\n"
+            "usage: %s [--n N] [--steps K] [--dt DT] [--eps E] [--ic plummer|sphere|galaxy|disc|reference]\n"
             "          [--seed S] [--dims 2|3] [--gpus G] [--precision f32|f64]\n"
             "          [--rsqrt fast|refcompat] [--clamp on|off] [--boundary on|off]\n"
             "          [--energy-every M] [--in snapshot] [--out snapshot] [--splits S]\n",
@@ -81,6 +81,7 @@ int main(int argc, char **argv)
     else if (!strcmp(ic, "plummer")) rc = nbody_ic_plummer(b, n, seed, dims);
     else if (!strcmp(ic, "sphere")) rc = nbody_ic_uniform_sphere(b, n, seed, dims, 0.5);
     else if (!strcmp(ic, "galaxy")) rc = nbody_ic_two_galaxy(b, n, seed, dims);
+    else if (!strcmp(ic, "reference")) rc = nbody_ic_reference_disc(b, n);   /* the reference's own uniform_disc scene */
     else if (!strcmp(ic, "disc")) rc = nbody_ic_spinning_disc(b, n, seed, 100.0f * sqrtf((float)n / 1024.0f), 0.3f / sqrtf((float)n / 1024.0f), 1.0f);
     else { usage(argv[0]); return 2; }
     if (rc != 0) { fprintf(stderr, "initial conditions failed (%d)\n", rc); return 1; }

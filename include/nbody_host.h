@@ -36,6 +36,13 @@ int nbody_ic_two_galaxy(nbody_body_t *b, size_t n, uint64_t seed, int dims);
  * mass = m each (reference-unit scale: scale=100, spin=0.3, m=1, eps=1). */
 int nbody_ic_spinning_disc(nbody_body_t *b, size_t n, uint64_t seed, float scale, float spin,
                            float m);
+/* The reference's own scene, Simulation::uniform_disc (Simulation.hpp:347-603), restated: body 0 is a
+ * 1e9 central mass of radius 200; the others follow an Euler-integrated Lorenz attractor scaled by
+ * sqrt(n)*300.7/10, masses from a three-bucket distribution drawn with std::mt19937(0), radius =
+ * cbrt(mass), sorted by |pos|, tangential speed sqrt(M_enclosed/r) applied to the reference's
+ * (double-divide) "normalised" direction (Vec2::normalize, Vec2.hpp:226-236).  Bit-identical to the
+ * strict libstdc++ build of the reference (tests/test_reference_scene.py). */
+int nbody_ic_reference_disc(nbody_body_t *b, size_t n);
 /* Scale lengths/velocities/masses in place (reference-unit runs with eps=1). */
 void nbody_ic_rescale(nbody_body_t *b, size_t n, float lscale, float vscale, float mscale);
 

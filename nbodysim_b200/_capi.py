@@ -113,6 +113,7 @@ HOST_SYMBOLS = {
     "nbody_ic_plummer": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int]),
     "nbody_ic_two_galaxy": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int]),
     "nbody_ic_spinning_disc": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float, C.c_float]),
+    "nbody_ic_reference_disc": (C.c_int, [C.c_void_p, C.c_size_t]),
     "nbody_ic_rescale": (None, [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float]),
     "nbody_snapshot_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p]),
     "nbody_snapshot_read_header": (C.c_int, [C.c_char_p, C.c_void_p]),

@@ -110,18 +110,21 @@ force_f32_refcompat_kernel(const float *__restrict__ posm, float *__restrict__ a
 }
 
 // ---- host-side launchers ------------------------------------------------------------------------
-using FastRing = Ring<BLK_ELEMS, FAST_STAGE_BLKS>;
+struct LargeCfg {
+    static constexpr int I = FAST_I, THREADS = FAST_THREADS, MINB = FAST_MINB, UNROLL = FAST_UNROLL,
+                         STAGE = FAST_STAGE_BLKS, TILE_BLKS = FAST_TILE_BLKS;
+};
+struct SmallCfg {
+    static constexpr int I = SMALL_I, THREADS = SMALL_THREADS, MINB = SMALL_MINB, UNROLL = SMALL_UNROLL,
+                         STAGE = SMALL_STAGE_BLKS, TILE_BLKS = SMALL_TILE_BLKS;
+};
 
-template <int FORM, bool GUARD, bool FUSE, int DIMS>
+template <typename C, int FORM, bool GUARD, bool FUSE, int DIMS>
 static cudaError_t launch_fast_d(const ForceLaunch &L, cudaStream_t st)
 {
-    auto kern = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM, GUARD, FUSE, DIMS>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    using RingT = Ring<BLK_ELEMS, C::STAGE>;
+    auto kern = force_f32_fast_kernel<C::I, C::THREADS, C::MINB, C::UNROLL, C::STAGE, FORM, GUARD, FUSE, DIMS>;
+    static_assert(RingT::SMEM <= 48 * 1024, "above 48 KiB the per-device opt-in attribute would be needed");
     FastArgs a;
     a.posm = (const float *)L.posm;
     a.accp = (float *)L.accp;
@@ -129,23 +132,31 @@ static cudaError_t launch_fast_d(const ForceLaunch &L, cudaStream_t st)
     a.j_blk0 = L.j_blk0; a.j_nblk = L.j_nblk; a.splits = L.splits; a.slot0 = L.slot0;
     a.eps2 = L.eps2; a.acc_scale = L.acc_scale; a.n_real = L.j_body_limit;
     a.posm_next = (float *)L.posm_next; a.vel = (float *)L.vel; a.acc = (float *)L.acc; a.ip = L.ip;
-    kern<<<force_f32_fast_grid(L), FAST_THREADS, FastRing::SMEM, st>>>(a);
+    kern<<<(L.n_iblk / C::TILE_BLKS) * L.splits, C::THREADS, RingT::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int FORM, bool GUARD, bool FUSE>
 static cudaError_t launch_fast_t(const ForceLaunch &L, cudaStream_t st)
 {
-    return L.dims == 2 ? launch_fast_d<FORM, GUARD, FUSE, 2>(L, st) : launch_fast_d<FORM, GUARD, FUSE, 3>(L, st);
+    if (L.small_tile) { // small tiles never fuse (FUSE instantiations exist for the large tile only)
+        return L.dims == 2 ? launch_fast_d<SmallCfg, FORM, GUARD, false, 2>(L, st)
+                           : launch_fast_d<SmallCfg, FORM, GUARD, false, 3>(L, st);
+    }
+    return L.dims == 2 ? launch_fast_d<LargeCfg, FORM, GUARD, FUSE, 2>(L, st)
+                       : launch_fast_d<LargeCfg, FORM, GUARD, FUSE, 3>(L, st);
 }
 
-int force_f32_fast_grid(const ForceLaunch &L) { return (L.n_iblk / FAST_TILE_BLKS) * L.splits; }
+int force_f32_fast_grid(const ForceLaunch &L)
+{
+    return (L.n_iblk / (L.small_tile ? SMALL_TILE_BLKS : FAST_TILE_BLKS)) * L.splits;
+}
 
 cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStream_t st)
 {
-    if (L.n_iblk % FAST_TILE_BLKS != 0 || L.splits < 1 || L.j_nblk < L.splits)
-        return cudaErrorInvalidValue;
-    if (L.fuse && L.splits != 1) return cudaErrorInvalidValue;
+    const int tile = L.small_tile ? SMALL_TILE_BLKS : FAST_TILE_BLKS;
+    if (L.n_iblk % tile != 0 || L.splits < 1 || L.j_nblk < L.splits) return cudaErrorInvalidValue;
+    if (L.fuse && (L.splits != 1 || L.small_tile)) return cudaErrorInvalidValue;
     const int v = (L.uniform_mass ? 4 : 0) | (guard_zero ? 2 : 0) | (L.fuse ? 1 : 0);
     switch (v) {
     case 0: return launch_fast_t<FORM_PLAIN, false, false>(L, st);
@@ -159,18 +170,30 @@ cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStr
     }
 }
 
-int force_f32_fast_ctas_per_sm(bool uniform_mass)
+int force_f32_fast_ctas_per_sm(bool uniform_mass, bool small_tile)
 {
     int n = 0;
     cudaError_t e;
-    if (uniform_mass) {
-        auto k = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_UNIFORM, false, false>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, FAST_THREADS, FastRing::SMEM);
+    if (small_tile) {
+        using RingT = Ring<BLK_ELEMS, SMALL_STAGE_BLKS>;
+        if (uniform_mass)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &n, force_f32_fast_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_UNIFORM, false, false, 3>,
+                SMALL_THREADS, RingT::SMEM);
+        else
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &n, force_f32_fast_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_PLAIN, false, false, 3>,
+                SMALL_THREADS, RingT::SMEM);
     } else {
-        auto k = force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_PLAIN, false, false>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastRing::SMEM);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, FAST_THREADS, FastRing::SMEM);
+        using RingT = Ring<BLK_ELEMS, FAST_STAGE_BLKS>;
+        if (uniform_mass)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &n, force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_UNIFORM, false, false, 3>,
+                FAST_THREADS, RingT::SMEM);
+        else
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &n, force_f32_fast_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_PLAIN, false, false, 3>,
+                FAST_THREADS, RingT::SMEM);
     }
     return e == cudaSuccess ? n : 0;
 }

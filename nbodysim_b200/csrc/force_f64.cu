@@ -128,13 +128,7 @@ force_f64_kernel(const double *__restrict__ posm, double *__restrict__ accp, int
 cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st)
 {
     if (L.splits < 1 || L.j_nblk < L.splits) return cudaErrorInvalidValue;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(
-            force_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F64_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static_assert(F64_SMEM <= 48 * 1024, "above 48 KiB the per-device opt-in attribute would be needed");
     const int grid = (L.n_iblk / F64_TILE_BLKS) * L.splits;
     force_f64_kernel<<<grid, F64_THREADS, F64_SMEM, st>>>(
         (const double *)L.posm, (double *)L.accp, L.i_blk0, L.i_blk_local0, L.n_iblk_shard,

@@ -45,8 +45,14 @@ struct Dev {
     std::vector<Range> plan;
     int nslots = 0;
     bool fused = false;
+    bool small_tile = false;      // fast kernel runs the 256-target tile geometry (small shards)
     int force_ctas = 0;
     BhWorkspace bh;               // Barnes-Hut path only
+    // CUDA graph of two consecutive steps (buffer parity returns to the start), keyed on dt and parity
+    cudaGraphExec_t graph = nullptr;
+    float graph_dt = 0.f;
+    int graph_cur = -1;
+    unsigned long long graph_launches = 0, graph_interactions = 0;
 };
 
 } // namespace
@@ -62,7 +68,7 @@ struct nbody_ctx {
     size_t esz = 4;
     std::vector<Dev> devs;
     nbody_body_t *h_stage = nullptr; // pinned, n records (download merges / uploads)
-    int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0;
+    int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0, ctas_per_sm_small = 0;
     unsigned long long launches = 0, interactions = 0;
     int profile_next = 0;
     float last_force_ms = 0.f, last_integ_ms = 0.f;
@@ -141,10 +147,18 @@ int plan_device(nbody_ctx *c, Dev &d)
     const bool refc = !c->f64 && c->p.rsqrt_mode == NBODY_RSQRT_REFCOMPAT;
     d.plan.clear();
     d.fused = false;
+    d.small_tile = false;
     int tiles, slots, min_chunk;
     if (c->f64) { tiles = ibn / F64_TILE_BLKS; slots = c->sm_count * 4; min_chunk = 4; }
     else if (refc) { tiles = ibn * 2; slots = c->sm_count * 4; min_chunk = 1; }
-    else { tiles = ibn / FAST_TILE_BLKS; slots = c->sm_count * std::max(1, c->ctas_per_sm); min_chunk = 8; }
+    else {
+        tiles = ibn / FAST_TILE_BLKS; slots = c->sm_count * std::max(1, c->ctas_per_sm); min_chunk = 8;
+        // small shard: 2048-target tiles could not even give every SM two CTAs -> 256-target tiles
+        const long long max_units = (long long)tiles * std::max(1, nblk / min_chunk);
+        d.small_tile = max_units < 2LL * c->sm_count;
+        if (c->p.fuse_integrator == 1 && c->p.j_splits == 1) d.small_tile = false;   // explicit request for the fused epilogue
+        if (d.small_tile) { tiles = ibn / SMALL_TILE_BLKS; slots = c->sm_count * std::max(1, c->ctas_per_sm_small); min_chunk = 1; }
+    }
 
     struct Seg { int b0, nb; bool remote; };
     std::vector<Seg> segs;
@@ -172,10 +186,10 @@ int plan_device(nbody_ctx *c, Dev &d)
         slot += S;
     }
     d.nslots = slot;
-    if (!c->f64 && !refc && c->world == 1 && d.plan.size() == 1 && d.plan[0].splits == 1) {
+    if (!c->f64 && !refc && !d.small_tile && c->world == 1 && d.plan.size() == 1 && d.plan[0].splits == 1) {
         d.fused = (c->p.fuse_integrator != 0);
     }
-    if (c->p.fuse_integrator == 1 && !(d.plan.size() == 1 && d.plan[0].splits == 1 && !c->f64 && !refc)) {
+    if (c->p.fuse_integrator == 1 && !(d.plan.size() == 1 && d.plan[0].splits == 1 && !c->f64 && !refc && !d.small_tile)) {
         // explicit request that cannot be honoured with this plan: fall back to separate kernels
         d.fused = false;
     }
@@ -235,6 +249,7 @@ ForceLaunch make_force(const nbody_ctx *c, const Dev &d, const Range &r, float d
     memset(&L, 0, sizeof L);
     L.posm = d.posm[d.cur];
     L.dims = c->p.dims;
+    L.small_tile = d.small_tile ? 1 : 0;
     L.uniform_mass = c->uniform ? 1 : 0;
     L.acc_scale = c->uniform ? c->p.G * c->uniform_mass : c->p.G;
     L.accp = d.accp;
@@ -378,6 +393,7 @@ void free_all(nbody_ctx *c)
         if (d.aos) cudaFree(d.aos);
         if (d.energy5) cudaFree(d.energy5);
         d.bh.release();
+        if (d.graph) cudaGraphExecDestroy(d.graph);
         if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
         if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
         for (int k = 0; k < 4; ++k) if (d.ev_t[k]) cudaEventDestroy(d.ev_t[k]);
@@ -516,7 +532,8 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->devs[0].device);
         ctx->sm_clock_khz = khz;
         cudaSetDevice(ctx->devs[0].device);
-        ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(ctx->uniform);
+        ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(ctx->uniform, false);
+        ctx->ctas_per_sm_small = force_f32_fast_ctas_per_sm(ctx->uniform, true);
     }
     for (Dev &d : ctx->devs) {
         if ((rc = plan_device(ctx, d)) != NBODY_OK) return fail(rc);
@@ -551,9 +568,50 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     return NBODY_OK;
 }
 
+// Launch-bound regime (small N: a step is two short kernels): replay pairs of steps from a CUDA graph.
+static int step_with_graph(nbody_ctx *ctx, float dt, int &remaining)
+{
+    Dev &d = ctx->devs[0];
+    CU(cudaSetDevice(d.device));
+    if (!d.graph || d.graph_dt != dt || d.graph_cur != d.cur) {
+        if (d.graph) { cudaGraphExecDestroy(d.graph); d.graph = nullptr; }
+        const unsigned long long l0 = ctx->launches, i0 = ctx->interactions;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_step(ctx, dt, false, false);
+        if (rc == NBODY_OK) rc = enqueue_step(ctx, dt, false, false);
+        cudaError_t e = cudaStreamEndCapture(d.stream, &g);
+        d.graph_launches = ctx->launches - l0;            // nothing ran yet: undo the bookkeeping of the capture
+        d.graph_interactions = ctx->interactions - i0;
+        ctx->launches = l0;
+        ctx->interactions = i0;
+        if (rc != NBODY_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        CU(e);
+        e = cudaGraphInstantiate(&d.graph, g, 0);
+        cudaGraphDestroy(g);
+        CU(e);
+        d.graph_dt = dt;
+        d.graph_cur = d.cur;                              // two steps flip the buffer parity twice
+    }
+    while (remaining >= 2) {
+        CU(cudaGraphLaunch(d.graph, d.stream));
+        ctx->launches += d.graph_launches;
+        ctx->interactions += d.graph_interactions;
+        remaining -= 2;
+    }
+    return NBODY_OK;
+}
+
 int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
 {
     if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
+    // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
+    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->bh && !ctx->profile_next && nsteps >= 8;
+    const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && ctx->n_padded <= 32768);
+    if (graph_ok && want) {
+        int rc = step_with_graph(ctx, dt, nsteps);
+        if (rc != NBODY_OK) return rc;
+    }
     for (int s = 0; s < nsteps; ++s) {
         const bool prof = ctx->profile_next && s == 0;
         int rc = enqueue_step(ctx, dt, false, prof);
@@ -722,7 +780,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
         ctx->devs[0].bh.node_count(ctx->n, ctx->devs[0].stream, &m);
         info->bh_nodes = m;
     }
-    info->graph = 0;
+    info->graph = (d0.graph != nullptr) ? 1 : 0;
     info->kernel_launches = ctx->launches;
     info->interactions = ctx->interactions;
     info->last_force_ms = ctx->last_force_ms;

@@ -38,6 +38,13 @@ def spinning_disc(n, seed=12345, scale=100.0, spin=0.3, mass=1.0):
     return b
 
 
+def reference_disc(n=25000):
+    """The reference's own scene, Simulation::uniform_disc (Simulation.hpp:347-603), bit-identical."""
+    b = empty_bodies(n)
+    _check(host_lib().nbody_ic_reference_disc(b.ctypes.data, n), "reference_disc")
+    return b
+
+
 def rescale(b, lscale=1.0, vscale=1.0, mscale=1.0):
     assert b.dtype == BODY_DTYPE and b.flags.c_contiguous
     host_lib().nbody_ic_rescale(b.ctypes.data, b.shape[0], lscale, vscale, mscale)
