@@ -5,7 +5,7 @@ HOSTCC  := $(shell [ -x /usr/bin/gcc ] && echo /usr/bin/gcc || echo gcc)
 ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude
 CSRC    := nbodysim_b200/csrc
-CU      := $(CSRC)/nbody_gpu.cu $(CSRC)/force_f32.cu $(CSRC)/force_f64.cu $(CSRC)/layout.cu $(CSRC)/barnes_hut.cu
+CU      := $(CSRC)/nbody_gpu.cu $(CSRC)/force_f32.cu $(CSRC)/force_f64.cu $(CSRC)/layout.cu $(CSRC)/barnes_hut.cu $(CSRC)/collide.cu
 HDR     := $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/force_f32_fast.cuh $(CSRC)/nccl_dyn.h include/nbody_gpu.h include/nbody_body.h
 OBJ     := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(CU))
 

@@ -80,6 +80,12 @@ typedef struct nbody_params {
                                  lane-ops per interaction).  auto uses the uniform-mass form (11 lane-ops;
                                  m factored out of the sum, same per-pair arithmetic otherwise) when
                                  every body has the same mass. */
+    int32_t  collide;         /* 1 = run the reference's collision pass after every step's integration
+                                 (Simulation::collide + resolve, Simulation.hpp:216-346): Simulation::step()
+                                 becomes nbody_gpu_step.  2-D fp32, one GPU.  Pairs are resolved in the
+                                 canonical order "sorted by (first, second)"; the reference's order is the
+                                 unspecified iteration order of an unordered_map, so results are bit-identical
+                                 whenever the colliding pairs of a step are disjoint. */
     int32_t  bh_fix_near_leaves; /* Barnes-Hut only.  0 = the reference's behaviour: a NEAR leaf contributes
                                  nothing (insert() leaves every body Range empty, Quadtree.hpp:133-147);
                                  1 = add the leaf's body for near leaves (self excluded) */
@@ -166,6 +172,12 @@ int nbody_gpu_energy(nbody_ctx *ctx, double *K, double *W, double P[3]);
 int nbody_gpu_profile_next_step(nbody_ctx *ctx, int enable);
 
 int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info);
+
+/* Run one collision pass on the current state (the reference's collide(), outside a step). */
+int nbody_gpu_collide(nbody_ctx *ctx);
+/* Counters of the last collision pass: candidate pairs kept after the broad phase and the pairs that
+ * passed resolve()'s overlap test.  Synchronises. */
+int nbody_gpu_collide_stats(nbody_ctx *ctx, uint32_t *candidate_pairs, uint32_t *resolved_pairs);
 
 /* Barnes-Hut diagnostics / parity: the node array of the last tree built, in walk (depth-first,
  * quadrant) order, WITHOUT the reference's empty leaves.  f6 = 6 floats per node: position (body or

@@ -43,6 +43,7 @@ class NbodyParams(C.Structure):
         ("fuse_integrator", C.c_int32),
         ("use_graph", C.c_int32),
         ("force_variant", C.c_int32),
+        ("collide", C.c_int32),
         ("bh_fix_near_leaves", C.c_int32),
         ("bh_walk", C.c_int32),
         ("ngpus", C.c_int32),
@@ -96,6 +97,8 @@ GPU_SYMBOLS = {
     "nbody_gpu_energy": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nbody_gpu_profile_next_step": (C.c_int, [C.c_void_p, C.c_int]),
     "nbody_gpu_get_info": (C.c_int, [C.c_void_p, C.POINTER(NbodyInfo)]),
+    "nbody_gpu_collide": (C.c_int, [C.c_void_p]),
+    "nbody_gpu_collide_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "nbody_gpu_bh_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nbody_gpu_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "nbody_gpu_shutdown": (None, [C.c_void_p]),

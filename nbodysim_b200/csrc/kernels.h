@@ -118,4 +118,17 @@ struct BhWorkspace {
     cudaError_t download_nodes(float *f6, unsigned *u2, size_t cap, cudaStream_t st);
 };
 
+// collision pass (collide.cu)
+struct CollideWorkspace {
+    size_t n_cap = 0;
+    unsigned entry_cap = 0, pair_cap = 0;
+    void *keys_in = nullptr, *keys = nullptr, *vals_in = nullptr, *vals = nullptr;
+    void *pairs_in = nullptr, *pairs = nullptr, *hot = nullptr, *counters = nullptr, *temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t alloc(size_t n);
+    void release();
+    cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches);
+    cudaError_t stats(cudaStream_t st, unsigned out[4]);
+};
+
 } // namespace nb

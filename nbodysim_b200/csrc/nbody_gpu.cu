@@ -48,6 +48,7 @@ struct Dev {
     bool small_tile = false;      // fast kernel runs the 256-target tile geometry (small shards)
     int force_ctas = 0;
     BhWorkspace bh;               // Barnes-Hut path only
+    CollideWorkspace col;         // collision pass only
     // CUDA graph of two consecutive steps (buffer parity returns to the start), keyed on dt and parity
     cudaGraphExec_t graph = nullptr;
     float graph_dt = 0.f;
@@ -215,6 +216,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaMalloc(&d.accp, shard * (size_t)std::max(1, d.nslots)));
     CU(cudaMalloc(&d.aos, ctx->n_padded * sizeof(nbody_body_t)));
     CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
+    if (ctx->p.collide) CU(d.col.alloc(ctx->n));
     if (ctx->bh) {
         CU(d.bh.alloc(ctx->n));
         d.bh.warp_walk = (ctx->p.bh_walk == 1);
@@ -336,6 +338,11 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             CU(ctx->f64 ? launch_integrate_f64(I, d.stream) : launch_integrate_f32(I, d.stream));
             ctx->launches++;
         }
+        if (ctx->p.collide && !acc_only) { // Simulation::step(): iterate(dt) ; collide()
+            int nl = 0;
+            CU(d.col.run((float *)d.posm[d.cur ^ 1], (float *)d.vel, ctx->n, d.stream, &nl));
+            ctx->launches += (unsigned long long)nl;
+        }
         if (prof) CU(cudaEventRecord(d.ev_t[2], d.stream));
         if (!acc_only) {
             size_t real = 0;
@@ -393,6 +400,7 @@ void free_all(nbody_ctx *c)
         if (d.aos) cudaFree(d.aos);
         if (d.energy5) cudaFree(d.energy5);
         d.bh.release();
+        d.col.release();
         if (d.graph) cudaGraphExecDestroy(d.graph);
         if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
         if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
@@ -455,6 +463,10 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     }
     if (p->force_algo != NBODY_FORCE_ALLPAIRS && p->force_algo != NBODY_FORCE_BARNES_HUT) {
         set_err(nullptr, "nbody_gpu_init: unknown force_algo %d", p->force_algo);
+        return NBODY_EINVAL;
+    }
+    if (p->collide && (p->dims != 2 || p->precision != NBODY_PRECISION_F32 || std::max(1, p->ngpus) > 1 || p->world > 1)) {
+        set_err(nullptr, "nbody_gpu_init: the collision pass is the reference's 2-D fp32 collide() on one GPU");
         return NBODY_EINVAL;
     }
     if (p->force_algo == NBODY_FORCE_BARNES_HUT && (p->dims != 2 || p->precision != NBODY_PRECISION_F32)) {
@@ -606,7 +618,7 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
 {
     if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
     // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
-    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->bh && !ctx->profile_next && nsteps >= 8;
+    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->bh && !ctx->p.collide && !ctx->profile_next && nsteps >= 8;
     const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && ctx->n_padded <= 32768);
     if (graph_ok && want) {
         int rc = step_with_graph(ctx, dt, nsteps);
@@ -785,6 +797,32 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->interactions = ctx->interactions;
     info->last_force_ms = ctx->last_force_ms;
     info->last_integ_ms = ctx->last_integ_ms;
+    return NBODY_OK;
+}
+
+int nbody_gpu_collide(nbody_ctx *ctx)
+{
+    if (!ctx) return NBODY_EINVAL;
+    if (!ctx->p.collide) return NBODY_ESTATE;
+    Dev &d = ctx->devs[0];
+    CU(cudaSetDevice(d.device));
+    int nl = 0;
+    CU(d.col.run((float *)d.posm[d.cur], (float *)d.vel, ctx->n, d.stream, &nl));
+    ctx->launches += (unsigned long long)nl;
+    return NBODY_OK;
+}
+
+int nbody_gpu_collide_stats(nbody_ctx *ctx, uint32_t *candidate_pairs, uint32_t *resolved_pairs)
+{
+    if (!ctx) return NBODY_EINVAL;
+    if (!ctx->p.collide) return NBODY_ESTATE;
+    Dev &d = ctx->devs[0];
+    CU(cudaSetDevice(d.device));
+    unsigned c[4] = {0, 0, 0, 0};
+    CU(d.col.stats(d.stream, c));
+    if (c[2]) { set_err(ctx, "collision pass: grid entry / pair buffer overflow (radii far larger than the 600-unit cells?)"); return NBODY_ESTATE; }
+    if (candidate_pairs) *candidate_pairs = c[1];
+    if (resolved_pairs) *resolved_pairs = c[3];
     return NBODY_OK;
 }
 

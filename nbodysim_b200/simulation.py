@@ -106,6 +106,16 @@ class Simulation:
         self._check(self._lib.nbody_gpu_energy(self._ctx, C.byref(K), C.byref(W), P))
         return K.value, W.value, np.array(list(P))
 
+    def collide(self):
+        """Simulation::collide(): one collision pass on the current state."""
+        self._check(self._lib.nbody_gpu_collide(self._ctx))
+
+    def collide_stats(self):
+        """(candidate pairs, resolved pairs) of the last collision pass."""
+        a, b = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.nbody_gpu_collide_stats(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def bh_nodes(self):
         """Barnes-Hut node array of the last tree built, in walk order:
         (f6[n,6] = x, y, mass, cx, cy, size ; next[n] ; depth[n] ; is_leaf[n])."""

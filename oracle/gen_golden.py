@@ -107,6 +107,38 @@ def main():
     np.savez_compressed(os.path.join(OUT, "bh2000.npz"), bodies=bh, theta=np.float32(1.0), eps=np.float32(1.0),
                         dt=np.float32(0.01), nsteps=10, acc=acc_bh, acc_theta05=acc_bh05, nnodes=nnodes,
                         end_pos=it["pos"], end_vel=it["vel"], end_acc=it["acc"])
+    # 8. collision pass (Simulation::collide + resolve) on scenes whose colliding pairs are disjoint, so the
+    #    reference's unspecified pair order cannot matter; and the reference's WHOLE step (Simulation::step =
+    #    BH iterate + clamp + boundary + collide) over 8 steps on such a scene.
+    def scene(n, L, rmax, seed, vsig=30.0):
+        r = np.random.default_rng(seed)
+        c = empty_bodies(n)
+        c["pos"] = r.uniform(-L, L, (n, 2))
+        c["vel"] = r.normal(0, vsig, (n, 2))
+        c["mass"] = r.uniform(0.1, 5, n)
+        c["radius"] = r.uniform(0.2 * rmax, rmax, n)
+        return c
+
+    col = scene(5000, 20000, 40, 2)
+    after = clean(O.ref_collide(col))
+    ora, npairs, nres = O.orc_collide(col)
+    assert nres > 20 and all(np.array_equal(ora[f].view(np.uint32), after[f].view(np.uint32)) for f in ("pos", "vel")), \
+        "collision golden scene is order-dependent; pick another seed"
+    st = scene(4000, 9000, 30, 7, vsig=60.0)
+    cur, ocur, tot = st.copy(), st.copy(), 0
+    for _ in range(8):
+        R.ref_step_full(cur.ctypes.data, 4000, 1.0, 1.0, 0.01, 1)
+        ocur["acc"] = O.orc_bh_acc(ocur, 1.0, 1.0)
+        O.oracle().orc_iterate_after_attract(ocur.ctypes.data, 4000, 0.01, 3, 2)
+        ocur, _, k = O.orc_collide(ocur)
+        tot += k
+        assert all(np.array_equal(ocur[f].view(np.uint32), cur[f].view(np.uint32)) for f in ("pos", "vel")), \
+            "step golden scene is order-dependent; pick another seed"
+    assert tot > 10
+    cur = clean(cur)
+    np.savez_compressed(os.path.join(OUT, "collide.npz"), bodies=col, after_pos=after["pos"], after_vel=after["vel"],
+                        resolved=nres, step_bodies=st, step_nsteps=8, step_dt=np.float32(0.01), step_resolved=tot,
+                        step_end_pos=cur["pos"], step_end_vel=cur["vel"], step_end_acc=cur["acc"])
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -393,3 +393,135 @@ void orc_bh_acc(const orc_node_t *nodes, size_t nnodes, float theta, float eps, 
 }
 
 void orc_free(void *p) { free(p); }
+
+/* ============================================================================ collision pass */
+/* SpatialGrid::hash_position, Simulation.hpp:31-34: int arithmetic (wraps in practice), widened to size_t */
+static uint64_t hash_position(int x, int y)
+{
+    const uint32_t h = (((uint32_t)x * 92837111u) ^ ((uint32_t)y * 689287499u)) * 15485863u;
+    return (uint64_t)(int64_t)(int32_t)h;
+}
+
+/* Simulation::resolve, Simulation.hpp:293-346.  b1/b2 alias bodies[i]/bodies[j] in the reference, so
+ * every read below happens at the same point of the update sequence as there. */
+int orc_resolve(orc_body_t *B, size_t i, size_t j)
+{
+    orc_body_t *b1 = &B[i], *b2 = &B[j];
+    float dx = b2->px - b1->px, dy = b2->py - b1->py;
+    const float r = b1->radius + b2->radius;
+    if (dx * dx + dy * dy > r * r) return 0;
+    const float vx = b2->vx - b1->vx, vy = b2->vy - b1->vy;
+    const float d_dot_v = dx * vx + dy * vy; /* Vec2::dot (dpps 0x31 == product, product, add) */
+    const float m1 = b1->mass, m2 = b2->mass;
+    const float weight1 = m2 / (m1 + m2);
+    const float weight2 = m1 / (m1 + m2);
+    if (d_dot_v >= 0.0f && !(dx == 0.0f && dy == 0.0f)) { /* separating: push apart, :312-318 */
+        const float k = r / sqrtf(dx * dx + dy * dy) - 1.0f;
+        const float tx = dx * k, ty = dy * k;
+        b1->px -= tx * weight1; b1->py -= ty * weight1;
+        b2->px += tx * weight2; b2->py += ty * weight2;
+        return 1;
+    }
+    const float v_sq = vx * vx + vy * vy;
+    const float d_sq = dx * dx + dy * dy;
+    const float r_sq = r * r;
+    float disc = d_dot_v * d_dot_v - v_sq * (d_sq - r_sq);
+    if (disc < 0.0f) disc = 0.0f;
+    const float t = (d_dot_v + sqrtf(disc)) / v_sq;
+    b1->px -= b1->vx * t; b1->py -= b1->vy * t;           /* rewind to the moment of contact */
+    b2->px -= b2->vx * t; b2->py -= b2->vy * t;
+    const float ndx = b2->px - b1->px, ndy = b2->py - b1->py;
+    const float nd_dot_v = ndx * vx + ndy * vy;
+    const float nd_sq = ndx * ndx + ndy * ndy;
+    const float k = 1.5f * nd_dot_v / nd_sq;              /* new_d * (1.5f * new_d_dot_v / new_d_sq) */
+    const float tx = ndx * k, ty = ndy * k;
+    const float v1x = b1->vx + tx * weight1, v1y = b1->vy + ty * weight1;
+    const float v2x = b2->vx - tx * weight2, v2y = b2->vy - ty * weight2;
+    b1->vx = v1x; b1->vy = v1y;
+    b2->vx = v2x; b2->vy = v2y;
+    b1->px += v1x * t; b1->py += v1y * t;
+    b2->px += v2x * t; b2->py += v2y * t;
+    return 1;
+}
+
+typedef struct { uint64_t key; uint32_t body; } cell_entry_t;
+typedef struct { float value; uint32_t body; int is_end; } sweep_entry_t;
+typedef struct { uint32_t a, b; } pair_t;
+
+static int cmp_cell(const void *pa, const void *pb)
+{
+    const cell_entry_t *a = (const cell_entry_t *)pa, *b = (const cell_entry_t *)pb;
+    if (a->key != b->key) return a->key < b->key ? -1 : 1;
+    return (a->body > b->body) - (a->body < b->body);
+}
+static int cmp_sweep(const void *pa, const void *pb) /* SweepEntry::operator<, :43-46 */
+{
+    const sweep_entry_t *a = (const sweep_entry_t *)pa, *b = (const sweep_entry_t *)pb;
+    if (a->value != b->value) return a->value < b->value ? -1 : 1;
+    if (a->is_end != b->is_end) return a->is_end < b->is_end ? -1 : 1;
+    return (a->body > b->body) - (a->body < b->body); /* exact ties: unspecified in the reference */
+}
+static int cmp_pair(const void *pa, const void *pb)
+{
+    const pair_t *a = (const pair_t *)pa, *b = (const pair_t *)pb;
+    if (a->a != b->a) return a->a < b->a ? -1 : 1;
+    return (a->b > b->b) - (a->b < b->b);
+}
+
+size_t orc_collide(orc_body_t *B, size_t n, size_t *resolved)
+{
+    const float CELL = 600.0f;
+    size_t ne = 0, cap = 4 * n + 64;
+    cell_entry_t *ent = (cell_entry_t *)malloc(cap * sizeof *ent);
+    for (size_t i = 0; i < n; ++i) { /* :224-243 */
+        const float r = B[i].radius;
+        const int minX = (int)((B[i].px - r) / CELL), maxX = (int)((B[i].px + r) / CELL);
+        const int minY = (int)((B[i].py - r) / CELL), maxY = (int)((B[i].py + r) / CELL);
+        for (int y = minY; y <= maxY; ++y)
+            for (int x = minX; x <= maxX; ++x) {
+                if (ne == cap) { cap *= 2; ent = (cell_entry_t *)realloc(ent, cap * sizeof *ent); }
+                ent[ne].key = hash_position(x, y);
+                ent[ne].body = (uint32_t)i;
+                ++ne;
+            }
+    }
+    qsort(ent, ne, sizeof *ent, cmp_cell);
+    size_t np = 0, pcap = 1024;
+    pair_t *pairs = (pair_t *)malloc(pcap * sizeof *pairs);
+    sweep_entry_t *sw = NULL; uint32_t *active = NULL; size_t swcap = 0;
+    for (size_t s = 0; s < ne;) {
+        size_t e = s;
+        while (e < ne && ent[e].key == ent[s].key) ++e;
+        const size_t k = e - s;
+        if (k > 1) { /* :247-283 */
+            if (2 * k > swcap) { swcap = 2 * k; sw = (sweep_entry_t *)realloc(sw, swcap * sizeof *sw); active = (uint32_t *)realloc(active, swcap * sizeof *active); }
+            for (size_t q = 0; q < k; ++q) {
+                const orc_body_t *bd = &B[ent[s + q].body];
+                sw[2 * q] = (sweep_entry_t){bd->px - bd->radius, ent[s + q].body, 0};
+                sw[2 * q + 1] = (sweep_entry_t){bd->px + bd->radius, ent[s + q].body, 1};
+            }
+            qsort(sw, 2 * k, sizeof *sw, cmp_sweep);
+            size_t na = 0;
+            for (size_t q = 0; q < 2 * k; ++q) {
+                if (!sw[q].is_end) {
+                    for (size_t a = 0; a < na; ++a) {
+                        if (np == pcap) { pcap *= 2; pairs = (pair_t *)realloc(pairs, pcap * sizeof *pairs); }
+                        pairs[np].a = active[a]; pairs[np].b = sw[q].body; ++np;
+                    }
+                    active[na++] = sw[q].body;
+                } else {
+                    size_t w = 0;
+                    for (size_t a = 0; a < na; ++a) if (active[a] != sw[q].body) active[w++] = active[a];
+                    na = w;
+                }
+            }
+        }
+        s = e;
+    }
+    qsort(pairs, np, sizeof *pairs, cmp_pair); /* canonical order (the reference's is unspecified) */
+    size_t nres = 0;
+    for (size_t p = 0; p < np; ++p) nres += (size_t)orc_resolve(B, pairs[p].a, pairs[p].b);
+    if (resolved) *resolved = nres;
+    free(ent); free(pairs); free(sw); free(active);
+    return np;
+}

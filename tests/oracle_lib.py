@@ -51,6 +51,9 @@ def oracle():
         L.orc_bh_build.argtypes = [_vp, _sz, C.POINTER(_vp)]
         L.orc_bh_acc.argtypes = [_vp, _sz, _f, _f, _vp, _sz, _sz, _i, _vp]
         L.orc_free.argtypes = [_vp]
+        L.orc_collide.restype = _sz
+        L.orc_collide.argtypes = [_vp, _sz, C.POINTER(_sz)]
+        L.orc_resolve.argtypes = [_vp, _sz, _sz]
         _oracle = L
     return _oracle
 
@@ -169,3 +172,17 @@ def ref_bh_nodes(b, theta=1.0, eps=1.0, kind="strict"):
     m = reference(kind).ref_bh_nodes(b.ctypes.data, b.shape[0], theta, eps, f.ctypes.data, u.ctypes.data, cap)
     assert m <= cap
     return f[:m], u[:m]
+
+
+def orc_collide(b):
+    """returns (bodies after the collision pass, broad-phase pairs, resolved pairs)"""
+    b = b.copy()
+    res = _sz()
+    npairs = oracle().orc_collide(b.ctypes.data, b.shape[0], C.byref(res))
+    return b, npairs, res.value
+
+
+def ref_collide(b, kind="strict"):
+    b = b.copy()
+    reference(kind).ref_collide(b.ctypes.data, b.shape[0])
+    return b

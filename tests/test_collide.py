@@ -1,0 +1,128 @@
+"""Collision pass (Simulation::collide + resolve, Simulation.hpp:216-346): oracle restatement vs golden /
+compiled reference on CPU; GPU pass through the C ABI vs golden (bit-exact where the reference's pair
+order cannot matter) and vs the oracle's canonical order on chain-heavy scenes."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from nbodysim_b200 import Simulation, capi
+from nbodysim_b200.bodies import empty_bodies
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def scene(n, L, rmax, seed, vsig=30.0):
+    r = np.random.default_rng(seed)
+    c = empty_bodies(n)
+    c["pos"] = r.uniform(-L, L, (n, 2))
+    c["vel"] = r.normal(0, vsig, (n, 2))
+    c["mass"] = r.uniform(0.1, 5, n)
+    c["radius"] = r.uniform(0.2 * rmax, rmax, n)
+    return c
+
+
+def momentum(b):
+    return (b["mass"].astype(np.float64)[:, None] * b["vel"].astype(np.float64)).sum(0)
+
+
+# ------------------------------------------------------------------ CPU: oracle
+def test_oracle_collide_golden():
+    g = np.load(os.path.join(G, "collide.npz"))
+    out, npairs, nres = O.orc_collide(g["bodies"])
+    assert nres == int(g["resolved"]) and npairs >= nres
+    assert np.array_equal(bits(out["pos"]), bits(g["after_pos"])) and np.array_equal(bits(out["vel"]), bits(g["after_vel"]))
+
+
+def test_oracle_full_step_golden():
+    """Simulation::step() = BH iterate (clamp + boundary) + collide, 8 steps"""
+    g = np.load(os.path.join(G, "collide.npz"))
+    b = g["step_bodies"].copy()
+    tot = 0
+    for _ in range(int(g["step_nsteps"])):
+        b["acc"] = O.orc_bh_acc(b, 1.0, 1.0)
+        O.oracle().orc_iterate_after_attract(b.ctypes.data, b.shape[0], float(g["step_dt"]), 3, 2)
+        b, _, k = O.orc_collide(b)
+        tot += k
+    assert tot == int(g["step_resolved"])
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(b[f]), bits(g["step_end_" + f])), f
+
+
+def test_oracle_resolve_conserves_momentum_and_separates():
+    b = scene(3000, 1500, 25, 4)            # dense: chains of collisions
+    out, npairs, nres = O.orc_collide(b)
+    assert nres > 500
+    assert np.abs(momentum(out) - momentum(b)).max() <= 1e-3 * np.abs(b["mass"][:, None] * b["vel"]).sum()
+    assert np.isfinite(out["pos"]).all() and np.isfinite(out["vel"]).all()
+
+
+@pytest.mark.skipif(O.reference("strict") is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("n,L,rmax,seed", [(2000, 3000, 15, 1), (5000, 20000, 40, 2), (20000, 80000, 60, 3)])
+def test_oracle_collide_vs_reference_when_order_cannot_matter(n, L, rmax, seed):
+    b = scene(n, L, rmax, seed)
+    out, _, nres = O.orc_collide(b)
+    ref = O.ref_collide(b)
+    assert nres > 10
+    assert np.array_equal(bits(out["pos"]), bits(ref["pos"])) and np.array_equal(bits(out["vel"]), bits(ref["vel"]))
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_gpu_collide_bitexact_vs_golden():
+    g = np.load(os.path.join(G, "collide.npz"))
+    with Simulation(g["bodies"], dims=2, eps=1.0, collide=1) as s:
+        s.collide()
+        out = s.bodies.copy()
+        cand, res = s.collide_stats()
+    assert res == int(g["resolved"])
+    assert np.array_equal(bits(out["pos"]), bits(g["after_pos"])) and np.array_equal(bits(out["vel"]), bits(g["after_vel"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,L,rmax,seed", [(3000, 1500, 25, 4), (20000, 80000, 60, 3), (1000, 300, 30, 9)])
+def test_gpu_collide_equals_oracle_canonical_order(n, L, rmax, seed):
+    """chains included: the GPU pass and the oracle resolve in the same canonical order"""
+    b = scene(n, L, rmax, seed)
+    want, _, nres = O.orc_collide(b)
+    with Simulation(b, dims=2, eps=1.0, collide=1) as s:
+        s.collide()
+        out = s.bodies.copy()
+        cand, res = s.collide_stats()
+    assert res == nres
+    assert np.array_equal(bits(out["pos"]), bits(want["pos"])) and np.array_equal(bits(out["vel"]), bits(want["vel"]))
+
+
+@pytest.mark.gpu
+def test_gpu_full_reference_step_bitexact_vs_golden():
+    """nbody_gpu_step with BH + clamp + boundary + collide == Simulation::step(), 8 steps, bit for bit"""
+    g = np.load(os.path.join(G, "collide.npz"))
+    with Simulation(g["step_bodies"], dt=float(g["step_dt"]), dims=2, theta=1.0, eps=1.0, collide=1,
+                    force_algo=capi.FORCE_BARNES_HUT, rsqrt_mode=capi.RSQRT_REFCOMPAT,
+                    integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
+        s.step(int(g["step_nsteps"]))
+        out = s.bodies
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(out[f]), bits(g["step_end_" + f])), f
+
+
+@pytest.mark.gpu
+def test_gpu_collide_inert_for_zero_radii_and_rejected_in_3d():
+    import ctypes as C
+    from nbodysim_b200 import ic
+    from nbodysim_b200.simulation import default_params
+
+    b = ic.spinning_disc(2000, seed=3)
+    with Simulation(b, dims=2, eps=1.0, collide=1) as s:
+        s.collide()
+        out = s.bodies.copy()
+        assert s.collide_stats()[1] == 0
+    assert np.array_equal(bits(out["pos"]), bits(b["pos"]))
+    p = default_params(dims=3, collide=1)
+    ctx = C.c_void_p()
+    assert capi.gpu_lib().nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 2000) == capi.EINVAL

@@ -52,5 +52,29 @@ def main():
         print(json.dumps(row), flush=True)
 
 
+def reference_scene():
+    """The reference's own shipped configuration end to end: uniform_disc(25000), theta=1, eps=1, dt=0.01,
+    Simulation::step() = BH iterate (clamp + boundary) + collide -- GPU vs the reference on the host cores."""
+    n = 25000
+    b = ic.reference_disc(n)
+    row = {"scene": "reference uniform_disc", "n": n}
+    with Simulation(b, dt=0.01, force_algo=capi.FORCE_BARNES_HUT, dims=2, theta=1.0, eps=1.0, collide=1,
+                    rsqrt_mode=capi.RSQRT_REFCOMPAT, integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
+        s.step(5); s.sync()
+        t0 = time.perf_counter(); s.step(200); s.sync()
+        row["gpu_full_step_ms"] = 1e3 * (time.perf_counter() - t0) / 200
+    R = O.reference("fast")
+    if R is not None:
+        c = b.copy()
+        R.ref_step_full(c.ctypes.data, n, 1.0, 1.0, 0.01, 2)
+        t0 = time.perf_counter()
+        R.ref_step_full(c.ctypes.data, n, 1.0, 1.0, 0.01, 20)
+        row["cpu_reference_step_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+        row["cpu_threads"] = os.cpu_count()
+        row["speedup"] = row["cpu_reference_step_ms"] / row["gpu_full_step_ms"]
+    print(json.dumps(row), flush=True)
+
+
 if __name__ == "__main__":
+    reference_scene()
     main()
