@@ -71,3 +71,16 @@ def test_two_gpu_f64_matches_exact():
         _, _, a = s.download_f64()
     ex = O.orc_exact_acc(b, float(np.float32(0.01)), dims=3)
     assert (np.linalg.norm(a - ex, axis=1) / np.linalg.norm(ex, axis=1)).max() <= 1e-12
+
+
+@needs2
+def test_two_gpu_barnes_hut_bitexact_vs_golden():
+    """every GPU builds the (replicated) tree and walks its own shard of targets: still bit-exact"""
+    g = np.load(os.path.join(G, "bh2000.npz"))
+    with Simulation(g["bodies"], dt=float(g["dt"]), dims=2, theta=1.0, eps=1.0, force_algo=capi.FORCE_BARNES_HUT,
+                    rsqrt_mode=capi.RSQRT_REFCOMPAT, integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY,
+                    ngpus=2, device_ids=[0, 1]) as s:
+        s.step(int(g["nsteps"]))
+        out = s.bodies
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(out[f]), bits(g["end_" + f])), f
