@@ -6,10 +6,10 @@ ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude
 CSRC    := nbodysim_b200/csrc
 CU      := $(CSRC)/nbody_gpu.cu $(CSRC)/force_f32.cu $(CSRC)/force_f64.cu $(CSRC)/layout.cu $(CSRC)/barnes_hut.cu $(CSRC)/collide.cu
-HDR     := $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/force_f32_fast.cuh $(CSRC)/nccl_dyn.h include/nbody_gpu.h include/nbody_body.h
+HDR     := $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/force_f32_fast.cuh $(CSRC)/radix_sort.cuh $(CSRC)/nccl_dyn.h include/nbody_gpu.h include/nbody_body.h
 OBJ     := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(CU))
 
-all: lib host oracle
+all: lib host oracle tools
 
 lib: nbodysim_b200/libnbody_gpu.so
 build/obj/%.o: $(CSRC)/%.cu $(HDR)
@@ -30,7 +30,10 @@ oracle:
 	$(MAKE) -C oracle all
 
 # tuning / microbenchmark harnesses (not part of the product path)
-tools: build/kbench build/ubench
+tools: build/kbench build/ubench build/sort_check
+build/sort_check: tools/sort_check.cu $(CSRC)/radix_sort.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -o $@ $<
 build/kbench: tools/kbench.cu $(HDR)
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -o $@ $<

@@ -45,6 +45,7 @@ class NbodyParams(C.Structure):
         ("force_variant", C.c_int32),
         ("collide", C.c_int32),
         ("bh_fix_near_leaves", C.c_int32),
+        ("sort_impl", C.c_int32),
         ("bh_walk", C.c_int32),
         ("ngpus", C.c_int32),
         ("device_ids", C.c_int32 * NBODY_MAX_GPUS),

@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include "radix_sort.cuh"
 
 namespace nb {
 
@@ -377,7 +378,7 @@ cudaError_t BhWorkspace::alloc(size_t n)
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
-    temp_bytes = std::max(t1, t2);
+    temp_bytes = std::max(std::max(t1, t2), radix_sort_temp_bytes(n));
     BH_ALLOC(temp, temp_bytes)
     {   // co-resident grid size for the cooperative propagate kernel
         int dev = 0, sms = 0, per_sm = 0;
@@ -418,8 +419,13 @@ cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int
     bh_root_kernel<<<1, 1, 0, st>>>((const unsigned *)box, (BhRoot *)root);
     bh_keys_kernel<<<g256, 256, 0, st>>>(posm, n, (const BhRoot *)root, (unsigned long long *)keys_in, (unsigned *)idx_in);
     size_t tb = temp_bytes;
-    if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
-                                             (const unsigned *)idx_in, (unsigned *)idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
+    if (own_sort) { // stable LSD sort; the result lands back in the first buffer pair -> swap roles
+        if ((e = radix_sort_u64((unsigned long long *)keys_in, (unsigned long long *)keys, (unsigned *)idx_in, (unsigned *)idx,
+                                n, temp, st, 0, 64, launches)) != cudaSuccess) return e;
+        std::swap(keys_in, keys);
+        std::swap(idx_in, idx);
+    } else if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
+                                                    (const unsigned *)idx_in, (unsigned *)idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
     bh_count_kernel<<<g256, 256, 0, st>>>((const unsigned long long *)keys, n, cnt, (unsigned char *)first,
                                           (unsigned char *)leaf, cnt + n + 1);
     tb = temp_bytes;

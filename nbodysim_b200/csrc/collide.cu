@@ -16,6 +16,7 @@
 // reference); collisions are rare events (none in the first steps of the shipped scene).
 #include "kernels.h"
 #include <cub/device/device_radix_sort.cuh>
+#include "radix_sort.cuh"
 
 namespace nb {
 
@@ -169,7 +170,7 @@ cudaError_t CollideWorkspace::alloc(size_t n)
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)entry_cap, 0, 64);
     cub::DeviceRadixSort::SortKeys(nullptr, t2, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)pair_cap, 0, 64);
-    temp_bytes = std::max(t1, t2);
+    temp_bytes = std::max(std::max(t1, t2), radix_sort_temp_bytes(std::max<size_t>(entry_cap, pair_cap)));
     COL_ALLOC(temp, temp_bytes)
 #undef COL_ALLOC
     n_cap = n;
@@ -201,8 +202,13 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     if (h[2] || h[0] == 0) return cudaSuccess;                  // overflow is reported by nbody_gpu_collide_stats
     const unsigned ne = h[0], ge = (ne + 255) / 256;
     size_t tb = temp_bytes;
-    if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
-                                             (const unsigned *)vals_in, (unsigned *)vals, (int)ne, 0, 64, st)) != cudaSuccess) return e;
+    if (own_sort) {
+        if ((e = radix_sort_u64((unsigned long long *)keys_in, (unsigned long long *)keys, (unsigned *)vals_in, (unsigned *)vals,
+                                ne, temp, st, 0, 64, launches)) != cudaSuccess) return e;
+        std::swap(keys_in, keys);
+        std::swap(vals_in, vals);
+    } else if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
+                                                    (const unsigned *)vals_in, (unsigned *)vals, (int)ne, 0, 64, st)) != cudaSuccess) return e;
     for (int pass = 0; pass < 2; ++pass)
         col_pairs_kernel<<<ge, 256, 0, st>>>(posm, vel, (const unsigned long long *)keys, (const unsigned *)vals, cnt,
                                              (unsigned char *)hot, pass, (unsigned long long *)pairs_in, pair_cap, cnt);
@@ -211,8 +217,12 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     if (h[2] || h[1] == 0) return cudaSuccess;
     const unsigned np = std::min(h[1], pair_cap);
     tb = temp_bytes;
-    if ((e = cub::DeviceRadixSort::SortKeys(temp, tb, (const unsigned long long *)pairs_in, (unsigned long long *)pairs,
-                                            (int)np, 0, 64, st)) != cudaSuccess) return e;
+    if (own_sort) {
+        if ((e = radix_sort_u64((unsigned long long *)pairs_in, (unsigned long long *)pairs, nullptr, nullptr, np, temp, st,
+                                0, 64, launches)) != cudaSuccess) return e;
+        std::swap(pairs_in, pairs);
+    } else if ((e = cub::DeviceRadixSort::SortKeys(temp, tb, (const unsigned long long *)pairs_in, (unsigned long long *)pairs,
+                                                   (int)np, 0, 64, st)) != cudaSuccess) return e;
     col_resolve_kernel<<<1, 32, 0, st>>>(posm, vel, (const unsigned long long *)pairs, pair_cap, cnt);
     if (launches) *launches += 1 + 1;
     return cudaGetLastError();

@@ -109,6 +109,7 @@ struct BhWorkspace {
     int coop_blocks = 148;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
+    bool own_sort = false;       // hand-written radix sort (radix_sort.cuh) instead of cub::DeviceRadixSort
     cudaError_t alloc(size_t n);
     cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);
     void release();
@@ -125,6 +126,7 @@ struct CollideWorkspace {
     void *keys_in = nullptr, *keys = nullptr, *vals_in = nullptr, *vals = nullptr;
     void *pairs_in = nullptr, *pairs = nullptr, *hot = nullptr, *counters = nullptr, *temp = nullptr;
     size_t temp_bytes = 0;
+    bool own_sort = false;
     cudaError_t alloc(size_t n);
     void release();
     cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches);

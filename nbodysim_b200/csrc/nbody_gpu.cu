@@ -216,10 +216,14 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaMalloc(&d.accp, shard * (size_t)std::max(1, d.nslots)));
     CU(cudaMalloc(&d.aos, ctx->n_padded * sizeof(nbody_body_t)));
     CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
-    if (ctx->p.collide) CU(d.col.alloc(ctx->n));
+    if (ctx->p.collide) {
+        CU(d.col.alloc(ctx->n));
+        d.col.own_sort = (ctx->p.sort_impl == 1);
+    }
     if (ctx->bh) {
         CU(d.bh.alloc(ctx->n));
         d.bh.warp_walk = (ctx->p.bh_walk == 1);
+        d.bh.own_sort = (ctx->p.sort_impl == 1);
     }
     return NBODY_OK;
 }

@@ -99,10 +99,12 @@ def test_gpu_collide_equals_oracle_canonical_order(n, L, rmax, seed):
 
 
 @pytest.mark.gpu
-def test_gpu_full_reference_step_bitexact_vs_golden():
-    """nbody_gpu_step with BH + clamp + boundary + collide == Simulation::step(), 8 steps, bit for bit"""
+@pytest.mark.parametrize("sort_impl", [0, 1])
+def test_gpu_full_reference_step_bitexact_vs_golden(sort_impl):
+    """nbody_gpu_step with BH + clamp + boundary + collide == Simulation::step(), 8 steps, bit for bit
+    (with the library radix sort and with the hand-written one)"""
     g = np.load(os.path.join(G, "collide.npz"))
-    with Simulation(g["step_bodies"], dt=float(g["step_dt"]), dims=2, theta=1.0, eps=1.0, collide=1,
+    with Simulation(g["step_bodies"], dt=float(g["step_dt"]), dims=2, theta=1.0, eps=1.0, collide=1, sort_impl=sort_impl,
                     force_algo=capi.FORCE_BARNES_HUT, rsqrt_mode=capi.RSQRT_REFCOMPAT,
                     integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
         s.step(int(g["step_nsteps"]))

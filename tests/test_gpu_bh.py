@@ -84,6 +84,26 @@ def test_bh_acc_bitexact_vs_oracle_seeded(n, seed, theta):
     assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, theta, 1.0)))
 
 
+def test_bh_hand_written_sort_bitexact():
+    b = ic.spinning_disc(50000, seed=23, scale=700.0)
+    b["mass"] = np.random.default_rng(23).uniform(0.1, 3.0, 50000).astype(np.float32)
+    b[100]["pos"] = b[7]["pos"]            # coincident pair: merged in index order -> needs a STABLE sort
+    with bh_sim(b, theta=1.0, eps=1.0, sort_impl=1) as s:
+        s.attract()
+        out = s.download()["acc"].copy()
+    assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, 1.0, 1.0)))
+
+
+def test_radix_sort_checker_tool():
+    """tools/sort_check.cu: the hand-written sort against std::stable_sort on 46 cases"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "sort_check")
+    if not os.path.exists(exe):
+        pytest.skip("build/sort_check not built (make tools)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("walk", [0, 1])
 def test_bh_both_walks_bitexact(walk):
     """per-thread (0) and warp-cooperative (1) walks visit each target's nodes in the same order"""

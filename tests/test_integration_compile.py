@@ -1,0 +1,38 @@
+"""The reference-side binding of INTEGRATION.md compiles: (a) against the reference's own `Body` type
+(where /root/reference exists), (b) as plain C11 and C++17 consumers of the public headers (always)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/Nbodysim/headers"
+CXX = shutil.which("g++") or "g++"
+CC = shutil.which("gcc") or "gcc"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference absent (GPU box)")
+def test_adapter_compiles_against_reference_body(tmp_path):
+    src = os.path.join(ROOT, "tests", "cpp", "adapter_compiles_against_reference.cpp")
+    out = str(tmp_path / "a.o")
+    subprocess.check_call([CXX, "-std=c++20", "-msse4.1", "-w", "-I", REF, "-I", os.path.join(ROOT, "include"),
+                           "-c", src, "-o", out])
+    assert os.path.getsize(out) > 0
+
+
+def test_headers_are_plain_c(tmp_path):
+    src = tmp_path / "c.c"
+    src.write_text('#include "nbody_gpu.h"\n#include "nbody_host.h"\n'
+                   "int f(void){ nbody_params p; nbody_params_default(&p); return (int)sizeof(nbody_body_t) + p.dims; }\n")
+    subprocess.check_call([CC, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "c.o")])
+
+
+def test_c_driver_links_against_the_library(tmp_path):
+    """host/nbody_main.c + libnbody_gpu.so link into an executable (what `make host` does)"""
+    exe = os.path.join(ROOT, "host", "_build", "nbody_run")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "host"])
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage:" in r.stderr

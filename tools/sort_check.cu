@@ -1,0 +1,71 @@
+// tools/sort_check.cu -- correctness + timing of the hand-written radix sort against std::stable_sort
+// (and timing against cub::DeviceRadixSort for reference).  Exit code 0 = all cases identical.
+#include "../nbodysim_b200/csrc/radix_sort.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+#include <vector>
+using namespace nb;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(2); } } while (0)
+
+static int run_case(size_t n, int mode, bool with_vals)
+{
+    std::mt19937_64 rng(n * 7 + mode);
+    std::vector<unsigned long long> k(n);
+    for (auto &x : k) {
+        x = rng();
+        if (mode == 1) x &= 0xffull;                    // heavy duplicates: stability matters
+        if (mode == 2) x = (x & 0xffffull) << 40;       // only the middle bits differ
+        if (mode == 3) x = (unsigned long long)(long long)(int)(x & 0xffffffffu);   // sign-extended 32-bit hashes
+    }
+    std::vector<unsigned> v(n);
+    std::iota(v.begin(), v.end(), 0u);
+    std::vector<unsigned> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return k[a] < k[b]; });
+    unsigned long long *ka, *kb; unsigned *va, *vb; void *tmp;
+    CK(cudaMalloc(&ka, n * 8 + 8)); CK(cudaMalloc(&kb, n * 8 + 8)); CK(cudaMalloc(&va, n * 4 + 4)); CK(cudaMalloc(&vb, n * 4 + 4));
+    CK(cudaMalloc(&tmp, radix_sort_temp_bytes(n)));
+    CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    CK(radix_sort_u64(ka, kb, with_vals ? va : nullptr, vb, n, tmp, 0));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<unsigned long long> ko(n); std::vector<unsigned> vo(n);
+    CK(cudaMemcpy(ko.data(), ka, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(vo.data(), va, n * 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (size_t i = 0; i < n && bad < 5; ++i) {
+        if (ko[i] != k[order[i]] || (with_vals && vo[i] != order[i])) { ++bad; printf("  mismatch at %zu\n", i); }
+    }
+    // cub for the timing comparison
+    float cms = 0;
+    {
+        CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
+        size_t tb = 0; void *ct = nullptr;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, ka, kb, va, vb, (int)n, 0, 64);
+        CK(cudaMalloc(&ct, tb));
+        CK(cudaEventRecord(e0));
+        cub::DeviceRadixSort::SortPairs(ct, tb, ka, kb, va, vb, (int)n, 0, 64);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&cms, e0, e1));
+        cudaFree(ct);
+    }
+    printf("n=%9zu mode=%d vals=%d : %s   own %.3f ms   cub %.3f ms\n", n, mode, (int)with_vals, bad ? "MISMATCH" : "ok", ms, cms);
+    cudaFree(ka); cudaFree(kb); cudaFree(va); cudaFree(vb); cudaFree(tmp);
+    return bad;
+}
+
+int main()
+{
+    int bad = 0;
+    for (size_t n : {1ul, 2ul, 31ul, 33ul, 511ul, 4096ul, 4097ul, 25000ul, 100003ul, 1000000ul, 4194304ul})
+        for (int mode = 0; mode < 4; ++mode) bad += run_case(n, mode, true);
+    bad += run_case(77777, 0, false);
+    bad += run_case(1000000, 3, false);
+    printf(bad ? "FAILED\n" : "ALL OK\n");
+    return bad ? 1 : 0;
+}
