@@ -29,6 +29,7 @@ static void usage(const char *a0)
             "usage: %s [--n N] [--steps K] [--dt DT] [--eps E] [--ic plummer|sphere|galaxy|disc|reference]\n"
             "          [--seed S] [--dims 2|3] [--gpus G] [--precision f32|f64]\n"
             "          [--rsqrt fast|refcompat] [--clamp on|off] [--boundary on|off]\n"
+            "          [--algo allpairs|bh] [--theta T] [--collide on|off]\n"
             "          [--energy-every M] [--in snapshot] [--out snapshot] [--splits S]\n",
             a0);
 }
@@ -60,6 +61,9 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--rsqrt")) { NEED(); p.rsqrt_mode = !strcmp(v, "refcompat") ? NBODY_RSQRT_REFCOMPAT : NBODY_RSQRT_FAST; }
         else if (!strcmp(a, "--clamp")) { NEED(); if (!strcmp(v, "on")) p.integ_flags |= NBODY_INTEG_CLAMP; else p.integ_flags &= ~NBODY_INTEG_CLAMP; }
         else if (!strcmp(a, "--boundary")) { NEED(); if (!strcmp(v, "on")) p.integ_flags |= NBODY_INTEG_BOUNDARY; else p.integ_flags &= ~NBODY_INTEG_BOUNDARY; }
+        else if (!strcmp(a, "--algo")) { NEED(); p.force_algo = !strcmp(v, "bh") ? NBODY_FORCE_BARNES_HUT : NBODY_FORCE_ALLPAIRS; }
+        else if (!strcmp(a, "--theta")) { NEED(); p.theta = (float)atof(v); }
+        else if (!strcmp(a, "--collide")) { NEED(); p.collide = !strcmp(v, "on") ? 1 : 0; }
         else if (!strcmp(a, "--energy-every")) { NEED(); energy_every = atoi(v); }
         else if (!strcmp(a, "--in")) { NEED(); in_path = v; }
         else if (!strcmp(a, "--out")) { NEED(); out_path = v; }
