@@ -314,6 +314,25 @@ def native_arm(args):
         e2e = {"value": n * n * ke / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * 64 * world,
                "d2h_bytes_per_step": min(shard, n) * 64 * world, "steps": ke, "ms_per_step": 1e3 * te / ke}
 
+    # ---------------- the general-mass form of the same kernel, for transparency -------------------
+    # The synthetic Plummer workload has equal masses, so the library runs the uniform-mass form (11 fp32
+    # lane-ops per interaction).  Time the general form (12 lane-ops: the per-source mass multiply stays in
+    # the loop) on the same bodies as well, 3 profiled steps after 2 warm-up steps.
+    general = None
+    if world == 1 and i1["uniform_mass"]:
+        with Simulation(host, **dict(kw, force_variant=0)) as sg:
+            sg.step(2)
+            gf = []
+            for _ in range(3):
+                flush.fill_(1); sg.sync(); torch.cuda.synchronize()
+                sg.profile_next_step(True)
+                sg.step(1)
+                gi = sg.info()
+                gf.append(gi["last_force_ms"] + gi["last_integ_ms"])
+            gms = statistics.mean(gf)
+            general = {"value": n * n / (gms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": gms, "steps": 3,
+                       "note": "force_variant=0: general-mass form (12 lane-ops/interaction), same bodies"}
+
     if rank != 0:
         sim.close()
         if dist is not None:
@@ -371,11 +390,15 @@ def native_arm(args):
         "config": {"workload": wname, "n": n, "dims": 3, "eps": EPS, "dt": DT, "ic_seed": SEED,
                    "rsqrt": "fast (MUFU.RSQ)", "parallelism": f"targets sharded over {world} GPU(s), positions allgathered",
                    "l2": "flushed (256 MiB write) before every timed step", "j_splits": i1["j_splits"],
-                   "force_ctas": i1["force_ctas"], "ctas_per_sm": i1["ctas_per_sm"], "fused_integrator": bool(i1["fused"])},
+                   "force_ctas": i1["force_ctas"], "ctas_per_sm": i1["ctas_per_sm"], "fused_integrator": bool(i1["fused"]),
+                   "mass_form": ("uniform-mass (equal masses detected: 11 fp32 lane-ops per interaction)" if i1["uniform_mass"]
+                                 else "general masses (12 fp32 lane-ops per interaction)")},
         "tflops_20flop": value * FLOP_PER_INTERACTION / 1e3,
         "clocks": dict(clocks or {}, remeasured=remeasured), "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_integrator": roof_integ,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "general_mass_form": general,
     }
+    if general is not None:
+        general["frac_fp32_peak"] = general["value"] * 1e9 * FLOP_PER_INTERACTION / 1e12 / peak_tf
     print(json.dumps(line), flush=True)
     sim.close()
     if dist is not None:
