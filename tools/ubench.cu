@@ -19,12 +19,16 @@ constexpr int K = 8; // independent chains per thread
 // MODE 5: MODE 0 + 1 MUFU per 6 FFMA2
 // MODE 6: MUFU only
 // MODE 7: MODE 1 + 1 MUFU per 3 FFMA2
+// MODE 9 / 10: MODE 2 (FFMA2 a*a+acc, 2 cycles each) + 12 / 24 scalar FFMA per iteration: do packed and
+//               scalar fp32 share one datapath, or can they overlap?
 // MODE 8: FFMA2 scalar-broadcast c     acc[k] = a[k]*a[k] + s  then acc used next iter as a
 template <int MODE>
 __global__ void __launch_bounds__(256) ub(float2 *out, float seed, long long *cycles)
 {
     float2 a[K], b[K], acc[K];
     float m[K];
+    float sc[K], sa[K];
+    for (int k = 0; k < K; ++k) { sc[k] = seed * k; sa[k] = 1.0f + 1e-5f * k + seed * 1e-6f; }
     for (int k = 0; k < K; ++k) {
         a[k] = make_float2(seed + k + threadIdx.x * 1e-3f, seed - k);
         b[k] = make_float2(1.0f + 1e-6f * k, 1.0f - 1e-6f * k);
@@ -44,6 +48,8 @@ __global__ void __launch_bounds__(256) ub(float2 *out, float seed, long long *cy
                 if (MODE == 2) acc[k] = __ffma2_rn(a[k], a[k], acc[k]);
                 if (MODE == 3) { acc[k].x = fmaf(a[k].x, b[k].x, acc[k].x); acc[k].y = fmaf(a[k].y, b[k].y, acc[k].y); }
                 if (MODE == 8) acc[k] = __ffma2_rn(acc[k], a[k], make_float2(seed, seed));
+                if (MODE == 9 || MODE == 10) acc[k] = __ffma2_rn(a[k], a[k], acc[k]);
+                if (MODE == 10 || (MODE == 9 && (k & 1))) sc[k] = fmaf(sc[k], sa[k], sa[k]);
             }
             if (MODE == 4 || MODE == 5) {
 #pragma unroll
@@ -61,7 +67,7 @@ __global__ void __launch_bounds__(256) ub(float2 *out, float seed, long long *cy
     }
     long long t1 = clock64();
     float2 s = make_float2(0.f, 0.f);
-    for (int k = 0; k < K; ++k) { s.x += acc[k].x + m[k]; s.y += acc[k].y; }
+    for (int k = 0; k < K; ++k) { s.x += acc[k].x + m[k]; s.y += acc[k].y + sc[k]; }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
@@ -93,7 +99,7 @@ void run(const char *name, int ctas_per_sm, double fma_per_iter, double mufu_per
 
 int main()
 {
-    for (int c : {1, 2, 4}) {
+    for (int c : {1}) {
         run<0>("FFMA2 3 distinct pairs", c, 24, 0);
         run<1>("FFMA2 shared b (reuse)", c, 24, 0);
         run<2>("FFMA2 a*a+acc (2 pairs)", c, 24, 0);
@@ -103,6 +109,8 @@ int main()
         run<5>("FFMA2 3 distinct + MUFU 1:6", c, 24, 4);
         run<7>("FFMA2 shared b + MUFU 3:8", c, 24, 9);
         run<6>("MUFU only", c, 0, 8);
+        run<9>("FFMA2 a*a+acc + 12 scalar FFMA (x2 col = packed only)", c, 24, 0);
+        run<10>("FFMA2 a*a+acc + 24 scalar FFMA (x2 col = packed only)", c, 24, 0);
     }
     return 0;
 }
