@@ -29,7 +29,7 @@ static void usage(const char *a0)
             "usage: %s [--n N] [--steps K] [--dt DT] [--eps E] [--ic plummer|sphere|galaxy|disc|reference]\n"
             "          [--seed S] [--dims 2|3] [--gpus G] [--precision f32|f64]\n"
             "          [--rsqrt fast|refcompat] [--clamp on|off] [--boundary on|off]\n"
-            "          [--algo allpairs|bh] [--theta T] [--collide on|off]\n"
+            "          [--algo allpairs|bh] [--theta T] [--collide on|off] [--exchange auto|nccl]\n"
             "          [--energy-every M] [--in snapshot] [--out snapshot] [--splits S]\n",
             a0);
 }
@@ -64,6 +64,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--algo")) { NEED(); p.force_algo = !strcmp(v, "bh") ? NBODY_FORCE_BARNES_HUT : NBODY_FORCE_ALLPAIRS; }
         else if (!strcmp(a, "--theta")) { NEED(); p.theta = (float)atof(v); }
         else if (!strcmp(a, "--collide")) { NEED(); p.collide = !strcmp(v, "on") ? 1 : 0; }
+        else if (!strcmp(a, "--exchange")) { NEED(); p.exchange = !strcmp(v, "nccl") ? 1 : 0; }
         else if (!strcmp(a, "--energy-every")) { NEED(); energy_every = atoi(v); }
         else if (!strcmp(a, "--in")) { NEED(); in_path = v; }
         else if (!strcmp(a, "--out")) { NEED(); out_path = v; }
@@ -104,9 +105,9 @@ int main(int argc, char **argv)
     }
     nbody_info info;
     nbody_gpu_get_info(ctx, &info);
-    printf("%s\nn=%zu (padded %llu) dims=%d eps=%g dt=%g gpus=%d sms=%d splits=%d ctas=%d fused=%d\n",
+    printf("%s\nn=%zu (padded %llu) dims=%d eps=%g dt=%g gpus=%d sms=%d splits=%d ctas=%d fused=%d exchange=%s\n",
            nbody_gpu_version(), n, (unsigned long long)info.n_padded, dims, eps, dt, gpus, info.sm_count,
-           info.j_splits, info.force_ctas, info.fused);
+           info.j_splits, info.force_ctas, info.fused, gpus > 1 ? (info.p2p_exchange ? "p2p-push" : "nccl") : "none");
 
     double K0 = 0, W0 = 0, P[3];
     if (energy_every > 0) {

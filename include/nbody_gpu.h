@@ -96,6 +96,10 @@ typedef struct nbody_params {
                                  (default: measured faster at theta = 1, where walks are ~125 nodes long);
                                  1 = warp-cooperative walk (each node record loaded once per warp).
                                  Identical results bit for bit; only the memory access pattern differs. */
+    int32_t  exchange;        /* how the new positions reach the other GPUs each step.  0 = auto: with ngpus > 1 in one
+                                 process and full peer access, the integrator kernel stores every new position
+                                 directly into all peers' buffers over NVLink (integrate + allgather in ONE kernel, no
+                                 collective call); otherwise ncclAllGather on a communication stream.  1 = always NCCL. */
     /* --- single-process multi-GPU (C driver): ngpus devices, NCCL comms created internally --- */
     int32_t  ngpus;           /* 0 or 1 = single GPU */
     int32_t  device_ids[NBODY_MAX_GPUS]; /* CUDA ordinals; device_ids[0] is used when ngpus<=1 */
@@ -112,6 +116,7 @@ typedef struct nbody_info {
     uint64_t shard_start;     /* first target owned by this process (all local GPUs) */
     uint64_t shard_count;
     int32_t  world, rank, ngpus_local;
+    int32_t  p2p_exchange;    /* 1 if positions are exchanged by peer-to-peer stores from the integrator kernel */
     int32_t  sm_count;        /* of the first local device */
     int32_t  sm_clock_khz;    /* cudaDevAttrClockRate */
     int32_t  j_splits;        /* source-range splits chosen for the force kernel */

@@ -47,6 +47,7 @@ class NbodyParams(C.Structure):
         ("bh_fix_near_leaves", C.c_int32),
         ("sort_impl", C.c_int32),
         ("bh_walk", C.c_int32),
+        ("exchange", C.c_int32),
         ("ngpus", C.c_int32),
         ("device_ids", C.c_int32 * NBODY_MAX_GPUS),
         ("world", C.c_int32),
@@ -65,6 +66,7 @@ class NbodyInfo(C.Structure):
         ("world", C.c_int32),
         ("rank", C.c_int32),
         ("ngpus_local", C.c_int32),
+        ("p2p_exchange", C.c_int32),
         ("sm_count", C.c_int32),
         ("sm_clock_khz", C.c_int32),
         ("j_splits", C.c_int32),

@@ -213,7 +213,7 @@ cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st)
 // acc = G * sum over partial slots in slot order; then the same integrate_body_f32 as the fused
 // epilogue.  Bytes per body: read posm 16 + vel 12 + 12*nslots, write posm 16 + vel 12 + acc 12.
 __global__ void __launch_bounds__(256)
-integrate_f32_kernel(const float *__restrict__ posm_cur, float *__restrict__ posm_next,
+integrate_f32_kernel(const float *__restrict__ posm_cur, PeerDests dests,
                      float *__restrict__ vel, float *__restrict__ acc,
                      const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
                      int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
@@ -255,8 +255,11 @@ integrate_f32_kernel(const float *__restrict__ posm_cur, float *__restrict__ pos
         integrate_body_f32(P[0].z, P[1].z, P[2].z, V[0].z, V[1].z, V[2].z, A[0].z, A[1].z, A[2].z, ip);
     if (body0 + 3 < n_real)
         integrate_body_f32(P[0].w, P[1].w, P[2].w, V[0].w, V[1].w, V[2].w, A[0].w, A[1].w, A[2].w, ip);
+    for (int d = 0; d < dests.n; ++d) {   // own next buffer, or every GPU's (P2P stores over NVLink)
+        float *dst = reinterpret_cast<float *>(dests.p[d]) + goff;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4 *>(posm_next + goff + c * BLK) = P[c];
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<float4 *>(dst + c * BLK) = P[c];
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) *reinterpret_cast<float4 *>(vel + loff + c * BLK) = V[c];
 }
@@ -265,7 +268,7 @@ cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st)
 {
     const int threads = L.n_iblk_shard * 64;
     const int grid = (threads + 255) / 256;
-    integrate_f32_kernel<<<grid, 256, 0, st>>>((const float *)L.posm_cur, (float *)L.posm_next,
+    integrate_f32_kernel<<<grid, 256, 0, st>>>((const float *)L.posm_cur, L.dests,
                                                (float *)L.vel, (float *)L.acc,
                                                (const float *)L.accp, L.acc_scale, L.nslots, L.i_blk0,
                                                L.n_iblk_shard, L.acc_only, L.n_real, L.ip);

@@ -137,7 +137,7 @@ cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st)
 }
 
 __global__ void __launch_bounds__(256)
-integrate_f64_kernel(const double *__restrict__ posm_cur, double *__restrict__ posm_next,
+integrate_f64_kernel(const double *__restrict__ posm_cur, PeerDests dests,
                      double *__restrict__ vel, double *__restrict__ acc,
                      const double *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
                      int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
@@ -161,8 +161,10 @@ integrate_f64_kernel(const double *__restrict__ posm_cur, double *__restrict__ p
     const double m = posm_cur[goff + 3 * BLK];
     double vx = vel[loff], vy = vel[loff + BLK], vz = vel[loff + 2 * BLK];
     integrate_body_f64(px, py, pz, vx, vy, vz, a[0], a[1], a[2], ip);
-    posm_next[goff] = px; posm_next[goff + BLK] = py; posm_next[goff + 2 * BLK] = pz;
-    posm_next[goff + 3 * BLK] = m;
+    for (int d = 0; d < dests.n; ++d) {   // own next buffer, or every GPU's (P2P stores over NVLink)
+        double *dst = reinterpret_cast<double *>(dests.p[d]) + goff;
+        dst[0] = px; dst[BLK] = py; dst[2 * BLK] = pz; dst[3 * BLK] = m;
+    }
     vel[loff] = vx; vel[loff + BLK] = vy; vel[loff + 2 * BLK] = vz;
 }
 
@@ -170,7 +172,7 @@ cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st)
 {
     const int threads = L.n_iblk_shard * BLK;
     integrate_f64_kernel<<<(threads + 255) / 256, 256, 0, st>>>(
-        (const double *)L.posm_cur, (double *)L.posm_next, (double *)L.vel, (double *)L.acc,
+        (const double *)L.posm_cur, L.dests, (double *)L.vel, (double *)L.acc,
         (const double *)L.accp, L.acc_scale, L.nslots, L.i_blk0, L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
     return cudaGetLastError();
 }

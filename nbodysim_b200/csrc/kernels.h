@@ -47,9 +47,18 @@ struct ForceLaunch {
     IntegParams ip;
 };
 
+// Destinations of the integrator's new positions.  One entry (this GPU's next buffer) normally; with the
+// peer-to-peer exchange, the next buffer of EVERY GPU of the process: the kick-drift kernel then stores each
+// new position straight into all peers' memory over NVLink -- integrate and allgather in one kernel.
+struct PeerDests {
+    void *p[16];
+    int n;
+};
+
 struct IntegLaunch {
     const void *posm_cur;    // blocked, full array
     void *posm_next;         // blocked, full array
+    PeerDests dests;         // where the new positions are stored (n >= 1; dests.p[0] == posm_next unless peer exchange)
     void *vel, *acc;         // blocked, shard-local
     const void *accp;        // partial slots
     float acc_scale;         // G, or G*m when the uniform-mass force kernel summed unit masses

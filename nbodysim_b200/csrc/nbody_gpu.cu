@@ -34,6 +34,7 @@ struct Dev {
     int rank = 0;                 // global rank of this GPU
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     bool own_stream = true;
+    cudaEvent_t ev_pushed[2] = {nullptr, nullptr};   // P2P exchange: this GPU's integrate-and-push of step parity 0/1 is done
     cudaEvent_t ev_integrated = nullptr, ev_gathered = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
     void *posm[2] = {nullptr, nullptr};
     void *vel = nullptr, *acc = nullptr, *accp = nullptr, *aos = nullptr;
@@ -63,6 +64,8 @@ struct nbody_ctx {
     size_t n = 0, n_padded = 0;
     int world = 1;               // total GPUs
     bool f64 = false;
+    bool p2p = false;            // positions exchanged by peer stores from the integrator kernel (one process, ngpus > 1)
+    unsigned long long step_index = 0;
     bool bh = false;             // force_algo == NBODY_FORCE_BARNES_HUT
     bool uniform = false;        // every massive body has the same mass: 11-op force kernel
     float uniform_mass = 0.f;
@@ -205,9 +208,10 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     const size_t esz = ctx->esz;
     const size_t full = ctx->n_padded * 4 * esz, shard = d.shard_count * 4 * esz;
     if (d.own_stream) CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-    if (ctx->world > 1) CU(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking));
+    if (ctx->world > 1 && !ctx->p2p) CU(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&d.ev_integrated, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&d.ev_gathered, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) CU(cudaEventCreateWithFlags(&d.ev_pushed[k], cudaEventDisableTiming));
     for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&d.ev_t[k]));
     CU(cudaMalloc(&d.posm[0], full));
     CU(cudaMalloc(&d.posm[1], full));
@@ -283,13 +287,24 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
 {
     const bool refc = !ctx->f64 && ctx->p.rsqrt_mode == NBODY_RSQRT_REFCOMPAT;
     const bool guard = (ctx->p.eps == 0.0f);
+    const int par_prev = (int)((ctx->step_index + 1) & 1);     // parity of the previous step's push events
+    // remote positions of the previous step must have landed: NCCL allgather done, or every peer's push done
+    auto wait_remote = [&](Dev &d) -> cudaError_t {
+        if (!ctx->p2p) return cudaStreamWaitEvent(d.stream, d.ev_gathered, 0);
+        for (Dev &o : ctx->devs) {
+            if (&o == &d) continue;
+            cudaError_t e = cudaStreamWaitEvent(d.stream, o.ev_pushed[par_prev], 0);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
     for (Dev &d : ctx->devs) {
         CU(cudaSetDevice(d.device));
         const bool prof = profile && (&d == &ctx->devs[0]);
         if (prof) CU(cudaEventRecord(d.ev_t[0], d.stream));
         bool waited = false;
         if (ctx->bh) {
-            if (d.gathered_pending) { CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0)); waited = true; }
+            if (d.gathered_pending) { CU(wait_remote(d)); waited = true; }
             int nl = 0;
             CU(d.bh.build((const float *)d.posm[d.cur], ctx->n, d.stream, &nl));
             CU(d.bh.walk((const float *)d.posm[d.cur], ctx->n, ctx->p.theta, ctx->p.eps, refc, ctx->p.bh_fix_near_leaves != 0,
@@ -299,7 +314,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         for (const Range &r : d.plan) {
             if (ctx->bh) break;
             if (r.remote && d.gathered_pending && !waited) {
-                CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0));
+                CU(wait_remote(d));
                 waited = true;
             }
             ForceLaunch L = make_force(ctx, d, r, dt);
@@ -314,7 +329,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             ctx->launches++;
         }
         if (d.gathered_pending && !waited) { // local-only plan cannot happen with world>1, but be safe
-            CU(cudaStreamWaitEvent(d.stream, d.ev_gathered, 0));
+            CU(wait_remote(d));
         }
         if (prof) CU(cudaEventRecord(d.ev_t[1], d.stream));
         const bool fused_now = d.fused && !acc_only && !ctx->f64 && !refc;
@@ -323,6 +338,12 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             memset(&I, 0, sizeof I);
             I.posm_cur = d.posm[d.cur];
             I.posm_next = d.posm[d.cur ^ 1];
+            I.dests.n = 0;
+            if (ctx->p2p && !acc_only) {   // integrate-and-push: new positions go to every GPU's next buffer
+                for (Dev &o : ctx->devs) I.dests.p[I.dests.n++] = o.posm[o.cur ^ 1];
+            } else {
+                I.dests.p[I.dests.n++] = d.posm[d.cur ^ 1];
+            }
             I.vel = d.vel;
             I.acc = d.acc;
             I.accp = d.accp;
@@ -356,7 +377,15 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
     }
     if (acc_only) return NBODY_OK;
 
-    if (ctx->world > 1) {
+    if (ctx->p2p) {
+        // the integrator kernels already stored the new positions into every peer's next buffer
+        const int par = (int)(ctx->step_index & 1);
+        for (Dev &d : ctx->devs) {
+            CU(cudaSetDevice(d.device));
+            CU(cudaEventRecord(d.ev_pushed[par], d.stream));
+            d.gathered_pending = true;
+        }
+    } else if (ctx->world > 1) {
         // new positions of every shard -> every GPU, in place in the next buffer, on the comm stream
         for (Dev &d : ctx->devs) {
             CU(cudaSetDevice(d.device));
@@ -378,6 +407,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         }
     }
     for (Dev &d : ctx->devs) d.cur ^= 1;
+    ctx->step_index++;
     return NBODY_OK;
 }
 
@@ -408,6 +438,7 @@ void free_all(nbody_ctx *c)
         if (d.graph) cudaGraphExecDestroy(d.graph);
         if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
         if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
+        for (int k = 0; k < 2; ++k) if (d.ev_pushed[k]) cudaEventDestroy(d.ev_pushed[k]);
         for (int k = 0; k < 4; ++k) if (d.ev_t[k]) cudaEventDestroy(d.ev_t[k]);
         if (d.comm_stream) cudaStreamDestroy(d.comm_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
@@ -551,6 +582,28 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(ctx->uniform, false);
         ctx->ctas_per_sm_small = force_f32_fast_ctas_per_sm(ctx->uniform, true);
     }
+    if (!multiproc && nlocal > 1 && p->exchange != 1) {
+        // peer-to-peer exchange needs every local GPU to reach every other one (NVLink / NVSwitch)
+        bool all = true;
+        for (int a = 0; a < nlocal && all; ++a)
+            for (int b = 0; b < nlocal && all; ++b) {
+                if (a == b) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, ctx->devs[a].device, ctx->devs[b].device) != cudaSuccess || !can) all = false;
+            }
+        if (all) {
+            for (int a = 0; a < nlocal; ++a) {
+                cudaSetDevice(ctx->devs[a].device);
+                for (int b = 0; b < nlocal; ++b) {
+                    if (a == b) continue;
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->devs[b].device, 0);
+                    if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (pe != cudaSuccess) all = false;
+                }
+            }
+        }
+        ctx->p2p = all;
+    }
     for (Dev &d : ctx->devs) {
         if ((rc = plan_device(ctx, d)) != NBODY_OK) return fail(rc);
         if ((rc = alloc_device(ctx, d)) != NBODY_OK) return fail(rc);
@@ -559,7 +612,7 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         set_err(ctx, "cudaMallocHost(%zu) failed", ctx->n * sizeof(nbody_body_t));
         return fail(NBODY_ENOMEM);
     }
-    if (world > 1) {
+    if (world > 1 && !ctx->p2p) {
         if (!nccl().load()) {
             set_err(ctx, "libnccl.so.2 could not be loaded: %s", dlerror());
             return fail(NBODY_ENCCL);
@@ -783,6 +836,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->world = ctx->world;
     info->rank = d0.rank;
     info->ngpus_local = (int)ctx->devs.size();
+    info->p2p_exchange = ctx->p2p ? 1 : 0;
     info->sm_count = ctx->sm_count;
     info->sm_clock_khz = ctx->sm_clock_khz;
     info->j_splits = d0.plan.empty() ? 0 : d0.plan[0].splits;

@@ -31,12 +31,15 @@ def bits(a):
 
 
 @needs2
-def test_two_gpu_refcompat_trajectory_bitexact_vs_golden():
-    """sharding targets does not change any per-target sum: still bit-exact vs the reference"""
+@pytest.mark.parametrize("exchange", [0, 1])
+def test_two_gpu_refcompat_trajectory_bitexact_vs_golden(exchange):
+    """sharding targets does not change any per-target sum: still bit-exact vs the reference -- with the
+    peer-to-peer integrate-and-push exchange (0 = auto) and with ncclAllGather (1)"""
     g = np.load(os.path.join(G, "disc1024.npz"))
     with Simulation(g["bodies"], dt=float(g["dt"]), eps=float(g["eps"]), dims=2, rsqrt_mode=capi.RSQRT_REFCOMPAT,
-                    ngpus=2, device_ids=[0, 1]) as s:
+                    ngpus=2, device_ids=[0, 1], exchange=exchange) as s:
         assert s.info()["world"] == 2
+        assert s.info()["p2p_exchange"] == (1 if exchange == 0 else 0)
         s.step(int(g["nsteps"]))
         out = s.bodies
     for f in ("pos", "vel", "acc"):
@@ -44,10 +47,11 @@ def test_two_gpu_refcompat_trajectory_bitexact_vs_golden():
 
 
 @needs2
-def test_two_gpu_fast_matches_one_gpu_and_exact():
+@pytest.mark.parametrize("exchange", [0, 1])
+def test_two_gpu_fast_matches_one_gpu_and_exact(exchange):
     b = ic.plummer(20000, seed=3, dims=3)
     with Simulation(b, dt=1e-3, eps=0.01, dims=3, device_ids=[0]) as s1, \
-         Simulation(b, dt=1e-3, eps=0.01, dims=3, ngpus=2, device_ids=[0, 1]) as s2:
+         Simulation(b, dt=1e-3, eps=0.01, dims=3, ngpus=2, device_ids=[0, 1], exchange=exchange) as s2:
         s2.attract()
         a2 = acc3(s2.download()).astype(np.float64)
         ex = O.orc_exact_acc(b, float(np.float32(0.01)), dims=3)
@@ -84,3 +88,16 @@ def test_two_gpu_barnes_hut_bitexact_vs_golden():
         out = s.bodies
     for f in ("pos", "vel", "acc"):
         assert np.array_equal(bits(out[f]), bits(g["end_" + f])), f
+
+
+@needs2
+def test_two_gpu_exchanges_agree_bitwise_over_many_steps():
+    """P2P push and NCCL allgather move the same bytes: 60 steps, identical state"""
+    b = ic.plummer(30000, seed=11, dims=3)
+    outs = []
+    for ex in (0, 1):
+        with Simulation(b, dt=1e-3, eps=0.01, dims=3, ngpus=2, device_ids=[0, 1], exchange=ex) as s:
+            s.step(60)
+            outs.append(s.bodies.copy())
+    for f in ("pos", "pos_z", "vel", "vel_z", "acc", "acc_z"):
+        assert np.array_equal(bits(outs[0][f]), bits(outs[1][f])), f
