@@ -14,7 +14,7 @@ using namespace nb;
 struct Result { float ms; double maxrel; };
 
 template <int I, int THREADS, int MINB, int UNROLL, int STAGE_BLKS, int FORM>
-Result run(const char *name, const float *posm, const float *src5, float *accp, int nblk, int splits, float eps2,
+Result run(const char *name, const float *posm, float *accp, int nblk, int splits, float eps2,
            int reps, const std::vector<float> &ref, std::vector<float> &out, int sms)
 {
     auto kern = force_f32_fast_kernel<I, THREADS, MINB, UNROLL, STAGE_BLKS, FORM, false, false>;
@@ -86,9 +86,8 @@ int main(int argc, char **argv)
         size_t o = blk_index(i, 0);
         h[o] = x; h[o + BLK] = y; h[o + 2 * BLK] = z; h[o + 3 * BLK] = 1.0f;  // equal masses (so the uniform-mass form can be checked too)
     }
-    float *posm, *src5, *accp;
+    float *posm, *accp;
     CK(cudaMalloc(&posm, h.size() * 4));
-    CK(cudaMalloc(&src5, (size_t)nblk * 5 * BLK * 4));
     CK(cudaMalloc(&accp, h.size() * 4 * 64));
     CK(cudaMemcpy(posm, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     const float eps2 = 1e-4f;
@@ -96,15 +95,15 @@ int main(int argc, char **argv)
     const int sms = prop.multiProcessorCount;
     std::vector<float> ref, out, none;
     //            I  THR MINB UNR STG FORM (0 = general masses, 1 = uniform mass)
-    run<8, 256, 1, 1, 2, 0>("plain   I8 t256 b1 u1 s2 (product)", posm, src5, accp, nblk, 0, eps2, reps, none, ref, sms);
-    run<8, 256, 1, 1, 2, 1>("uniform I8 t256 b1 u1 s2 (product)", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<4, 256, 2, 2, 2, 0>("plain   I4 t256 b2 u2 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<4, 256, 2, 1, 2, 1>("uniform I4 t256 b2 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<8, 128, 2, 1, 2, 0>("plain   I8 t128 b2 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<8, 128, 2, 1, 2, 1>("uniform I8 t128 b2 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<6, 128, 3, 1, 2, 0>("plain   I6 t128 b3 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<6, 128, 3, 1, 2, 1>("uniform I6 t128 b3 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<12, 256, 1, 1, 2, 0>("plain   I12 t256 b1 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<12, 256, 1, 1, 2, 1>("uniform I12 t256 b1 u1 s2", posm, src5, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<8, 256, 1, 1, 2, 0>("plain   I8 t256 b1 u1 s2 (product)", posm, accp, nblk, 0, eps2, reps, none, ref, sms);
+    run<8, 256, 1, 1, 2, 1>("uniform I8 t256 b1 u1 s2 (product)", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<4, 256, 2, 2, 2, 0>("plain   I4 t256 b2 u2 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<4, 256, 2, 1, 2, 1>("uniform I4 t256 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<8, 128, 2, 1, 2, 0>("plain   I8 t128 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<8, 128, 2, 1, 2, 1>("uniform I8 t128 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<6, 128, 3, 1, 2, 0>("plain   I6 t128 b3 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<6, 128, 3, 1, 2, 1>("uniform I6 t128 b3 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<12, 256, 1, 1, 2, 0>("plain   I12 t256 b1 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    run<12, 256, 1, 1, 2, 1>("uniform I12 t256 b1 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
     return 0;
 }
