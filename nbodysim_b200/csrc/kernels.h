@@ -24,7 +24,7 @@ struct IntegParams {
 // [j_blk0, j_blk0 + j_nblk) cut into `splits` chunks; CTA (tile, s) writes its partial sum into
 // partial slot slot0 + s.  Slots are summed in index order by the integrator (deterministic).
 struct ForceLaunch {
-    int small_tile;          // fast kernel: 1 = 256-target tiles (small shards), 0 = 2048-target tiles
+    int small_tile;          // fast kernel: 1 = 512-target tiles (small shards), 0 = 2048-target tiles
     int dims;                // fast kernel: 2 = planar data (z == 0 everywhere): z operations dropped
     int uniform_mass;        // fast kernel: 1 = every massive source has the same mass (11-op form)
     float acc_scale;         // fused epilogue: G (plain) or G*m (uniform)
@@ -74,10 +74,10 @@ struct IntegLaunch {
 // 8 targets per thread, 256 threads, one CTA of 8 warps per SM, ~228 registers per thread)
 constexpr int FAST_THREADS = 256, FAST_I = 8, FAST_MINB = 1, FAST_UNROLL = 1, FAST_STAGE_BLKS = 2;
 constexpr int FAST_TILE_BLKS = FAST_I / (BLK / FAST_THREADS);                // 8 blocks = 2048 targets / CTA
-// small shards (the reference's own N = 25,000 included): 256-target tiles so that the grid still covers
-// the 148 SMs; 2 targets per thread, 128 threads, several CTAs per SM, one source block per stage
-constexpr int SMALL_THREADS = 128, SMALL_I = 2, SMALL_MINB = 6, SMALL_UNROLL = 2, SMALL_STAGE_BLKS = 1;
-constexpr int SMALL_TILE_BLKS = SMALL_I / (BLK / SMALL_THREADS);             // 1 block = 256 targets / CTA
+// small shards (the reference's own N = 25,000 included): 512-target tiles so that the grid still covers
+// the 148 SMs; 4 targets per thread, 128 threads, 4 CTAs per SM, one source block per stage (kbench sweep)
+constexpr int SMALL_THREADS = 128, SMALL_I = 4, SMALL_MINB = 4, SMALL_UNROLL = 2, SMALL_STAGE_BLKS = 1;
+constexpr int SMALL_TILE_BLKS = SMALL_I / (BLK / SMALL_THREADS);             // 2 blocks = 512 targets / CTA
 constexpr int REF_THREADS = 128, REF_TILE_BODIES = 128;                      // refcompat: 1 / thread
 constexpr int F64_THREADS = 128, F64_I = 2, F64_TILE_BLKS = 1;               // 256 targets / CTA
 constexpr int TARGET_GRANULE = FAST_TILE_BLKS * BLK;                         // shard granularity

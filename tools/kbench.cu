@@ -13,7 +13,7 @@ using namespace nb;
 
 struct Result { float ms; double maxrel; };
 
-template <int I, int THREADS, int MINB, int UNROLL, int STAGE_BLKS, int FORM>
+template <int I, int THREADS, int MINB, int UNROLL, int STAGE_BLKS, int FORM, int MINCHUNK = 8>
 Result run(const char *name, const float *posm, float *accp, int nblk, int splits, float eps2,
            int reps, const std::vector<float> &ref, std::vector<float> &out, int sms)
 {
@@ -30,7 +30,7 @@ Result run(const char *name, const float *posm, float *accp, int nblk, int split
     a.i_blk0 = 0; a.i_blk_local0 = 0; a.n_iblk_shard = nblk; a.j_blk0 = 0; a.j_nblk = nblk;
     if (splits <= 0) { // pick splits for ~whole waves
         int tiles = nblk / TILE_BLKS, slots = sms * occ; double best = -1; splits = 1;
-        for (int s = 1; s <= 64 && nblk / s >= 8; ++s) {
+        for (int s = 1; s <= 64 && nblk / s >= MINCHUNK; ++s) {
             long long units = (long long)tiles * s, waves = (units + slots - 1) / slots;
             double eff = (double)units / (waves * slots); if (waves < 4) eff *= 0.97;
             if (eff > best + 0.01) { best = eff; splits = s; }
@@ -73,7 +73,7 @@ int main(int argc, char **argv)
 {
     int n = argc > 1 ? atoi(argv[1]) : 262144;
     int reps = argc > 2 ? atoi(argv[2]) : 5;
-    n = (n / 30720) * 30720;   // whole tiles for every I in {2,4,6,8,10,12}
+    n = (n / 6144) * 6144;   // whole tiles for every I in {1,2,4,6,8}
     const int nblk = n / BLK;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     printf("device %s, %d SMs, N=%d, reps=%d\n", prop.name, prop.multiProcessorCount, n, reps);
@@ -94,16 +94,26 @@ int main(int argc, char **argv)
     CK(cudaDeviceSynchronize());
     const int sms = prop.multiProcessorCount;
     std::vector<float> ref, out, none;
-    //            I  THR MINB UNR STG FORM (0 = general masses, 1 = uniform mass)
-    run<8, 256, 1, 1, 2, 0>("plain   I8 t256 b1 u1 s2 (product)", posm, accp, nblk, 0, eps2, reps, none, ref, sms);
-    run<8, 256, 1, 1, 2, 1>("uniform I8 t256 b1 u1 s2 (product)", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<4, 256, 2, 2, 2, 0>("plain   I4 t256 b2 u2 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<4, 256, 2, 1, 2, 1>("uniform I4 t256 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<8, 128, 2, 1, 2, 0>("plain   I8 t128 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<8, 128, 2, 1, 2, 1>("uniform I8 t128 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<6, 128, 3, 1, 2, 0>("plain   I6 t128 b3 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<6, 128, 3, 1, 2, 1>("uniform I6 t128 b3 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<12, 256, 1, 1, 2, 0>("plain   I12 t256 b1 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
-    run<12, 256, 1, 1, 2, 1>("uniform I12 t256 b1 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    //            I  THR MINB UNR STG FORM (0 = general masses, 1 = uniform mass) [MINCHUNK]
+    if (n >= 60000) {
+        run<8, 256, 1, 1, 2, 0>("plain   I8 t256 b1 u1 s2 (product)", posm, accp, nblk, 0, eps2, reps, none, ref, sms);
+        run<8, 256, 1, 1, 2, 1>("uniform I8 t256 b1 u1 s2 (product)", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<4, 256, 2, 2, 2, 0>("plain   I4 t256 b2 u2 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<4, 256, 2, 1, 2, 1>("uniform I4 t256 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<8, 128, 2, 1, 2, 1>("uniform I8 t128 b2 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<6, 128, 3, 1, 2, 1>("uniform I6 t128 b3 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    } else { // small shards: small-tile geometries, source chunks down to one block
+        run<2, 128, 6, 2, 1, 1, 1>("uniform I2 t128 b6 u2 s1 (product small)", posm, accp, nblk, 0, eps2, reps, none, ref, sms);
+        run<2, 128, 6, 1, 1, 1, 1>("uniform I2 t128 b6 u1 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<2, 128, 8, 2, 1, 1, 1>("uniform I2 t128 b8 u2 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<4, 128, 4, 1, 1, 1, 1>("uniform I4 t128 b4 u1 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<4, 128, 4, 2, 1, 1, 1>("uniform I4 t128 b4 u2 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<4, 128, 3, 1, 2, 1, 2>("uniform I4 t128 b3 u1 s2", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<4, 256, 2, 1, 1, 1, 1>("uniform I4 t256 b2 u1 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<2, 256, 4, 2, 1, 1, 1>("uniform I2 t256 b4 u2 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<1, 256, 4, 2, 1, 1, 1>("uniform I1 t256 b4 u2 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<6, 128, 3, 1, 1, 1, 1>("uniform I6 t128 b3 u1 s1", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+        run<8, 256, 1, 1, 2, 1, 2>("uniform I8 t256 b1 u1 s2 (large tile)", posm, accp, nblk, 0, eps2, reps, ref, out, sms);
+    }
     return 0;
 }
