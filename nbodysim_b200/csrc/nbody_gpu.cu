@@ -127,7 +127,7 @@ IntegParams make_ip(const nbody_ctx *c, float dt)
 // Choose the number of source-range splits so that the CTAs of one launch fill whole waves of
 // the GPU (slots = SMs x resident CTAs per SM): wave-quantisation efficiency
 //   eff(S) = units / (ceil(units/slots) * slots),  units = target_tiles * S.
-// Prefer the smallest S within 1 % of the best; each chunk keeps >= min_chunk_blks source blocks.
+// Prefer the smallest S within 1 % (relative) of the best; each chunk keeps >= min_chunk_blks source blocks.
 int choose_splits(int tiles, int j_nblk, int slots, int min_chunk_blks, int max_splits)
 {
     if (tiles <= 0 || slots <= 0) return 1;
@@ -140,7 +140,7 @@ int choose_splits(int tiles, int j_nblk, int slots, int min_chunk_blks, int max_
         double eff = (double)units / (double)(waves * slots);
         // a launch of very few waves also suffers the imbalance of a dynamic tail: favour >= 4 waves
         if (waves < 4) eff *= 0.97;
-        if (eff > best + 0.01) { best = eff; best_s = s; }
+        if (eff > best * 1.01) { best = eff; best_s = s; }   // prefer the smallest S within 1 % of the best
     }
     return best_s;
 }

@@ -33,7 +33,7 @@ Result run(const char *name, const float *posm, float *accp, int nblk, int split
         for (int s = 1; s <= 64 && nblk / s >= MINCHUNK; ++s) {
             long long units = (long long)tiles * s, waves = (units + slots - 1) / slots;
             double eff = (double)units / (waves * slots); if (waves < 4) eff *= 0.97;
-            if (eff > best + 0.01) { best = eff; splits = s; }
+            if (eff > best * 1.01) { best = eff; splits = s; }
         }
     }
     a.splits = splits; a.slot0 = 0; a.eps2 = eps2; a.acc_scale = 1.0f; a.n_real = (long long)nblk * BLK;
