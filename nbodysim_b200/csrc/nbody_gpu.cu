@@ -684,8 +684,10 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
 {
     if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
     // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
-    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->bh && !ctx->p.collide && !ctx->profile_next && nsteps >= 8;
-    const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && ctx->n_padded <= 32768);
+    // (the Barnes-Hut build is fully asynchronous -- sort, scan and the cooperative COM pass included -- so it
+    //  captures too; the collision pass reads counters back and does not)
+    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->p.collide && !ctx->profile_next && nsteps >= 8;
+    const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && (ctx->n_padded <= 32768 || (ctx->bh && ctx->n_padded <= 262144)));
     if (graph_ok && want) {
         int rc = step_with_graph(ctx, dt, nsteps);
         if (rc != NBODY_OK) return rc;

@@ -115,6 +115,19 @@ def test_bh_both_walks_bitexact(walk):
     assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, 0.8, 1.0)))
 
 
+def test_bh_graph_replay_bitexact_vs_golden():
+    """the whole Barnes-Hut step (build incl. sort, scan, cooperative COM pass; walk; integrator) replayed from
+    a CUDA graph: 10 reference steps, still bit-exact"""
+    g = np.load(os.path.join(G, "bh2000.npz"))
+    with bh_sim(g["bodies"], dt=float(g["dt"]), theta=1.0, eps=1.0, use_graph=1,
+                integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
+        s.step(int(g["nsteps"]))
+        out = s.bodies
+        assert s.info()["graph"] == 1
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(out[f]), bits(g["end_" + f])), f
+
+
 def test_bh_coincident_bodies_merge():
     b = ic.spinning_disc(64, seed=8)
     b[10]["pos"] = b[3]["pos"]
