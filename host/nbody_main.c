@@ -2,9 +2,10 @@
  *
  * The reference has no command line at all: `int main()` takes no argv (main.cpp:637) and every
  * parameter is a compile-time literal.  This driver's flags are new
- * surface whose DEFAULTS are those literals (N=25000 Simulation.hpp:61, eps=1 / theta=1 :59,
- * dt=0.01 main.cpp:39, clamp/boundary constants :120-124), so a no-argument run uses the
- * reference's parameters on a synthetic disc.  It replaces simulation_thread's loop
+ * surface whose DEFAULTS are those literals, so a NO-ARGUMENT RUN IS THE REFERENCE'S SIMULATION,
+ * headless (other scenes, --ic plummer etc., default to the fast all-pairs path): uniform_disc(25000) (Simulation.hpp:61,347-603), Barnes-Hut theta=1, eps=1 (:59),
+ * dt=0.01 (main.cpp:39), clamp + soft boundary (:120-155), collide() (:216-346), the reference's
+ * own rsqrt -- i.e. Simulation::step() bit for bit.  It replaces simulation_thread's loop
  * (main.cpp:612-635): step, then hand the bodies to a consumer (here: diagnostics / snapshot).
  */
 #define _POSIX_C_SOURCE 200809L
@@ -40,9 +41,12 @@ int main(int argc, char **argv)
     int steps = 100, dims = 2, gpus = 1, energy_every = 0, splits = 0;
     float dt = 0.01f, eps = 1.0f;
     unsigned long long seed = 0;
-    const char *ic = "disc", *in_path = NULL, *out_path = NULL;
+    const char *ic = "reference", *in_path = NULL, *out_path = NULL;
     nbody_params p;
     nbody_params_default(&p);
+    /* explicit choices (-1 = not given): with the default scene (--ic reference) the unset ones fall back to
+     * the reference's shipped configuration, with any other scene to the library defaults */
+    int o_algo = -1, o_rsqrt = -1, o_clamp = -1, o_boundary = -1, o_collide = -1;
 
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
@@ -58,12 +62,12 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--gpus")) { NEED(); gpus = atoi(v); }
         else if (!strcmp(a, "--splits")) { NEED(); splits = atoi(v); }
         else if (!strcmp(a, "--precision")) { NEED(); p.precision = !strcmp(v, "f64") ? NBODY_PRECISION_F64 : NBODY_PRECISION_F32; }
-        else if (!strcmp(a, "--rsqrt")) { NEED(); p.rsqrt_mode = !strcmp(v, "refcompat") ? NBODY_RSQRT_REFCOMPAT : NBODY_RSQRT_FAST; }
-        else if (!strcmp(a, "--clamp")) { NEED(); if (!strcmp(v, "on")) p.integ_flags |= NBODY_INTEG_CLAMP; else p.integ_flags &= ~NBODY_INTEG_CLAMP; }
-        else if (!strcmp(a, "--boundary")) { NEED(); if (!strcmp(v, "on")) p.integ_flags |= NBODY_INTEG_BOUNDARY; else p.integ_flags &= ~NBODY_INTEG_BOUNDARY; }
-        else if (!strcmp(a, "--algo")) { NEED(); p.force_algo = !strcmp(v, "bh") ? NBODY_FORCE_BARNES_HUT : NBODY_FORCE_ALLPAIRS; }
+        else if (!strcmp(a, "--rsqrt")) { NEED(); o_rsqrt = !strcmp(v, "refcompat"); }
+        else if (!strcmp(a, "--clamp")) { NEED(); o_clamp = !strcmp(v, "on"); }
+        else if (!strcmp(a, "--boundary")) { NEED(); o_boundary = !strcmp(v, "on"); }
+        else if (!strcmp(a, "--algo")) { NEED(); o_algo = !strcmp(v, "bh"); }
         else if (!strcmp(a, "--theta")) { NEED(); p.theta = (float)atof(v); }
-        else if (!strcmp(a, "--collide")) { NEED(); p.collide = !strcmp(v, "on") ? 1 : 0; }
+        else if (!strcmp(a, "--collide")) { NEED(); o_collide = !strcmp(v, "on"); }
         else if (!strcmp(a, "--exchange")) { NEED(); p.exchange = !strcmp(v, "nccl") ? 1 : 0; }
         else if (!strcmp(a, "--energy-every")) { NEED(); energy_every = atoi(v); }
         else if (!strcmp(a, "--in")) { NEED(); in_path = v; }
@@ -91,6 +95,17 @@ int main(int argc, char **argv)
     else { usage(argv[0]); return 2; }
     if (rc != 0) { fprintf(stderr, "initial conditions failed (%d)\n", rc); return 1; }
 
+    {
+        /* the reference's configuration (BH theta=1, its own rsqrt, clamp + boundary, collide) for its own scene */
+        const int refcfg = !in_path && !strcmp(ic, "reference") && dims == 2 && gpus == 1 && p.precision == NBODY_PRECISION_F32;
+        const int algo = o_algo >= 0 ? o_algo : refcfg, rsq = o_rsqrt >= 0 ? o_rsqrt : refcfg;
+        const int clamp = o_clamp >= 0 ? o_clamp : refcfg, bound = o_boundary >= 0 ? o_boundary : refcfg;
+        const int coll = o_collide >= 0 ? o_collide : refcfg;
+        p.force_algo = algo ? NBODY_FORCE_BARNES_HUT : NBODY_FORCE_ALLPAIRS;
+        p.rsqrt_mode = rsq ? NBODY_RSQRT_REFCOMPAT : NBODY_RSQRT_FAST;
+        p.integ_flags = (clamp ? NBODY_INTEG_CLAMP : 0u) | (bound ? NBODY_INTEG_BOUNDARY : 0u);
+        p.collide = coll;
+    }
     p.dims = dims;
     p.eps = eps;
     p.j_splits = splits;

@@ -66,7 +66,19 @@ def test_c_driver_reference_configuration_equals_oracle(tmp_path):
         assert np.array_equal(bits(got[f]), bits(g["step_end_" + f])), f
 
 
-def test_c_driver_reference_scene_runs():
-    out = run(["--ic", "reference", "--n", "25000", "--steps", "20", "--algo", "bh", "--rsqrt", "refcompat", "--clamp", "on",
-               "--boundary", "on", "--collide", "on"])
-    assert "20 steps in" in out
+def test_c_driver_no_argument_run_is_the_reference_simulation(tmp_path):
+    """no flags = Simulation(): uniform_disc(25000), BH theta=1, eps=1, dt=0.01, clamp + boundary + collide,
+    the reference's rsqrt; checked against the oracle pipeline on the same scene (first 3 steps)"""
+    dst = str(tmp_path / "out.nbody")
+    out = run(["--steps", "3", "--out", dst])
+    assert "n=25000" in out and "3 steps in" in out
+    got = read_snapshot(dst, 25000)
+    want = ic.reference_disc(25000)
+    for _ in range(3):
+        want["acc"] = O.orc_bh_acc(want, 1.0, 1.0)
+        O.oracle().orc_iterate_after_attract(want.ctypes.data, 25000, 0.01, 3, 2)
+        want, _, _ = O.orc_collide(want)
+    assert np.array_equal(bits(got["acc"]), bits(want["acc"]))
+    inside = (want["pos"].astype(np.float64) ** 2).sum(1) < (0.79e5) ** 2     # beyond: expf differs by an ulp
+    assert np.array_equal(bits(got["pos"][inside]), bits(want["pos"][inside]))
+    np.testing.assert_allclose(got["pos"], want["pos"], rtol=2e-6, atol=1e-3)
