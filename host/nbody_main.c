@@ -147,8 +147,12 @@ int main(int argc, char **argv)
     nbody_gpu_sync(ctx);
     const double t1 = now_s();
     nbody_gpu_get_info(ctx, &info);
-    printf("%d steps in %.3f s  (%.3f ms/step, %.2f G pair-interactions/s incl. diagnostics)\n", steps,
-           t1 - t0, 1e3 * (t1 - t0) / (steps > 0 ? steps : 1), 1e-9 * (double)n * (double)n * steps / (t1 - t0));
+    if (p.force_algo == NBODY_FORCE_BARNES_HUT)
+        printf("%d steps in %.3f s  (%.3f ms/step incl. diagnostics; Barnes-Hut theta=%g%s)\n", steps, t1 - t0,
+               1e3 * (t1 - t0) / (steps > 0 ? steps : 1), (double)p.theta, p.collide ? " + collision pass" : "");
+    else
+        printf("%d steps in %.3f s  (%.3f ms/step, %.2f G pair-interactions/s incl. diagnostics)\n", steps,
+               t1 - t0, 1e3 * (t1 - t0) / (steps > 0 ? steps : 1), 1e-9 * (double)n * (double)n * steps / (t1 - t0));
 
     rc = nbody_gpu_download(ctx, b, n, NBODY_FIELD_ALL);
     if (rc != NBODY_OK) { fprintf(stderr, "download: %s\n", nbody_gpu_last_error(ctx)); return 1; }
