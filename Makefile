@@ -30,7 +30,10 @@ oracle:
 	$(MAKE) -C oracle all
 
 # tuning / microbenchmark harnesses (not part of the product path)
-tools: build/kbench build/ubench build/sort_check
+tools: build/kbench build/ubench build/sort_check build/kbench_sym
+build/kbench_sym: tools/kbench_sym.cu $(HDR)
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -o $@ $<
 build/sort_check: tools/sort_check.cu $(CSRC)/radix_sort.cuh
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -o $@ $<
