@@ -43,7 +43,8 @@ typedef struct nbody_ctx nbody_ctx;
                                    reference's direct sum bit for bit */
 /* nbody_params.force_algo */
 #define NBODY_FORCE_ALLPAIRS   0 /* direct sum == Quadtree::acc leaf loop, Quadtree.hpp:133-144 */
-#define NBODY_FORCE_BARNES_HUT 1 /* quadtree walk == Quadtree::build + acc (2-D only) */
+#define NBODY_FORCE_BARNES_HUT 1 /* tree walk == Quadtree::build + acc: the reference's quadtree for dims = 2,
+                                    the same construction as an octree for dims = 3 */
 /* nbody_params.integ_flags: extras of Simulation::iterate beyond Body::update */
 #define NBODY_INTEG_CLAMP    1u /* |v| <= max_velocity            Simulation.hpp:133-137 */
 #define NBODY_INTEG_BOUNDARY 2u /* exponential soft boundary + damping, Simulation.hpp:140-155 */
@@ -189,11 +190,11 @@ int nbody_gpu_collide(nbody_ctx *ctx);
 int nbody_gpu_collide_stats(nbody_ctx *ctx, uint32_t *candidate_pairs, uint32_t *resolved_pairs);
 
 /* Barnes-Hut diagnostics / parity: the node array of the last tree built, in walk (depth-first,
- * quadrant) order, WITHOUT the reference's empty leaves.  f6 = 6 floats per node: position (body or
- * centre of mass) x,y ; mass ; quad centre x,y ; quad size  (Node::data, Node.hpp:35-40).
+ * quadrant) order, WITHOUT the reference's empty leaves.  f8 = 8 floats per node: position (body or
+ * centre of mass) x,y,z ; mass ; cell centre x,y,z ; cell size  (Node::data, Node.hpp:35-40; z = 0 in 2-D).
  * u2 = 2 words per node: next (skip pointer, 0 = end of walk; Node::next) ; depth | is_leaf << 8.
  * Writes min(cap, count) nodes; *count receives the total. */
-int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f6, uint32_t *u2, size_t cap, size_t *count);
+int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f8, uint32_t *u2, size_t cap, size_t *count);
 
 /* rank 0 creates the NCCL id that every rank passes in nbody_params.nccl_id. */
 int nbody_gpu_nccl_unique_id(uint8_t id[NBODY_NCCL_ID_BYTES]);

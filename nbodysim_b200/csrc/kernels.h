@@ -112,20 +112,21 @@ struct BhWorkspace {
     unsigned node_cap = 0, n_nodes = 0;
     void *root = nullptr, *box = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
-    void *node_data = nullptr, *node_quad = nullptr, *node_next = nullptr, *node_meta = nullptr;
+    void *node_data = nullptr, *node_quad = nullptr, *node_z = nullptr, *node_next = nullptr, *node_meta = nullptr;
+    int dims = 2;                // 2 = the reference's quadtree, 3 = octree
     void *temp = nullptr;
     size_t temp_bytes = 0;
     int coop_blocks = 148;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
     bool own_sort = false;       // hand-written radix sort (radix_sort.cuh) instead of cub::DeviceRadixSort
-    cudaError_t alloc(size_t n);
+    cudaError_t alloc(size_t n, int dims);
     cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);
     void release();
     cudaError_t build(const float *posm, size_t n, cudaStream_t st, int *launches);
     cudaError_t walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
                      size_t shard_start, size_t shard_count, float *accp, cudaStream_t st);
-    cudaError_t download_nodes(float *f6, unsigned *u2, size_t cap, cudaStream_t st);
+    cudaError_t download_nodes(float *f8, unsigned *u2, size_t cap, cudaStream_t st);
 };
 
 // collision pass (collide.cu)

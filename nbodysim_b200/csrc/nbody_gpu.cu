@@ -223,7 +223,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
         d.col.own_sort = (ctx->p.sort_impl == 1);
     }
     if (ctx->bh) {
-        CU(d.bh.alloc(ctx->n));
+        CU(d.bh.alloc(ctx->n, ctx->p.dims));
         d.bh.warp_walk = (ctx->p.bh_walk == 1);
         d.bh.own_sort = (ctx->p.sort_impl == 1);
     }
@@ -502,8 +502,8 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         set_err(nullptr, "nbody_gpu_init: the collision pass is the reference's 2-D fp32 collide() on one GPU");
         return NBODY_EINVAL;
     }
-    if (p->force_algo == NBODY_FORCE_BARNES_HUT && (p->dims != 2 || p->precision != NBODY_PRECISION_F32)) {
-        set_err(nullptr, "nbody_gpu_init: the Barnes-Hut path is the reference's 2-D fp32 quadtree (dims=2, f32)");
+    if (p->force_algo == NBODY_FORCE_BARNES_HUT && p->precision != NBODY_PRECISION_F32) {
+        set_err(nullptr, "nbody_gpu_init: the Barnes-Hut path is fp32 (the reference's quadtree in 2-D, its octree generalisation in 3-D)");
         return NBODY_EINVAL;
     }
     const int nlocal = std::max(1, p->ngpus);
@@ -895,7 +895,7 @@ int nbody_gpu_collide_stats(nbody_ctx *ctx, uint32_t *candidate_pairs, uint32_t 
     return NBODY_OK;
 }
 
-int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f6, uint32_t *u2, size_t cap, size_t *count)
+int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f8, uint32_t *u2, size_t cap, size_t *count)
 {
     if (!ctx || !count) return NBODY_EINVAL;
     if (!ctx->bh) return NBODY_ESTATE;
@@ -904,8 +904,8 @@ int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f6, uint32_t *u2, size_t cap, size
     unsigned m = 0;
     CU(d.bh.node_count(ctx->n, d.stream, &m));
     *count = m;
-    if (cap == 0 || !f6 || !u2) return NBODY_OK;
-    CU(d.bh.download_nodes(f6, u2, cap, d.stream));
+    if (cap == 0 || !f8 || !u2) return NBODY_OK;
+    CU(d.bh.download_nodes(f8, u2, cap, d.stream));
     return NBODY_OK;
 }
 

@@ -118,13 +118,13 @@ class Simulation:
 
     def bh_nodes(self):
         """Barnes-Hut node array of the last tree built, in walk order:
-        (f6[n,6] = x, y, mass, cx, cy, size ; next[n] ; depth[n] ; is_leaf[n])."""
+        (f8[n,8] = x, y, z, mass, cx, cy, cz, size ; next[n] ; depth[n] ; is_leaf[n])."""
         cnt = C.c_size_t()
         self._check(self._lib.nbody_gpu_bh_nodes(self._ctx, None, None, 0, C.byref(cnt)))
-        f6 = np.zeros((cnt.value, 6), dtype=np.float32)
+        f8 = np.zeros((cnt.value, 8), dtype=np.float32)
         u2 = np.zeros((cnt.value, 2), dtype=np.uint32)
-        self._check(self._lib.nbody_gpu_bh_nodes(self._ctx, f6.ctypes.data, u2.ctypes.data, cnt.value, C.byref(cnt)))
-        return f6, u2[:, 0].copy(), (u2[:, 1] & 255).astype(np.uint32), (u2[:, 1] >> 8).astype(bool)
+        self._check(self._lib.nbody_gpu_bh_nodes(self._ctx, f8.ctypes.data, u2.ctypes.data, cnt.value, C.byref(cnt)))
+        return f8, u2[:, 0].copy(), (u2[:, 1] & 255).astype(np.uint32), (u2[:, 1] >> 8).astype(bool)
 
     def profile_next_step(self, enable=True):
         self._check(self._lib.nbody_gpu_profile_next_step(self._ctx, 1 if enable else 0))

@@ -525,3 +525,117 @@ size_t orc_collide(orc_body_t *B, size_t n, size_t *resolved)
     free(ent); free(pairs); free(sw); free(active);
     return np;
 }
+
+/* ============================================================================ octree (3-D generalisation) */
+typedef struct { orc_node3_t *v; size_t n, cap; } node3vec_t;
+static void n3_push(node3vec_t *a, orc_node3_t x)
+{
+    if (a->n == a->cap) {
+        a->cap = a->cap ? a->cap * 2 : 1024;
+        a->v = (orc_node3_t *)realloc(a->v, a->cap * sizeof *a->v);
+    }
+    a->v[a->n++] = x;
+}
+static orc_node3_t make_node3(uint64_t next, float cx, float cy, float cz, float size, uint64_t depth)
+{
+    orc_node3_t nd;
+    nd.px = nd.py = nd.pz = 0.0f; nd.mass = 0.0f;
+    nd.cx = cx; nd.cy = cy; nd.cz = cz; nd.size = size;
+    nd.children = 0; nd.next = next; nd.depth = depth;
+    return nd;
+}
+static size_t find_octant(const orc_node3_t *nd, float x, float y, float z)
+{
+    return ((size_t)(z > nd->cz) << 2) | ((size_t)(y > nd->cy) << 1) | (size_t)(x > nd->cx);
+}
+static void bh3_insert(node3vec_t *nodes, idxvec_t *parents, float x, float y, float z, float mass)
+{
+    size_t node = 0;
+    while (nodes->v[node].children != 0) node = nodes->v[node].children + find_octant(&nodes->v[node], x, y, z);
+    if (nodes->v[node].mass == 0.0f) {
+        nodes->v[node].px = x; nodes->v[node].py = y; nodes->v[node].pz = z; nodes->v[node].mass = mass;
+        return;
+    }
+    const float ex = nodes->v[node].px, ey = nodes->v[node].py, ez = nodes->v[node].pz, em = nodes->v[node].mass;
+    if (x == ex && y == ey && z == ez) { nodes->v[node].mass += mass; return; }
+    for (;;) {
+        const size_t children = nodes->n;
+        nodes->v[node].children = children;
+        iv_push(parents, node);
+        for (size_t i = 0; i < 8; ++i) {
+            const orc_node3_t parent = nodes->v[node];
+            const float ns = parent.size * 0.5f;
+            const float cx = parent.cx + ((i & 1) ? 0.5f : -0.5f) * ns;
+            const float cy = parent.cy + ((i & 2) ? 0.5f : -0.5f) * ns;
+            const float cz = parent.cz + ((i & 4) ? 0.5f : -0.5f) * ns;
+            n3_push(nodes, make_node3((i < 7) ? children + i + 1 : parent.next, cx, cy, cz, ns, parent.depth + 1));
+        }
+        const size_t q1 = find_octant(&nodes->v[node], ex, ey, ez), q2 = find_octant(&nodes->v[node], x, y, z);
+        if (q1 == q2) { node = children + q1; continue; }
+        orc_node3_t *a = &nodes->v[children + q1], *c = &nodes->v[children + q2];
+        a->px = ex; a->py = ey; a->pz = ez; a->mass = em;
+        c->px = x; c->py = y; c->pz = z; c->mass = mass;
+        return;
+    }
+}
+
+size_t orc_bh3_build(const orc_body_t *b, size_t n, orc_node3_t **nodes_out)
+{
+    node3vec_t nodes = {0, 0, 0};
+    idxvec_t parents = {0, 0, 0};
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (size_t i = 0; i < n; ++i) {
+        const float p[3] = {b[i].px, b[i].py, b[i].pz};
+        for (int a = 0; a < 3; ++a) { mn[a] = p[a] < mn[a] ? p[a] : mn[a]; mx[a] = mx[a] < p[a] ? p[a] : mx[a]; }
+    }
+    float size = mx[0] - mn[0];
+    for (int a = 1; a < 3; ++a) { const float e = mx[a] - mn[a]; size = size < e ? e : size; }
+    n3_push(&nodes, make_node3(0, (mn[0] + mx[0]) * 0.5f, (mn[1] + mx[1]) * 0.5f, (mn[2] + mx[2]) * 0.5f, size, 0));
+    for (size_t i = 0; i < n; ++i) bh3_insert(&nodes, &parents, b[i].px, b[i].py, b[i].pz, b[i].mass);
+    for (size_t k = parents.n; k-- > 0;) {
+        const size_t node = parents.v[k], child = nodes.v[node].children;
+        float px = 0.0f, py = 0.0f, pz = 0.0f, m = 0.0f;
+        for (size_t i = 0; i < 8; ++i) {
+            const orc_node3_t *c = &nodes.v[child + i];
+            px += c->px * c->mass; py += c->py * c->mass; pz += c->pz * c->mass;
+            m += c->mass;
+        }
+        if (m > 0) { const float inv = 1.0f / m; px *= inv; py *= inv; pz *= inv; }
+        nodes.v[node].px = px; nodes.v[node].py = py; nodes.v[node].pz = pz; nodes.v[node].mass = m;
+    }
+    free(parents.v);
+    *nodes_out = nodes.v;
+    return nodes.n;
+}
+
+void orc_bh3_acc(const orc_node3_t *nodes, float theta, float eps, const orc_body_t *b, size_t i0, size_t i1,
+                 int fix_near_leaves, float *acc_out)
+{
+    const float t_sq = theta * theta, e_sq = eps * eps;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long ii = (long long)i0; ii < (long long)i1; ++ii) {
+        const float px = b[ii].px, py = b[ii].py, pz = b[ii].pz;
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        size_t node = 0;
+        for (;;) {
+            const orc_node3_t *n = &nodes[node];
+            const float dx = n->px - px, dy = n->py - py, dz = n->pz - pz;
+            const float d_sq = (dx * dx + dy * dy) + dz * dz;
+            const int far = n->size * n->size < d_sq * t_sq;
+            if (far || n->children == 0) {
+                if ((far || (fix_near_leaves && n->mass != 0.0f)) && d_sq > 0) {
+                    const float inv = orc_fast_inv_sqrt(d_sq + e_sq);
+                    const float s = n->mass * (inv * inv * inv);
+                    ax += dx * s; ay += dy * s; az += dz * s;
+                }
+                if (n->next == 0) break;
+                node = n->next;
+            } else {
+                node = n->children;
+            }
+        }
+        float *o = acc_out + 3 * (ii - (long long)i0);
+        o[0] = ax; o[1] = ay; o[2] = az;
+    }
+}

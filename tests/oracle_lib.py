@@ -51,6 +51,9 @@ def oracle():
         L.orc_bh_build.argtypes = [_vp, _sz, C.POINTER(_vp)]
         L.orc_bh_acc.argtypes = [_vp, _sz, _f, _f, _vp, _sz, _sz, _i, _vp]
         L.orc_free.argtypes = [_vp]
+        L.orc_bh3_build.restype = _sz
+        L.orc_bh3_build.argtypes = [_vp, _sz, C.POINTER(_vp)]
+        L.orc_bh3_acc.argtypes = [_vp, _f, _f, _vp, _sz, _sz, _i, _vp]
         L.orc_collide.restype = _sz
         L.orc_collide.argtypes = [_vp, _sz, C.POINTER(_sz)]
         L.orc_resolve.argtypes = [_vp, _sz, _sz]
@@ -186,3 +189,26 @@ def ref_collide(b, kind="strict"):
     b = b.copy()
     reference(kind).ref_collide(b.ctypes.data, b.shape[0])
     return b
+
+
+ORC_NODE3_DTYPE = np.dtype([("px", "<f4"), ("py", "<f4"), ("pz", "<f4"), ("mass", "<f4"), ("cx", "<f4"), ("cy", "<f4"),
+                            ("cz", "<f4"), ("size", "<f4"), ("children", "<u8"), ("next", "<u8"), ("depth", "<u8")])
+assert ORC_NODE3_DTYPE.itemsize == 56
+
+
+def orc_bh3_build(b):
+    ptr = _vp()
+    m = oracle().orc_bh3_build(b.ctypes.data, b.shape[0], C.byref(ptr))
+    buf = (C.c_char * (m * ORC_NODE3_DTYPE.itemsize)).from_address(ptr.value)
+    nodes = np.frombuffer(buf, dtype=ORC_NODE3_DTYPE, count=m).copy()
+    oracle().orc_free(ptr)
+    return nodes
+
+
+def orc_bh3_acc(b, theta, eps, nodes=None, i0=0, i1=None, fix_near_leaves=False):
+    n = b.shape[0]
+    i1 = n if i1 is None else i1
+    nodes = orc_bh3_build(b) if nodes is None else nodes
+    out = np.zeros((i1 - i0, 3), dtype=np.float32)
+    oracle().orc_bh3_acc(nodes.ctypes.data, theta, eps, b.ctypes.data, i0, i1, 1 if fix_near_leaves else 0, out.ctypes.data)
+    return out

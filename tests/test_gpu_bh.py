@@ -45,11 +45,12 @@ def test_tree_matches_reference_cells(n, seed):
     want = oracle_preorder(O.orc_bh_build(b))
     with bh_sim(b, theta=1.0, eps=1.0) as s:
         s.attract()
-        f6, nxt, depth, leaf = s.bh_nodes()
-        assert s.info()["bh_nodes"] == f6.shape[0]
-    assert f6.shape[0] == want.shape[0]
-    for col, k in enumerate(("px", "py", "mass", "cx", "cy", "size")):
-        assert np.array_equal(bits(f6[:, col]), bits(want[k])), k
+        f8, nxt, depth, leaf = s.bh_nodes()
+        assert s.info()["bh_nodes"] == f8.shape[0]
+    assert f8.shape[0] == want.shape[0]
+    for col, k in ((0, "px"), (1, "py"), (3, "mass"), (4, "cx"), (5, "cy"), (7, "size")):
+        assert np.array_equal(bits(f8[:, col]), bits(want[k])), k
+    assert not f8[:, 2].any() and not f8[:, 6].any()
     assert np.array_equal(depth, want["depth"].astype(np.uint32))
     assert np.array_equal(leaf, want["children"] == 0)
 
@@ -154,13 +155,74 @@ def test_bh_fixed_near_leaves_and_fast_rsqrt():
     assert 5e-4 < np.median(rel) < 5e-3
 
 
-def test_bh_rejects_3d_and_f64():
+def test_bh_rejects_f64():
     b = ic.plummer(128, dims=3)
     lib = capi.gpu_lib()
     import ctypes as C
     from nbodysim_b200.simulation import default_params
 
-    for kw in ({"dims": 3}, {"dims": 2, "precision": capi.PRECISION_F64}):
+    for kw in ({"dims": 3, "precision": capi.PRECISION_F64}, {"dims": 2, "precision": capi.PRECISION_F64}):
         p = default_params(force_algo=capi.FORCE_BARNES_HUT, **kw)
         ctx = C.c_void_p()
         assert lib.nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 128) == capi.EINVAL
+
+
+# ------------------------------------------------------------------ octree (dims = 3)
+def oracle_preorder3(nodes):
+    out, stack = [], [0]
+    while stack:
+        i = stack.pop()
+        nd = nodes[i]
+        if nd["children"] == 0 and nd["mass"] == 0.0 and i != 0:
+            continue
+        out.append(i)
+        if nd["children"] != 0:
+            c = int(nd["children"])
+            stack.extend(range(c + 7, c - 1, -1))
+    return nodes[out]
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (2, 2), (9, 3), (500, 4), (20000, 5)])
+def test_octree_matches_oracle_cells(n, seed):
+    """dims=3: the same construction one dimension up (8 children, 3 bits x 21 levels); cells, centres of mass
+    and walk order equal the oracle's octree bit for bit"""
+    b = ic.plummer(n, seed=seed, dims=3)
+    if n > 2:
+        b["mass"] = (b["mass"] * np.random.default_rng(seed).uniform(0.2, 3.0, n)).astype(np.float32)
+    want = oracle_preorder3(O.orc_bh3_build(b))
+    with Simulation(b, force_algo=capi.FORCE_BARNES_HUT, dims=3, theta=0.7, eps=0.01, rsqrt_mode=capi.RSQRT_REFCOMPAT) as s:
+        s.attract()
+        f8, nxt, depth, leaf = s.bh_nodes()
+    assert f8.shape[0] == want.shape[0]
+    for col, k in enumerate(("px", "py", "pz", "mass", "cx", "cy", "cz", "size")):
+        assert np.array_equal(bits(f8[:, col]), bits(want[k])), k
+    assert np.array_equal(depth, want["depth"].astype(np.uint32)) and np.array_equal(leaf, want["children"] == 0)
+
+
+@pytest.mark.parametrize("theta,fix,walk", [(1.0, 0, 0), (0.5, 1, 0), (0.5, 1, 1), (0.3, 0, 1)])
+def test_octree_acc_bitexact_vs_oracle(theta, fix, walk):
+    b = ic.plummer(30000, seed=11, dims=3)
+    with Simulation(b, force_algo=capi.FORCE_BARNES_HUT, dims=3, theta=theta, eps=0.01, rsqrt_mode=capi.RSQRT_REFCOMPAT,
+                    bh_fix_near_leaves=fix, bh_walk=walk) as s:
+        s.attract()
+        out = s.download().copy()
+    want = O.orc_bh3_acc(b, theta, 0.01, fix_near_leaves=bool(fix))
+    got = np.concatenate([out["acc"], out["acc_z"][:, None]], axis=1)
+    assert np.array_equal(bits(got), bits(want))
+
+
+def test_octree_fast_accuracy_and_energy():
+    """accurate rsqrt + near leaves included + theta = 0.4: a usable O(N log N) 3-D force (median error ~1e-3),
+    and a 200-step run conserves energy to 1e-3"""
+    b = ic.plummer(50000, seed=8, dims=3)
+    with Simulation(b, dt=1e-3, force_algo=capi.FORCE_BARNES_HUT, dims=3, theta=0.4, eps=0.01, bh_fix_near_leaves=1) as s:
+        s.attract()
+        out = s.download().copy()
+        a = np.concatenate([out["acc"], out["acc_z"][:, None]], axis=1).astype(np.float64)
+        ex = O.orc_exact_acc(b, float(np.float32(0.01)), dims=3, i0=0, i1=2000)
+        rel = np.linalg.norm(a[:2000] - ex, axis=1) / np.linalg.norm(ex, axis=1)
+        assert np.median(rel) < 3e-3 and np.percentile(rel, 99) < 3e-2, (np.median(rel), np.percentile(rel, 99))
+        k0, w0, _ = s.energy()
+        s.step(200)
+        k1, w1, _ = s.energy()
+    assert abs((k1 + w1 - k0 - w0) / (k0 + w0)) < 1e-3
