@@ -94,10 +94,11 @@ typedef struct nbody_params {
     int32_t  sort_impl;       /* radix sort used by the Barnes-Hut build and the collision pass: 0 = cub::DeviceRadixSort
                                  (library; default, 0.23 ms for 1M 64-bit keys), 1 = the hand-written stable LSD sort of
                                  csrc/radix_sort.cuh (0.75 ms).  Identical results. */
-    int32_t  bh_walk;         /* Barnes-Hut only.  0 = one independent walk per thread, targets in Z-order
-                                 (default: measured faster at theta = 1, where walks are ~125 nodes long);
-                                 1 = warp-cooperative walk (each node record loaded once per warp).
-                                 Identical results bit for bit; only the memory access pattern differs. */
+    int32_t  bh_walk;         /* Barnes-Hut only.  0 = auto, 1 = one independent walk per thread (targets in Z-order),
+                                 2 = warp-cooperative walk (the warp walks the union of its 32 targets' traversals, every
+                                 node record loaded once per warp).  Identical results bit for bit.  Measured: short
+                                 walks (the reference's 2-D theta = 1, ~125 nodes) favour 1; long walks (3-D, or
+                                 theta < 0.7) favour 2 by up to 1.8x -- auto picks accordingly. */
     int32_t  exchange;        /* how the new positions reach the other GPUs each step.  0 = auto: with ngpus > 1 in one
                                  process and full peer access, the integrator kernel stores every new position
                                  directly into all peers' buffers over NVLink (integrate + allgather in ONE kernel, no

@@ -30,6 +30,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "radix_sort.cuh"
+#include <cstring>
 
 namespace nb {
 
@@ -169,12 +170,12 @@ bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned 
 }
 
 // node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag
+// Two 16-byte records per node so that a visit costs two vector loads:
+//   data = (x, y, mass, size*size)          aux = (z bits [octree], next, depth | leaf << 8, 0)
 struct BhNodes {
-    float4 *data;        // x, y, mass, size*size
-    float *z;            // z of the position (octree only)
+    float4 *data;
+    uint4 *aux;
     float4 *quad;        // cx, cy, size, cz (diagnostics / parity tests)
-    unsigned *next;
-    unsigned *meta;      // depth (low 8 bits) | leaf << 8
 };
 
 // ---- 5. emit the pre-order node array -------------------------------------------------------------
@@ -205,9 +206,7 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
             if (c < cap) {
                 const bool is_leaf = (d == leafd);
                 nodes.data[c] = make_float4(is_leaf ? x : 0.f, is_leaf ? y : 0.f, is_leaf ? mass : 0.f, __fmul_rn(size, size));
-                if (DIMS == 3) nodes.z[c] = is_leaf ? z : 0.f;
                 nodes.quad[c] = make_float4(cx, cy, size, cz);
-                nodes.meta[c] = (unsigned)d | (is_leaf ? 256u : 0u);
                 // skip pointer: first sorted body after s whose depth-d prefix differs
                 unsigned nx = 0;
                 if (d > 0) {
@@ -220,7 +219,7 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                     }
                     nx = (lo < n) ? offs[lo] : 0u;
                 }
-                nodes.next[c] = nx;
+                nodes.aux[c] = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx, (unsigned)d | (is_leaf ? 256u : 0u), 0u);
             }
         }
         if (d < leafd) {
@@ -241,19 +240,19 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
 template <int DIMS>
 __device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned c, unsigned m, unsigned level)
 {
-    const unsigned end = nodes.next[c];
+    const unsigned end = nodes.aux[c].y;
     float px = 0.f, py = 0.f, pz = 0.f, mass = 0.f;
     unsigned ch = c + 1;                                   // children in quadrant order
     for (unsigned i = 0; i < BhT<DIMS>::NCHILD && ch != end && ch < m; ++i) {
-        if ((nodes.meta[ch] & 255u) != level + 1u) break;
+        const uint4 a = nodes.aux[ch];
+        if ((a.z & 255u) != level + 1u) break;
         const float4 d = nodes.data[ch];
         px = __fadd_rn(px, __fmul_rn(d.x, d.z));
         py = __fadd_rn(py, __fmul_rn(d.y, d.z));
-        if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(nodes.z[ch], d.z));
+        if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(__uint_as_float(a.x), d.z));
         mass = __fadd_rn(mass, d.z);
-        const unsigned nx = nodes.next[ch];
-        if (nx == 0) break;
-        ch = nx;
+        if (a.y == 0) break;
+        ch = a.y;
     }
     if (mass > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
         const float inv = __fdiv_rn(1.0f, mass);
@@ -264,7 +263,7 @@ __device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned
     float4 d = nodes.data[c];
     d.x = px; d.y = py; d.z = mass;
     nodes.data[c] = d;
-    if (DIMS == 3) nodes.z[c] = pz;
+    if (DIMS == 3) reinterpret_cast<float *>(&nodes.aux[c])[0] = pz;
 }
 
 template <int DIMS>
@@ -338,9 +337,8 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
     unsigned i = 0;
     do {
         const float4 nd = nodes.data[i];
-        const float ndz = (DIMS == 3) ? nodes.z[i] : 0.f;
-        const bool is_leaf = (nodes.meta[i] & 256u) != 0u;
-        if (bh_visit<DIMS, REFCOMPAT>(nd, ndz, is_leaf, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = nodes.next[i];
+        const uint4 na = nodes.aux[i];
+        if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
         else i = i + 1;
     } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (reported by node_count)
     const size_t l = blk_index(body - shard_start, 0);
@@ -372,13 +370,11 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
     unsigned resume = mine ? 0u : DONE;
     unsigned i = __reduce_min_sync(0xffffffffu, resume);
     while (i < cap) {                                        // DONE (and an overflowed tree) end the walk
-        const float4 nd = nodes.data[i];                     // warp-uniform loads
-        const unsigned nx = nodes.next[i];
-        const float ndz = (DIMS == 3) ? nodes.z[i] : 0.f;
-        const bool is_leaf = (nodes.meta[i] & 256u) != 0u;
+        const float4 nd = nodes.data[i];                     // warp-uniform loads: two 16-byte records per node
+        const uint4 na = nodes.aux[i];
         if (resume == i) {
-            if (bh_visit<DIMS, REFCOMPAT>(nd, ndz, is_leaf, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az))
-                resume = nx ? nx : DONE;
+            if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az))
+                resume = na.y ? na.y : DONE;
             else
                 resume = i + 1;
         }
@@ -402,8 +398,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
     BH_ALLOC(node_data, (size_t)node_cap * 16) BH_ALLOC(node_quad, (size_t)node_cap * 16)
-    BH_ALLOC(node_z, (size_t)node_cap * 4)
-    BH_ALLOC(node_next, (size_t)node_cap * 4) BH_ALLOC(node_meta, (size_t)node_cap * 4)
+    BH_ALLOC(node_aux, (size_t)node_cap * 16)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
@@ -424,7 +419,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_z, node_next, node_meta, temp};
+    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_aux, temp};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -432,8 +427,7 @@ void BhWorkspace::release()
 static BhNodes bh_nodes(const BhWorkspace &w)
 {
     BhNodes nd;
-    nd.data = (float4 *)w.node_data; nd.z = (float *)w.node_z; nd.quad = (float4 *)w.node_quad;
-    nd.next = (unsigned *)w.node_next; nd.meta = (unsigned *)w.node_meta;
+    nd.data = (float4 *)w.node_data; nd.aux = (uint4 *)w.node_aux; nd.quad = (float4 *)w.node_quad;
     return nd;
 }
 
@@ -530,19 +524,18 @@ cudaError_t BhWorkspace::download_nodes(float *f8, unsigned *u2, size_t cap, cud
 {
     const size_t m = std::min<size_t>(std::min<size_t>(cap, n_nodes), node_cap);
     std::vector<float4> d(m), q(m);
-    std::vector<float> z(m, 0.f);
-    std::vector<unsigned> nx(m), me(m);
+    std::vector<uint4> a(m);
     cudaError_t e;
     if ((e = cudaMemcpyAsync(d.data(), node_data, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(q.data(), node_quad, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if (dims == 3 && (e = cudaMemcpyAsync(z.data(), node_z, m * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(nx.data(), node_next, m * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(me.data(), node_meta, m * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(a.data(), node_aux, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     for (size_t i = 0; i < m; ++i) {
-        f8[8 * i + 0] = d[i].x; f8[8 * i + 1] = d[i].y; f8[8 * i + 2] = z[i]; f8[8 * i + 3] = d[i].z;
+        float z;
+        memcpy(&z, &a[i].x, 4);
+        f8[8 * i + 0] = d[i].x; f8[8 * i + 1] = d[i].y; f8[8 * i + 2] = (dims == 3) ? z : 0.f; f8[8 * i + 3] = d[i].z;
         f8[8 * i + 4] = q[i].x; f8[8 * i + 5] = q[i].y; f8[8 * i + 6] = (dims == 3) ? q[i].w : 0.f; f8[8 * i + 7] = q[i].z;
-        u2[2 * i + 0] = nx[i]; u2[2 * i + 1] = me[i];
+        u2[2 * i + 0] = a[i].y; u2[2 * i + 1] = a[i].z;
     }
     return cudaSuccess;
 }

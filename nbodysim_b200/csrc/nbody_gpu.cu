@@ -224,7 +224,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     }
     if (ctx->bh) {
         CU(d.bh.alloc(ctx->n, ctx->p.dims));
-        d.bh.warp_walk = (ctx->p.bh_walk == 1);
+        d.bh.warp_walk = ctx->p.bh_walk == 2 || (ctx->p.bh_walk == 0 && (ctx->p.dims == 3 || ctx->p.theta < 0.7f));
         d.bh.own_sort = (ctx->p.sort_impl == 1);
     }
     return NBODY_OK;
