@@ -71,3 +71,21 @@ def test_bh_coincident_bodies_merge_like_reference():
     nodes = O.orc_bh_build(b)
     assert m == nodes.shape[0]
     assert np.array_equal(bits(O.orc_bh_acc(b, 1.0, 1.0, nodes)), bits(a_ref))
+
+
+def test_octree_oracle_properties():
+    """the 3-D generalisation in the oracle (checker of the library's dims=3 path): with theta -> 0 and near
+    leaves included the walk IS the direct sum over bodies; with theta = 0.5 it approximates exact math"""
+    b = ic.plummer(1500, seed=3, dims=3)
+    nodes = O.orc_bh3_build(b)
+    leaves = nodes[(nodes["children"] == 0) & (nodes["mass"] > 0)]
+    assert leaves.shape[0] == 1500 and abs(leaves["mass"].astype(np.float64).sum() - 1.0) < 1e-5
+    assert abs(float(nodes[0]["mass"]) - 1.0) < 1e-5                      # root holds the total mass
+    direct = O.orc_acc_f64sum(b, 0.01, dims=3)
+    fixed = O.orc_bh3_acc(b, 0.0, 0.01, nodes, fix_near_leaves=True).astype(np.float64)
+    assert np.abs(fixed - direct).max() <= 3e-5 * np.abs(direct).max()
+    assert not O.orc_bh3_acc(b, 0.0, 0.01, nodes).any()                   # the reference's quirk: near leaves dropped
+    ex = O.orc_exact_acc(b, 0.01, dims=3)
+    a = O.orc_bh3_acc(b, 0.5, 0.01, nodes, fix_near_leaves=True).astype(np.float64)
+    rel = np.linalg.norm(a - ex, axis=1) / np.linalg.norm(ex, axis=1)
+    assert np.median(rel) < 8e-3
