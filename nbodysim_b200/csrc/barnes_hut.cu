@@ -20,13 +20,13 @@
 //   4. cells owned by each sorted body = the path cells that first appear with it; exclusive scan
 //      -> depth-first pre-order node array WITHOUT the reference's empty leaves (they contribute +-0)
 //   5. skip pointers (`next`) by binary search on the sorted keys; first child = index + 1
-//   6. centres of mass bottom-up, one launch per level, children summed in quadrant order
+//   6. centres of mass bottom-up in one launch: every leaf climbs towards the root, the LAST child to arrive at a
+//      cell (atomic arrival counter) sums the cell's children in quadrant order
 //   7. walk: one thread per target (targets in Z-order for coherence), node records from L2.
 // Limits: bodies whose positions agree in all 32 levels are merged like the reference's coincident
 // bodies (`pos == existing_pos`, masses added in index order); the reference would subdivide
 // further if their positions differ beyond that depth.
 #include "kernels.h"
-#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "radix_sort.cuh"
@@ -185,7 +185,7 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                const unsigned *__restrict__ idx, size_t n, const BhRoot *__restrict__ root,
                const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
                const unsigned char *__restrict__ first, const unsigned char *__restrict__ leaf,
-               BhNodes nodes, unsigned cap)
+               BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap)
 {
     constexpr int BITS = BhT<DIMS>::BITS;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +219,23 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                     }
                     nx = (lo < n) ? offs[lo] : 0u;
                 }
-                nodes.aux[c] = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx, (unsigned)d | (is_leaf ? 256u : 0u), 0u);
+                // parent cell: the previous cell of this body's chain, or -- for the first owned cell -- the
+                // depth d-1 cell of the first sorted body that shares the (d-1)-prefix
+                unsigned par = 0xffffffffu;
+                if (d > firstd) par = c - 1;
+                else if (d == 1) par = 0u;
+                else if (d > 1) {
+                    const int shp = 64 - BITS * (d - 1);
+                    const unsigned long long pp = k >> shp;
+                    size_t lo = 0, hi = s;               // first j in [0, s] with (keys[j] >> shp) >= pp
+                    while (lo < hi) {
+                        const size_t mid = (lo + hi) >> 1;
+                        if ((keys[mid] >> shp) >= pp) hi = mid; else lo = mid + 1;
+                    }
+                    par = offs[lo] + (unsigned)(d - 1 - (int)first[lo]);
+                }
+                if (par != 0xffffffffu && par < cap) atomicAdd(&arrive[par], 1u);   // low byte: number of children
+                nodes.aux[c] = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx, (unsigned)d | (is_leaf ? 256u : 0u), par);
             }
         }
         if (d < leafd) {
@@ -234,19 +250,21 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
 }
 
 // ---- 6. centres of mass (Quadtree::propagate, :236-258) -------------------------------------------------
-// One cooperative launch: levels deepest-first with a grid-wide barrier between levels.  Sorted body s
-// owns the consecutive cells offs[s] .. offs[s]+count[s]-1 at depths first[s] .. leaf[s], so the branch
-// cell of level L on its chain is found by index arithmetic -- no per-level node lists.
+// One launch, no level barriers: the thread of every leaf climbs towards the root; at each cell it adds one
+// arrival (high bits of arrive[], the low byte holds the number of children counted by the emit kernel) and
+// stops unless it is the LAST child to arrive, in which case all children are complete and it sums them in
+// quadrant order -- `pos += child.pos * child.mass; mass += child.mass`, then `pos *= 1/mass` -- exactly the
+// reference's arithmetic and order.  Children written by other SMs are read with L1-bypassing loads.
 template <int DIMS>
 __device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned c, unsigned m, unsigned level)
 {
-    const unsigned end = nodes.aux[c].y;
+    const unsigned end = __ldcg(&nodes.aux[c]).y;
     float px = 0.f, py = 0.f, pz = 0.f, mass = 0.f;
     unsigned ch = c + 1;                                   // children in quadrant order
     for (unsigned i = 0; i < BhT<DIMS>::NCHILD && ch != end && ch < m; ++i) {
-        const uint4 a = nodes.aux[ch];
+        const uint4 a = __ldcg(&nodes.aux[ch]);
         if ((a.z & 255u) != level + 1u) break;
-        const float4 d = nodes.data[ch];
+        const float4 d = __ldcg(&nodes.data[ch]);
         px = __fadd_rn(px, __fmul_rn(d.x, d.z));
         py = __fadd_rn(py, __fmul_rn(d.y, d.z));
         if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(__uint_as_float(a.x), d.z));
@@ -260,30 +278,32 @@ __device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned
         py = __fmul_rn(py, inv);
         if (DIMS == 3) pz = __fmul_rn(pz, inv);
     }
-    float4 d = nodes.data[c];
+    float4 d = __ldcg(&nodes.data[c]);
     d.x = px; d.y = py; d.z = mass;
-    nodes.data[c] = d;
-    if (DIMS == 3) reinterpret_cast<float *>(&nodes.aux[c])[0] = pz;
+    __stcg(&nodes.data[c], d);
+    if (DIMS == 3) __stcg(reinterpret_cast<float *>(&nodes.aux[c]), pz);
 }
 
 template <int DIMS>
 __global__ void __launch_bounds__(256)
 bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned char *__restrict__ first,
-                    const unsigned char *__restrict__ leaf, const unsigned *__restrict__ count, unsigned cap)
+                    const unsigned char *__restrict__ leaf, const unsigned *__restrict__ count, unsigned *__restrict__ arrive,
+                    unsigned cap)
 {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || count[s] == 0) return;
     const unsigned m = min(offs[n], cap);
-    const int dmax = (int)min(count[n + 1], (unsigned)BhT<DIMS>::LEVELS);
-    for (int level = dmax - 1; level >= 0; --level) {
-        for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (size_t)gridDim.x * blockDim.x) {
-            const int f = first[s], l = leaf[s];
-            if (count[s] != 0 && f <= level && level < l) {
-                const unsigned c = offs[s] + (unsigned)(level - f);
-                if (c < m) bh_propagate_cell<DIMS>(nodes, c, m, (unsigned)level);
-            }
-        }
+    unsigned c = offs[s] + (unsigned)(leaf[s] - first[s]);           // this body's leaf cell
+    while (c < m) {
+        const uint4 a = __ldcg(&nodes.aux[c]);
+        const unsigned par = a.w;
+        if (par == 0xffffffffu || par >= m) break;                     // reached the root
+        __threadfence();                                               // my cell is complete before I announce it
+        const unsigned old = atomicAdd(&arrive[par], 0x100u);
+        if ((old >> 8) + 1u != (old & 0xffu)) break;                   // a sibling will arrive later and do the work
         __threadfence();
-        grid.sync();
+        bh_propagate_cell<DIMS>(nodes, par, m, (a.z & 255u) - 1u);
+        c = par;
     }
 }
 
@@ -398,28 +418,20 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
     BH_ALLOC(node_data, (size_t)node_cap * 16) BH_ALLOC(node_quad, (size_t)node_cap * 16)
-    BH_ALLOC(node_aux, (size_t)node_cap * 16)
+    BH_ALLOC(node_aux, (size_t)node_cap * 16) BH_ALLOC(node_arrive, (size_t)node_cap * 4)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
     temp_bytes = std::max(std::max(t1, t2), radix_sort_temp_bytes(n));
     BH_ALLOC(temp, temp_bytes)
-    {   // co-resident grid size for the cooperative propagate kernel
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (dims == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_propagate_kernel<3>, 256, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_propagate_kernel<2>, 256, 0);
-        coop_blocks = std::max(1, sms * std::max(1, std::min(per_sm, 4)));
-    }
 #undef BH_ALLOC
     return cudaSuccess;
 }
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_aux, temp};
+    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_aux, node_arrive, temp};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -453,19 +465,14 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
                                                 (unsigned char *)w.leaf, cnt + n + 1);
     tb = w.temp_bytes;
     if ((e = cub::DeviceScan::ExclusiveSum(w.temp, tb, (const unsigned *)w.count, (unsigned *)w.offs, (int)n + 1, st)) != cudaSuccess) return e;
+    // arrival counters of at most min(node_cap, 4n + 1024) cells (a tree over n bodies has < that many in practice)
+    if ((e = cudaMemsetAsync(w.node_arrive, 0, (size_t)w.node_cap * 4, st)) != cudaSuccess) return e;
     bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
                                                (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,
-                                               (const unsigned char *)w.leaf, bh_nodes(w), w.node_cap);
-    {
-        BhNodes nd = bh_nodes(w);
-        size_t nn = n;
-        const unsigned *po = (const unsigned *)w.offs, *pc = (const unsigned *)w.count;
-        const unsigned char *pf = (const unsigned char *)w.first, *pl = (const unsigned char *)w.leaf;
-        unsigned cap = w.node_cap;
-        void *args[] = {&nd, &nn, &po, &pf, &pl, &pc, &cap};
-        const unsigned grid = std::min(g256, (unsigned)w.coop_blocks);
-        if ((e = cudaLaunchCooperativeKernel((void *)bh_propagate_kernel<DIMS>, dim3(grid), dim3(256), args, 0, st)) != cudaSuccess) return e;
-    }
+                                               (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, w.node_cap);
+    bh_propagate_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned char *)w.first,
+                                                    (const unsigned char *)w.leaf, (const unsigned *)w.count, (unsigned *)w.node_arrive,
+                                                    w.node_cap);
     w.count_valid = false;
     if (launches) *launches += 7 + 3;                        // own kernels + the sort/scan passes (counted as 3)
     return cudaGetLastError();

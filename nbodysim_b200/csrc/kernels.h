@@ -112,11 +112,10 @@ struct BhWorkspace {
     unsigned node_cap = 0, n_nodes = 0;
     void *root = nullptr, *box = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
-    void *node_data = nullptr, *node_quad = nullptr, *node_aux = nullptr;
+    void *node_data = nullptr, *node_quad = nullptr, *node_aux = nullptr, *node_arrive = nullptr;
     int dims = 2;                // 2 = the reference's quadtree, 3 = octree
     void *temp = nullptr;
     size_t temp_bytes = 0;
-    int coop_blocks = 148;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
     bool own_sort = false;       // hand-written radix sort (radix_sort.cuh) instead of cub::DeviceRadixSort

@@ -117,7 +117,7 @@ def test_bh_both_walks_bitexact(walk):
 
 
 def test_bh_graph_replay_bitexact_vs_golden():
-    """the whole Barnes-Hut step (build incl. sort, scan, cooperative COM pass; walk; integrator) replayed from
+    """the whole Barnes-Hut step (build incl. sort, scan, COM pass; walk; integrator) replayed from
     a CUDA graph: 10 reference steps, still bit-exact"""
     g = np.load(os.path.join(G, "bh2000.npz"))
     with bh_sim(g["bodies"], dt=float(g["dt"]), theta=1.0, eps=1.0, use_graph=1,
