@@ -35,6 +35,8 @@ def read_snapshot(path, n):
 
 
 def run(args):
+    if not os.path.exists(EXE):
+        pytest.skip("host/_build/nbody_run not built (make host)")
     r = subprocess.run([EXE] + args, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     return r.stdout
