@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--splits", type=int, default=0)
+    ap.add_argument("--exchange", choices=["auto", "nccl", "peer"], default="auto",
+                    help="multi-GPU position exchange: auto = fused integrate-and-push over CUDA IPC peer mappings when "
+                         "every rank can map its peers (else ncclAllGather); nccl / peer force one")
     return ap.parse_args()
 
 
@@ -222,7 +225,8 @@ def native_arm(args):
             idbuf = torch.tensor(list(raw), dtype=torch.uint8)
         idbuf = idbuf.to(dev)
         dist.broadcast(idbuf, 0)
-        kw.update(world=world, rank=rank, nccl_id=bytes(idbuf.cpu().tolist()))
+        kw.update(world=world, rank=rank, nccl_id=bytes(idbuf.cpu().tolist()),
+                  exchange={"auto": 0, "nccl": 1, "peer": 2}[args.exchange])
     stream = torch.cuda.current_stream()
     if world == 1:
         kw["stream"] = stream.cuda_stream          # launch on torch's current stream: torch events see the kernels
@@ -388,7 +392,11 @@ def native_arm(args):
         "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wname, "n": n, "dims": 3, "eps": EPS, "dt": DT, "ic_seed": SEED,
-                   "rsqrt": "fast (MUFU.RSQ)", "parallelism": f"targets sharded over {world} GPU(s), positions allgathered",
+                   "rsqrt": "fast (MUFU.RSQ)", "parallelism": (f"targets sharded over {world} GPU(s); new positions reach the other ranks by " +
+                                   ("peer stores from the integrator kernel over NVLink (CUDA IPC mappings, completion "
+                                    "flags in peer memory; no collective call)" if i1["p2p_exchange"] == 2 else
+                                    "ncclAllGather on a communication stream") if world > 1 else "one GPU"),
+                   "exchange": {0: "nccl_allgather", 1: "peer_stores_one_process", 2: "peer_stores_ipc"}[i1["p2p_exchange"]] if world > 1 else None,
                    "l2": "flushed (256 MiB write) before every timed step", "j_splits": i1["j_splits"],
                    "force_ctas": i1["force_ctas"], "ctas_per_sm": i1["ctas_per_sm"], "fused_integrator": bool(i1["fused"]),
                    "mass_form": ("uniform-mass (equal masses detected: 11 fp32 lane-ops per interaction)" if i1["uniform_mass"]

@@ -99,10 +99,13 @@ typedef struct nbody_params {
                                  node record loaded once per warp).  Identical results bit for bit.  Measured: short
                                  walks (the reference's 2-D theta = 1, ~125 nodes) favour 1; long walks (3-D, or
                                  theta < 0.7) favour 2 by up to 1.8x -- auto picks accordingly. */
-    int32_t  exchange;        /* how the new positions reach the other GPUs each step.  0 = auto: with ngpus > 1 in one
-                                 process and full peer access, the integrator kernel stores every new position
-                                 directly into all peers' buffers over NVLink (integrate + allgather in ONE kernel, no
-                                 collective call); otherwise ncclAllGather on a communication stream.  1 = always NCCL. */
+    int32_t  exchange;        /* how the new positions reach the other GPUs each step.  0 = auto: when every GPU can map
+                                 every other one (ngpus > 1 in one process with peer access; or world > 1, one process
+                                 per GPU on one node, peers mapped through CUDA IPC), the integrator kernel stores
+                                 every new position directly into all peers' buffers over NVLink and publishes a
+                                 completion counter there (integrate + allgather + signal in ONE kernel, no
+                                 collective call); otherwise ncclAllGather on a communication stream.  1 = always
+                                 NCCL.  2 = require the peer path (init fails instead of falling back). */
     /* --- single-process multi-GPU (C driver): ngpus devices, NCCL comms created internally --- */
     int32_t  ngpus;           /* 0 or 1 = single GPU */
     int32_t  device_ids[NBODY_MAX_GPUS]; /* CUDA ordinals; device_ids[0] is used when ngpus<=1 */
@@ -119,7 +122,8 @@ typedef struct nbody_info {
     uint64_t shard_start;     /* first target owned by this process (all local GPUs) */
     uint64_t shard_count;
     int32_t  world, rank, ngpus_local;
-    int32_t  p2p_exchange;    /* 1 if positions are exchanged by peer-to-peer stores from the integrator kernel */
+    int32_t  p2p_exchange;    /* positions exchanged by peer stores from the integrator kernel: 1 = GPUs of one process,
+                                 2 = across processes (CUDA IPC mappings + completion flags in peer memory); 0 = NCCL */
     int32_t  sm_count;        /* of the first local device */
     int32_t  sm_clock_khz;    /* cudaDevAttrClockRate */
     int32_t  j_splits;        /* source-range splits chosen for the force kernel */

@@ -74,6 +74,44 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// ---- cross-process exchange: completion flags in peer memory (CUDA IPC over NVLink) -------------
+// Every rank owns an array `flags[world]` of 64-bit step counters in its own HBM; flags[r] is written only by
+// rank r (through an IPC mapping) and says "all positions rank r pushed for steps < flags[r] have landed here".
+struct PeerSignal {
+    unsigned long long *slot[16];   // slot[k]: this rank's counter inside peer k's flag array
+    int n;                          // peers to signal (0: no signalling, e.g. single GPU)
+    unsigned long long value;       // number of integrate-and-push steps completed once this launch is done
+    unsigned *arrive;               // CTA arrival counter of this launch (device-local, self-resetting)
+};
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Called by EVERY thread of the grid after its last peer store.  The last CTA to arrive publishes `value` to
+// every peer: each thread fences its own stores at system scope, the CTA's arrival is a device-scope atomic,
+// and the publishing thread fences again before the release stores (fence-atomic / atomic-fence chains make
+// all CTAs' stores happen-before the flag).
+__device__ __forceinline__ void signal_peers_when_grid_done(const PeerSignal &sig)
+{
+    if (sig.n == 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(sig.arrive, 1u);
+        if (prev == gridDim.x - 1) {
+            *sig.arrive = 0;                       // the next launch is stream-ordered after this one
+            __threadfence_system();
+            for (int k = 0; k < sig.n; ++k) st_release_sys_u64(sig.slot[k], sig.value);
+        }
+    }
+}
+
 // MUFU.RSQ, no denormal fix-up code around it
 __device__ __forceinline__ float rsqrt_approx(float x)
 {

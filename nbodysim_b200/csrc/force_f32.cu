@@ -212,11 +212,11 @@ cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st)
 // One thread per 4 consecutive bodies of a block: float4 loads/stores on every component array.
 // acc = G * sum over partial slots in slot order; then the same integrate_body_f32 as the fused
 // epilogue.  Bytes per body: read posm 16 + vel 12 + 12*nslots, write posm 16 + vel 12 + acc 12.
-__global__ void __launch_bounds__(256)
-integrate_f32_kernel(const float *__restrict__ posm_cur, PeerDests dests,
-                     float *__restrict__ vel, float *__restrict__ acc,
-                     const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
-                     int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
+__device__ __forceinline__ void
+integrate_f32_group(const float *__restrict__ posm_cur, const PeerDests &dests,
+                    float *__restrict__ vel, float *__restrict__ acc,
+                    const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                    int n_iblk_shard, int acc_only, long long n_real, const IntegParams &ip)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // one per 4 bodies
     const int lb = gid >> 6;                                 // 64 float4 groups per block
@@ -264,11 +264,23 @@ integrate_f32_kernel(const float *__restrict__ posm_cur, PeerDests dests,
     for (int c = 0; c < 3; ++c) *reinterpret_cast<float4 *>(vel + loff + c * BLK) = V[c];
 }
 
+// With the cross-process exchange (`sig.n > 0`) the kernel is integrate + allgather + completion signal in one:
+// the last CTA to finish publishes this rank's step counter into every peer's flag array.
+__global__ void __launch_bounds__(256)
+integrate_f32_kernel(const float *__restrict__ posm_cur, PeerDests dests, PeerSignal sig,
+                     float *__restrict__ vel, float *__restrict__ acc,
+                     const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                     int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
+{
+    integrate_f32_group(posm_cur, dests, vel, acc, accp, acc_scale, nslots, i_blk0, n_iblk_shard, acc_only, n_real, ip);
+    signal_peers_when_grid_done(sig);
+}
+
 cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st)
 {
     const int threads = L.n_iblk_shard * 64;
     const int grid = (threads + 255) / 256;
-    integrate_f32_kernel<<<grid, 256, 0, st>>>((const float *)L.posm_cur, L.dests,
+    integrate_f32_kernel<<<grid, 256, 0, st>>>((const float *)L.posm_cur, L.dests, L.signal,
                                                (float *)L.vel, (float *)L.acc,
                                                (const float *)L.accp, L.acc_scale, L.nslots, L.i_blk0,
                                                L.n_iblk_shard, L.acc_only, L.n_real, L.ip);

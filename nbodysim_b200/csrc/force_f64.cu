@@ -136,11 +136,11 @@ cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st)
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256)
-integrate_f64_kernel(const double *__restrict__ posm_cur, PeerDests dests,
-                     double *__restrict__ vel, double *__restrict__ acc,
-                     const double *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
-                     int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
+__device__ __forceinline__ void
+integrate_f64_one(const double *__restrict__ posm_cur, const PeerDests &dests,
+                  double *__restrict__ vel, double *__restrict__ acc,
+                  const double *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                  int n_iblk_shard, int acc_only, long long n_real, const IntegParams &ip)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x; // one body
     const int lb = gid >> 8;
@@ -168,11 +168,21 @@ integrate_f64_kernel(const double *__restrict__ posm_cur, PeerDests dests,
     vel[loff] = vx; vel[loff + BLK] = vy; vel[loff + 2 * BLK] = vz;
 }
 
+__global__ void __launch_bounds__(256)
+integrate_f64_kernel(const double *__restrict__ posm_cur, PeerDests dests, PeerSignal sig,
+                     double *__restrict__ vel, double *__restrict__ acc,
+                     const double *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                     int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
+{
+    integrate_f64_one(posm_cur, dests, vel, acc, accp, acc_scale, nslots, i_blk0, n_iblk_shard, acc_only, n_real, ip);
+    signal_peers_when_grid_done(sig);   // cross-process exchange: see integrate_f32_kernel
+}
+
 cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st)
 {
     const int threads = L.n_iblk_shard * BLK;
     integrate_f64_kernel<<<(threads + 255) / 256, 256, 0, st>>>(
-        (const double *)L.posm_cur, L.dests, (double *)L.vel, (double *)L.acc,
+        (const double *)L.posm_cur, L.dests, L.signal, (double *)L.vel, (double *)L.acc,
         (const double *)L.accp, L.acc_scale, L.nslots, L.i_blk0, L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
     return cudaGetLastError();
 }

@@ -59,6 +59,7 @@ struct IntegLaunch {
     const void *posm_cur;    // blocked, full array
     void *posm_next;         // blocked, full array
     PeerDests dests;         // where the new positions are stored (n >= 1; dests.p[0] == posm_next unless peer exchange)
+    PeerSignal signal;       // cross-process exchange: completion counters to publish (n == 0: none)
     void *vel, *acc;         // blocked, shard-local
     const void *accp;        // partial slots
     float acc_scale;         // G, or G*m when the uniform-mass force kernel summed unit masses
@@ -90,6 +91,10 @@ int force_f32_fast_grid(const ForceLaunch &L);
 
 cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st);
 cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st);
+// cross-process exchange: block the stream until every peer's counter in `flags[0..world)` (this rank's own
+// flag array) has reached `need`; after `timeout_ns` without progress *status is set to 1 and the kernel ends
+cudaError_t launch_wait_peer_flags(const unsigned long long *flags, int world, int self, unsigned long long need,
+                                   unsigned long long timeout_ns, unsigned *status, cudaStream_t st);
 
 // AoS (reference Body, 64 B) <-> blocked SoA
 cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,

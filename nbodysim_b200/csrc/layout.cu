@@ -185,4 +185,34 @@ cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, si
     return cudaGetLastError();
 }
 
+// ---- cross-process exchange: wait until every peer's pushes of the previous step have landed ----------------
+// One lane per peer polls that peer's counter in this rank's own flag array (written by the peer's integrator
+// kernel through its IPC mapping, st.release.sys) with ld.acquire.sys.  The launches that follow in the stream
+// read the pushed positions.  A peer that stops advancing must not hang the GPU: after timeout_ns the kernel
+// gives up and raises *status, which the host turns into NBODY_ESTATE at the next synchronisation.
+__global__ void wait_peer_flags_kernel(const unsigned long long *flags, int world, int self, unsigned long long need,
+                                       unsigned long long timeout_ns, unsigned *status)
+{
+    const int r = threadIdx.x;
+    if (r >= world || r == self) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(flags + r) < need) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) { atomicExch(status, 1u); return; }
+        }
+    }
+}
+
+cudaError_t launch_wait_peer_flags(const unsigned long long *flags, int world, int self, unsigned long long need,
+                                   unsigned long long timeout_ns, unsigned *status, cudaStream_t st)
+{
+    wait_peer_flags_kernel<<<1, 32, 0, st>>>(flags, world, self, need, timeout_ns, status);
+    return cudaGetLastError();
+}
+
 } // namespace nb

@@ -40,6 +40,11 @@ struct Dev {
     void *vel = nullptr, *acc = nullptr, *accp = nullptr, *aos = nullptr;
     double *energy5 = nullptr;
     ncclComm_t comm = nullptr;
+    // cross-process exchange (one process per GPU): the peers' position buffers and flag arrays, mapped by CUDA IPC
+    void *peer_posm[NBODY_MAX_GPUS][2] = {};
+    unsigned long long *peer_flags[NBODY_MAX_GPUS] = {};
+    unsigned long long *flags = nullptr;     // own flag array: flags[r] = steps of rank r whose pushes have landed here
+    unsigned *ipc_words = nullptr;           // [0] CTA arrival counter, [1] time-out status, [4..] barrier scratch
     size_t shard_start = 0, shard_count = 0; // bodies (padded index space)
     int cur = 0;
     bool gathered_pending = false;           // an allgather into posm[cur] may still be in flight
@@ -66,6 +71,8 @@ struct nbody_ctx {
     bool f64 = false;
     bool small_tile = false;     // fast kernel geometry: 512-target tiles (small shards) instead of 2048
     bool p2p = false;            // positions exchanged by peer stores from the integrator kernel (one process, ngpus > 1)
+    bool ipc = false;            // same exchange across processes: peers mapped by CUDA IPC, completion flags in peer memory
+    unsigned long long peer_timeout_ns = 120ull * 1000000000ull;
     unsigned long long step_index = 0;
     bool bh = false;             // force_algo == NBODY_FORCE_BARNES_HUT
     bool uniform = false;        // every massive body has the same mass: 11-op force kernel
@@ -230,6 +237,8 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     return NBODY_OK;
 }
 
+int ipc_barrier(nbody_ctx *ctx);
+
 int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies)
 {
     for (Dev &d : ctx->devs) {
@@ -243,6 +252,10 @@ int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies)
         // for the shard's own blocks, so seed both buffers with the full packed state)
         CU(cudaMemcpyAsync(d.posm[1], d.posm[0], ctx->n_padded * 4 * ctx->esz, cudaMemcpyDeviceToDevice, d.stream));
         d.gathered_pending = false;
+    }
+    if (ctx->ipc) {   // no peer may push into this rank's buffers before they are packed (and vice versa)
+        int rc = ipc_barrier(ctx);
+        if (rc != NBODY_OK) return rc;
     }
     for (Dev &d : ctx->devs) {
         CU(cudaSetDevice(d.device));
@@ -288,6 +301,11 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
     const int par_prev = (int)((ctx->step_index + 1) & 1);     // parity of the previous step's push events
     // remote positions of the previous step must have landed: NCCL allgather done, or every peer's push done
     auto wait_remote = [&](Dev &d) -> cudaError_t {
+        if (ctx->ipc) {
+            ctx->launches++;
+            return launch_wait_peer_flags(d.flags, ctx->world, d.rank, ctx->step_index, ctx->peer_timeout_ns,
+                                          d.ipc_words + 1, d.stream);
+        }
         if (!ctx->p2p) return cudaStreamWaitEvent(d.stream, d.ev_gathered, 0);
         for (Dev &o : ctx->devs) {
             if (&o == &d) continue;
@@ -339,6 +357,17 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             I.dests.n = 0;
             if (ctx->p2p && !acc_only) {   // integrate-and-push: new positions go to every GPU's next buffer
                 for (Dev &o : ctx->devs) I.dests.p[I.dests.n++] = o.posm[o.cur ^ 1];
+            } else if (ctx->ipc && !acc_only) {
+                // the same across processes: every rank is at the same buffer parity (SPMD), and the kernel's last
+                // CTA publishes "step_index + 1 steps pushed" into each peer's flag array
+                I.dests.p[I.dests.n++] = d.posm[d.cur ^ 1];
+                for (int r = 0; r < ctx->world; ++r) {
+                    if (r == d.rank) continue;
+                    I.dests.p[I.dests.n++] = d.peer_posm[r][d.cur ^ 1];
+                    I.signal.slot[I.signal.n++] = d.peer_flags[r] + d.rank;
+                }
+                I.signal.value = ctx->step_index + 1;
+                I.signal.arrive = d.ipc_words;
             } else {
                 I.dests.p[I.dests.n++] = d.posm[d.cur ^ 1];
             }
@@ -375,7 +404,9 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
     }
     if (acc_only) return NBODY_OK;
 
-    if (ctx->p2p) {
+    if (ctx->ipc) {
+        for (Dev &d : ctx->devs) d.gathered_pending = true;   // pushed by the integrator kernel; peers' flags gate the next step
+    } else if (ctx->p2p) {
         // the integrator kernels already stored the new positions into every peer's next buffer
         const int par = (int)(ctx->step_index & 1);
         for (Dev &d : ctx->devs) {
@@ -413,10 +444,111 @@ int sync_all(nbody_ctx *ctx)
 {
     for (Dev &d : ctx->devs) {
         CU(cudaSetDevice(d.device));
+        if (ctx->ipc && d.gathered_pending) {   // this rank's buffers are complete only once every peer's push has landed
+            CU(launch_wait_peer_flags(d.flags, ctx->world, d.rank, ctx->step_index, ctx->peer_timeout_ns,
+                                      d.ipc_words + 1, d.stream));
+            ctx->launches++;
+        }
         if (d.comm_stream) CU(cudaStreamSynchronize(d.comm_stream));
         CU(cudaStreamSynchronize(d.stream));
         d.gathered_pending = false;
+        if (ctx->ipc) {
+            unsigned status = 0;
+            CU(cudaMemcpy(&status, d.ipc_words + 1, sizeof status, cudaMemcpyDeviceToHost));
+            if (status) {
+                set_err(ctx, "peer exchange: a peer rank did not publish its positions within %.0f s", ctx->peer_timeout_ns * 1e-9);
+                return NBODY_ESTATE;
+            }
+        }
     }
+    return NBODY_OK;
+}
+
+// One process per GPU on one node: map every peer's two position buffers and flag array into this process
+// (cudaIpcGetMemHandle / cudaIpcOpenMemHandle, handles exchanged through the NCCL communicator), so that the
+// integrator kernel can store new positions straight into the peers' HBM over NVLink.  All ranks agree on
+// the outcome (sum of per-rank success flags); on failure everything is unmapped and the ncclAllGather path
+// stays in use, unless exchange == 2 demanded the peer path.
+int setup_ipc(nbody_ctx *ctx)
+{
+    struct Blob { cudaIpcMemHandle_t h[3]; int ok; int pad[15]; };
+    static_assert(sizeof(Blob) == 256, "blob layout");
+    Dev &d = ctx->devs[0];
+    const int W = ctx->world, me = d.rank;
+    CU(cudaSetDevice(d.device));
+    CU(cudaMalloc(&d.flags, NBODY_MAX_GPUS * sizeof(unsigned long long)));
+    CU(cudaMemset(d.flags, 0, NBODY_MAX_GPUS * sizeof(unsigned long long)));
+    CU(cudaMalloc(&d.ipc_words, 64));
+    CU(cudaMemset(d.ipc_words, 0, 64));
+    Blob mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = 1;
+    void *exported[3] = {d.posm[0], d.posm[1], d.flags};
+    for (int k = 0; k < 3; ++k)
+        if (cudaIpcGetMemHandle(&mine.h[k], exported[k]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    Blob *dev_blobs = nullptr;
+    CU(cudaMalloc(&dev_blobs, (size_t)W * sizeof(Blob)));
+    std::vector<Blob> blobs(W);
+    cudaError_t e = cudaMemcpyAsync(dev_blobs + me, &mine, sizeof mine, cudaMemcpyHostToDevice, d.stream);
+    int nr = 0;
+    if (e == cudaSuccess) nr = nccl().AllGather(dev_blobs + me, dev_blobs, sizeof(Blob), NCCL_UINT8, d.comm, d.stream);
+    if (e == cudaSuccess && nr == 0) e = cudaMemcpyAsync(blobs.data(), dev_blobs, (size_t)W * sizeof(Blob), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && nr == 0) e = cudaStreamSynchronize(d.stream);
+    if (nr != 0) { cudaFree(dev_blobs); NC(nr); }
+    if (e != cudaSuccess) { cudaFree(dev_blobs); CU(e); }
+
+    int ok = 1;
+    for (int r = 0; r < W; ++r) ok &= blobs[r].ok;
+    for (int r = 0; r < W && ok; ++r) {
+        if (r == me) continue;
+        void *ptr[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3 && ok; ++k)
+            if (cudaIpcOpenMemHandle(&ptr[k], blobs[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                set_err(ctx, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(cudaGetLastError()));
+                ok = 0;
+            }
+        d.peer_posm[r][0] = ptr[0];
+        d.peer_posm[r][1] = ptr[1];
+        d.peer_flags[r] = (unsigned long long *)ptr[2];
+    }
+    // consensus: every rank must have mapped every peer
+    int *dev_ok = reinterpret_cast<int *>(dev_blobs);
+    int sum = 0;
+    e = cudaMemcpyAsync(dev_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) nr = nccl().AllReduce(dev_ok, dev_ok, 1, NCCL_INT32, NCCL_SUM, d.comm, d.stream);
+    if (e == cudaSuccess && nr == 0) e = cudaMemcpyAsync(&sum, dev_ok, sizeof sum, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && nr == 0) e = cudaStreamSynchronize(d.stream);
+    cudaFree(dev_blobs);
+    if (nr != 0) NC(nr);
+    CU(e);
+    ctx->ipc = (sum == W);
+    if (!ctx->ipc) {
+        for (int r = 0; r < W; ++r) {
+            for (int k = 0; k < 2; ++k) if (d.peer_posm[r][k]) { cudaIpcCloseMemHandle(d.peer_posm[r][k]); d.peer_posm[r][k] = nullptr; }
+            if (d.peer_flags[r]) { cudaIpcCloseMemHandle(d.peer_flags[r]); d.peer_flags[r] = nullptr; }
+        }
+        cudaGetLastError();
+        if (ctx->p.exchange == 2) {
+            if (!ctx->err[0]) set_err(ctx, "peer exchange requested (exchange = 2) but a rank could not map its peers");
+            return NBODY_ECUDA;
+        }
+        ctx->err[0] = 0;
+    }
+    if (const char *t = getenv("NBODY_PEER_TIMEOUT_S")) {
+        const double sec = atof(t);
+        if (sec > 0) ctx->peer_timeout_ns = (unsigned long long)(sec * 1e9);
+    }
+    return NBODY_OK;
+}
+
+// Cross-rank barrier in stream order (a one-word allreduce): no kernel enqueued after it on any rank starts
+// before every rank has reached it.  Separates "all ranks have (re)written their buffers" from the first push.
+int ipc_barrier(nbody_ctx *ctx)
+{
+    Dev &d = ctx->devs[0];
+    CU(cudaSetDevice(d.device));
+    int *w = reinterpret_cast<int *>(d.ipc_words + 4);
+    NC(nccl().AllReduce(w, w, 1, NCCL_INT32, NCCL_SUM, d.comm, d.stream));
     return NBODY_OK;
 }
 
@@ -424,6 +556,12 @@ void free_all(nbody_ctx *c)
 {
     for (Dev &d : c->devs) {
         cudaSetDevice(d.device);
+        for (int r = 0; r < NBODY_MAX_GPUS; ++r) {
+            for (int k = 0; k < 2; ++k) if (d.peer_posm[r][k]) cudaIpcCloseMemHandle(d.peer_posm[r][k]);
+            if (d.peer_flags[r]) cudaIpcCloseMemHandle(d.peer_flags[r]);
+        }
+        if (d.flags) cudaFree(d.flags);
+        if (d.ipc_words) cudaFree(d.ipc_words);
         if (d.comm && nccl().CommDestroy) nccl().CommDestroy(d.comm);
         for (int k = 0; k < 2; ++k) if (d.posm[k]) cudaFree(d.posm[k]);
         if (d.vel) cudaFree(d.vel);
@@ -641,6 +779,9 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
             for (int k = 0; k < nlocal; ++k) ctx->devs[k].comm = comms[k];
         }
     }
+    if (multiproc && p->exchange != 1) {
+        if ((rc = setup_ipc(ctx)) != NBODY_OK) return fail(rc);
+    }
     if ((rc = upload_state(ctx, bodies)) != NBODY_OK) return fail(rc);
     *out = ctx;
     return NBODY_OK;
@@ -847,7 +988,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->world = ctx->world;
     info->rank = d0.rank;
     info->ngpus_local = (int)ctx->devs.size();
-    info->p2p_exchange = ctx->p2p ? 1 : 0;
+    info->p2p_exchange = ctx->p2p ? 1 : (ctx->ipc ? 2 : 0);
     info->sm_count = ctx->sm_count;
     info->sm_clock_khz = ctx->sm_clock_khz;
     info->j_splits = d0.plan.empty() ? 0 : d0.plan[0].splits;
@@ -922,6 +1063,9 @@ int nbody_gpu_nccl_unique_id(uint8_t id[NBODY_NCCL_ID_BYTES])
 void nbody_gpu_shutdown(nbody_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->ipc) {   // peers may still be storing into this rank's buffers: wait for them, then leave together
+        if (sync_all(ctx) == NBODY_OK) ipc_barrier(ctx);
+    }
     for (Dev &d : ctx->devs) {
         cudaSetDevice(d.device);
         if (d.comm_stream) cudaStreamSynchronize(d.comm_stream);

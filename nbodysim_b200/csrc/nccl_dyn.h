@@ -10,7 +10,7 @@ namespace nb {
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { NCCL_UINT8 = 1, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
 struct Nccl {
     void *handle = nullptr;
