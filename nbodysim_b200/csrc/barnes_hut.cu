@@ -16,7 +16,7 @@
 //   1. bounding box -> root quad                                       (Quad::new_containing)
 //   2. per body, the quadrant path by the SAME fp32 recursion -> 64-bit key, 2 bits per level,
 //      32 levels (Z-order == find_quadrant bit order, Quad.hpp:47-49)
-//   3. stable radix sort of (key, body)                                (cub::DeviceRadixSort)
+//   3. stable radix sort of (key, body)                                (radix_sort.cuh; cub::DeviceRadixSort selectable)
 //   4. cells owned by each sorted body = the path cells that first appear with it; exclusive scan
 //      -> depth-first pre-order node array WITHOUT the reference's empty leaves (they contribute +-0)
 //   5. skip pointers (`next`) by binary search on the sorted keys; first child = index + 1
@@ -423,7 +423,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
-    temp_bytes = std::max(std::max(t1, t2), radix_sort_temp_bytes(n));
+    temp_bytes = std::max(std::max(std::max(t1, t2), radix_sort_temp_bytes(n)), exclusive_scan_temp_bytes(n + 1));
     BH_ALLOC(temp, temp_bytes)
 #undef BH_ALLOC
     return cudaSuccess;
@@ -464,7 +464,9 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     bh_count_kernel<DIMS><<<g256, 256, 0, st>>>((const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first,
                                                 (unsigned char *)w.leaf, cnt + n + 1);
     tb = w.temp_bytes;
-    if ((e = cub::DeviceScan::ExclusiveSum(w.temp, tb, (const unsigned *)w.count, (unsigned *)w.offs, (int)n + 1, st)) != cudaSuccess) return e;
+    if (w.own_sort) {
+        if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.temp, st, launches)) != cudaSuccess) return e;
+    } else if ((e = cub::DeviceScan::ExclusiveSum(w.temp, tb, (const unsigned *)w.count, (unsigned *)w.offs, (int)n + 1, st)) != cudaSuccess) return e;
     // arrival counters of at most min(node_cap, 4n + 1024) cells (a tree over n bodies has < that many in practice)
     if ((e = cudaMemsetAsync(w.node_arrive, 0, (size_t)w.node_cap * 4, st)) != cudaSuccess) return e;
     bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
@@ -474,7 +476,8 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
                                                     (const unsigned char *)w.leaf, (const unsigned *)w.count, (unsigned *)w.node_arrive,
                                                     w.node_cap);
     w.count_valid = false;
-    if (launches) *launches += 7 + 3;                        // own kernels + the sort/scan passes (counted as 3)
+    if (launches) *launches += 7 + (w.own_sort ? 0 : 3);     // own kernels (+ the library's sort/scan passes, counted as 3;
+                                                             //  the hand-written sort and scan count their own launches)
     return cudaGetLastError();
 }
 

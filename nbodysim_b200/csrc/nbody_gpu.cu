@@ -227,12 +227,12 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
     if (ctx->p.collide) {
         CU(d.col.alloc(ctx->n));
-        d.col.own_sort = (ctx->p.sort_impl == 1);
+        d.col.own_sort = (ctx->p.sort_impl != 2);
     }
     if (ctx->bh) {
         CU(d.bh.alloc(ctx->n, ctx->p.dims));
         d.bh.warp_walk = ctx->p.bh_walk == 2 || (ctx->p.bh_walk == 0 && (ctx->p.dims == 3 || ctx->p.theta < 0.7f));
-        d.bh.own_sort = (ctx->p.sort_impl == 1);
+        d.bh.own_sort = (ctx->p.sort_impl != 2);
     }
     return NBODY_OK;
 }

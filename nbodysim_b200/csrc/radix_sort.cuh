@@ -1,148 +1,380 @@
 // radix_sort.cuh -- hand-written stable LSD radix sort of 64-bit keys (+ optional 32-bit values) for the
 // Barnes-Hut build (quadrant-path keys) and the collision pass (cell hashes, pair keys).
 //
-// 8 passes of 8 bits.  Per pass:
-//   1. rs_hist_kernel    each CTA owns a contiguous tile of 4096 keys, each of its 8 warps a contiguous
-//                        512-key chunk of the tile; digit counts per warp via __match_any_sync, summed per
-//                        CTA into hist[digit][cta]                                  (digit-major)
-//   2. rs_scan_kernel    one CTA: exclusive prefix sum over hist in digit-major order = the global start of
-//                        every (digit, cta) bucket
-//   3. rs_scatter_kernel re-reads the tile; rank of a key = start(digit, cta) + keys of the same digit in
-//                        earlier warps of the CTA + earlier rows of this warp + earlier lanes of this row.
-//                        Every term follows input order, so the sort is STABLE -- the Barnes-Hut merge of
-//                        coincident bodies "in body-index order" (Quadtree::insert :56-60) depends on it.
-// Ping-pong between two buffers; after the 8 passes the result is back in the FIRST buffer.
+// Single-pass-per-digit design ("onesweep": one read and one write of the data per 8-bit digit):
+//   os_hist_kernel   ONE read of the keys builds the digit histograms of all passes (shared-memory atomics,
+//                    then one global atomic per (pass, digit) and CTA).
+//   os_pass_kernel   per 8-bit digit.  A CTA takes the next tile of 4096 keys (ticket = start order, so a CTA
+//                    only ever waits for tiles that are already running), ranks its keys by digit in
+//                    registers (per-warp __match_any_sync, contiguous 512-key chunk per warp, rows in input
+//                    order => STABLE), publishes its per-digit counts, and obtains the count of every digit
+//                    in all EARLIER tiles by decoupled look-back over the tiles' status words (one thread per
+//                    digit).  Keys (and values) are then permuted into digit order in shared memory and
+//                    written out: consecutive threads write consecutive addresses within a digit's run.
+//                    A digit on which all keys agree (unused high bytes) makes the pass a plain copy.
+// HBM-/L2-bound: 12 B read + 12 B written per (key, value) pair and digit, plus 8 B per key for the histograms.
+// Stability matters: the Barnes-Hut merge of coincident bodies "in body-index order" (Quadtree::insert
+// :56-60) depends on it.  Ping-pong between two buffers; the result always ends in the FIRST buffer.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
 
 namespace nb {
 
-constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;          // 4096 keys per CTA
-constexpr int RS_CHUNK = RS_TILE / RS_WARPS;            // 512 keys per warp, contiguous
-constexpr int RS_ROWS = RS_CHUNK / 32;                  // 16 rows of 32 keys per warp
+constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32;
+// keys per thread: 16 (tile of 4096 keys, 512 contiguous keys = 16 rows of 32 per warp) for large inputs, 8 (tile
+// of 2048) while the larger tile would leave SMs without a CTA
+constexpr int RS_ROWS_LARGE = 16, RS_ROWS_SMALL = 8;
+constexpr int RS_MIN_TILE = RS_THREADS * RS_ROWS_SMALL;
+#ifndef RS_SMALL_TILE_MAX_N
+#define RS_SMALL_TILE_MAX_N (8u << 20)
+#endif
+constexpr int RS_MAX_PASSES = 8;
 
 __device__ __forceinline__ unsigned rs_digit(unsigned long long k, int shift) { return (unsigned)(k >> shift) & 255u; }
 
-// counts[w][d]: how many keys of warp w's chunk have digit d
-__device__ __forceinline__ void rs_warp_counts(const unsigned long long *__restrict__ keys, size_t n, size_t chunk0,
-                                               int shift, unsigned (*counts)[256], int w, int lane)
+// exclusive scan of one value per thread over the 256 threads of the CTA (scratch: 8 words of shared memory)
+__device__ __forceinline__ unsigned rs_block_excl_scan(unsigned v, unsigned *warp_sums, unsigned *total = nullptr)
 {
-    for (int d = lane; d < 256; d += 32) counts[w][d] = 0;
-    __syncwarp();
-    for (int r = 0; r < RS_ROWS; ++r) {
-        const size_t i = chunk0 + (size_t)r * 32 + lane;
-        const bool valid = i < n;
-        const unsigned d = valid ? rs_digit(keys[i], shift) : 256u + lane;    // invalid lanes match nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (valid && (peers & ((1u << lane) - 1u)) == 0u) counts[w][d] += __popc(peers);   // group leader
-        __syncwarp();
-    }
-}
-
-static __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const unsigned long long *__restrict__ keys, size_t n, int shift, unsigned *__restrict__ hist, unsigned nblocks)
-{
-    __shared__ unsigned counts[RS_WARPS][256];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    rs_warp_counts(keys, n, (size_t)blockIdx.x * RS_TILE + (size_t)w * RS_CHUNK, shift, counts, w, lane);
-    __syncthreads();
-    unsigned s = 0;                                      // thread d sums digit d over the warps
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned incl = v;
 #pragma unroll
-    for (int q = 0; q < RS_WARPS; ++q) s += counts[q][threadIdx.x];
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s;
-}
-
-// exclusive scan of `m` counters in place, one CTA of 1024 threads
-static __global__ void __launch_bounds__(1024) rs_scan_kernel(unsigned *__restrict__ a, size_t m)
-{
-    __shared__ unsigned part[1024];
-    const size_t per = (m + 1023) / 1024, lo = (size_t)threadIdx.x * per, hi = lo + per < m ? lo + per : m;
-    unsigned s = 0;
-    for (size_t i = lo; i < hi; ++i) s += a[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {                 // Hillis-Steele inclusive scan of the partials
-        const unsigned v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    unsigned run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
-    for (size_t i = lo; i < hi; ++i) { const unsigned v = a[i]; a[i] = run; run += v; }
-}
-
-template <bool HAS_VALS>
-static __global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, int shift,
-                  const unsigned *__restrict__ offs, unsigned nblocks, unsigned long long *__restrict__ keys_out,
-                  unsigned *__restrict__ vals_out)
-{
-    __shared__ unsigned counts[RS_WARPS][256];           // per-warp digit counts, then running bases
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t chunk0 = (size_t)blockIdx.x * RS_TILE + (size_t)w * RS_CHUNK;
-    rs_warp_counts(keys, n, chunk0, shift, counts, w, lane);
+    __syncthreads();                                      // warp_sums may still be read from a previous scan
+    if (lane == 31) warp_sums[w] = incl;
     __syncthreads();
-    {   // thread d: base of (digit d, warp q) = global start of (d, this CTA) + counts of earlier warps
-        const int d = threadIdx.x;
-        unsigned run = offs[(size_t)d * nblocks + blockIdx.x];
+    unsigned before = 0, all = 0;
 #pragma unroll
-        for (int q = 0; q < RS_WARPS; ++q) { const unsigned c = counts[q][d]; counts[q][d] = run; run += c; }
+    for (int q = 0; q < RS_WARPS; ++q) {
+        const unsigned s = warp_sums[q];
+        if (q < w) before += s;
+        all += s;
+    }
+    if (total) *total = all;
+    return before + incl - v;
+}
+
+// hist[p][d] += number of keys whose digit of pass (pass0 + p) is d
+static __global__ void __launch_bounds__(RS_THREADS)
+os_hist_kernel(const unsigned long long *__restrict__ keys, size_t n, int pass0, int npasses, unsigned *__restrict__ hist)
+{
+    __shared__ unsigned sh[RS_MAX_PASSES][256];
+    for (int p = 0; p < npasses; ++p) sh[p][threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_THREADS) {
+        const unsigned long long k = keys[i] >> (8 * pass0);
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; ++p)
+            if (p < npasses) atomicAdd(&sh[p][(unsigned)(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
-    for (int r = 0; r < RS_ROWS; ++r) {
-        const size_t i = chunk0 + (size_t)r * 32 + lane;
-        const bool valid = i < n;
-        unsigned long long k = 0;
-        unsigned d = 256u + lane;
-        if (valid) { k = keys[i]; d = rs_digit(k, shift); }
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned before = __popc(peers & ((1u << lane) - 1u));
-        unsigned base = 0;
-        if (valid) base = counts[w][d];
-        __syncwarp();
-        if (valid) {
-            const unsigned dst = base + before;
-            keys_out[dst] = k;
-            if (HAS_VALS) vals_out[dst] = vals[i];
-            if (before == 0u) counts[w][d] = base + __popc(peers);      // group leader advances the running base
+    for (int p = 0; p < npasses; ++p) {
+        const unsigned c = sh[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * 256 + threadIdx.x], c);
+    }
+}
+
+// status word of (tile, digit): [63:32] tag = 2 * (pass + 1) + is_inclusive_prefix, [31:0] count.  0 = not ready;
+// words left over from an earlier pass carry another tag and read as "not ready" too.
+__device__ __forceinline__ unsigned long long rs_pack(unsigned tag, unsigned count) { return ((unsigned long long)tag << 32) | count; }
+// status words are single 64-bit words carrying flag and value together: relaxed device-scope accesses (served by L2)
+__device__ __forceinline__ unsigned long long rs_ld_status(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rs_st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr int RS_LOOKBACK_WINDOW = 4;                     // predecessors' status words fetched at once
+
+template <bool HAS_VALS, int RS_ROWS>
+static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
+os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, int shift, unsigned pass,
+               const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, unsigned long long *status,
+               unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
+{
+    constexpr int RS_ITEMS = RS_ROWS, RS_CHUNK = 32 * RS_ROWS, RS_TILE = RS_THREADS * RS_ROWS;
+    __shared__ unsigned long long skeys[RS_TILE];        // the tile in digit order; reused for the values afterwards
+    unsigned *svals = reinterpret_cast<unsigned *>(skeys);
+    __shared__ unsigned counts[RS_WARPS][256];           // per-warp digit counts, then the warps' bases inside the digit
+    __shared__ unsigned dig_excl[256];                   // start of digit d in the tile's sorted order
+    __shared__ unsigned gbase[256];                      // output index of sorted-local index i of digit d = gbase[d] + i
+    __shared__ unsigned warp_sums[RS_WARPS];
+    __shared__ unsigned s_tile;
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int q = 0; q < RS_WARPS; ++q) counts[q][tid] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const size_t tile0 = (size_t)tile * RS_TILE;
+    const unsigned cnt = (unsigned)((n - tile0 < (size_t)RS_TILE) ? (n - tile0) : (size_t)RS_TILE);
+
+    // ---- every key has the same digit (e.g. the unused high bytes of small keys): the pass is the identity
+    if (__syncthreads_or(hist_p[tid] == (unsigned)n)) {
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            const unsigned i = (unsigned)j * RS_THREADS + tid;
+            if (i < cnt) {
+                keys_out[tile0 + i] = keys[tile0 + i];
+                if (HAS_VALS) vals_out[tile0 + i] = vals[tile0 + i];
+            }
         }
-        __syncwarp();
+        return;
+    }
+
+    // ---- load the warp's 512-key chunk row by row and rank every key among the chunk's keys of the same digit
+    unsigned long long k[RS_ROWS];
+    unsigned rank[RS_ROWS];
+    constexpr bool EARLY_VALS = HAS_VALS && RS_ROWS <= 8;   // registers permitting, fetch the values with the keys
+    unsigned v[EARLY_VALS ? RS_ROWS : 1];
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+        const unsigned i = (unsigned)w * RS_CHUNK + (unsigned)r * 32 + lane;
+        k[r] = (i < cnt) ? keys[tile0 + i] : ~0ull;
+        if (EARLY_VALS) v[r] = (i < cnt) ? vals[tile0 + i] : 0u;
+    }
+    // A group of lanes holding the same digit is ranked by ONE shared-memory atomic of its first lane (the
+    // atomics of a warp on one counter execute in program order, i.e. row order); no barrier between rows, so the
+    // matches, atomics and shuffles of all rows overlap.
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+        const unsigned i = (unsigned)w * RS_CHUNK + (unsigned)r * 32 + lane;
+        const bool valid = i < cnt;
+        const unsigned d = valid ? rs_digit(k[r], shift) : 256u + lane;       // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (valid && lane == leader) base = atomicAdd(&counts[w][d], (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[r] = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+
+    // ---- thread d: digit d's count in this tile, bases of the warps inside the digit
+    unsigned total = 0;
+#pragma unroll
+    for (int q = 0; q < RS_WARPS; ++q) { const unsigned c = counts[q][tid]; counts[q][tid] = total; total += c; }
+    const size_t sidx = (size_t)tile * 256 + tid;
+    const unsigned tag = 2u * (pass + 1u);
+    rs_st_status(status + sidx, rs_pack(tile == 0 ? tag + 1u : tag, total));                 // tile 0's aggregate IS its inclusive prefix
+
+    const unsigned dexcl = rs_block_excl_scan(total, warp_sums);               // start of digit d in the sorted tile
+    const unsigned gstart = rs_block_excl_scan(hist_p[tid], warp_sums);        // start of digit d in the whole output
+    dig_excl[tid] = dexcl;
+
+    // ---- decoupled look-back: keys of digit d in all earlier tiles
+    // The walk goes tile-1, tile-2, ... adding aggregates until it meets an inclusive prefix (tile 0 always
+    // publishes one).  Each step is an L2 round trip, so RS_LOOKBACK_WINDOW predecessors are fetched at once
+    // and consumed in order; a word that is not published yet is polled again.
+    unsigned excl = 0;
+    if (tile > 0) {
+        long long t = (long long)tile - 1;
+        bool done = false;
+        while (!done) {
+            unsigned long long v[RS_LOOKBACK_WINDOW];
+#pragma unroll
+            for (int j = 0; j < RS_LOOKBACK_WINDOW; ++j) {
+                const long long tj = t - j > 0 ? t - j : 0;
+                v[j] = rs_ld_status(status + (size_t)tj * 256 + tid);
+            }
+#pragma unroll
+            for (int j = 0; j < RS_LOOKBACK_WINDOW; ++j) {
+                if (done) break;
+                const long long tj = t - j > 0 ? t - j : 0;
+                unsigned vt = (unsigned)(v[j] >> 32);
+                while ((vt >> 1) != pass + 1u) {                               // not published yet: poll again
+                    v[j] = rs_ld_status(status + (size_t)tj * 256 + tid);
+                    vt = (unsigned)(v[j] >> 32);
+                }
+                excl += (unsigned)v[j];
+                done = (vt & 1u) != 0u;                                        // an inclusive prefix ends the walk
+            }
+            t -= RS_LOOKBACK_WINDOW;
+        }
+        rs_st_status(status + sidx, rs_pack(tag + 1u, excl + total));
+    }
+    gbase[tid] = gstart + excl - dexcl;
+    __syncthreads();
+
+    // ---- permute the keys into digit order in shared memory
+    unsigned pos[RS_ROWS];
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+        const unsigned i = (unsigned)w * RS_CHUNK + (unsigned)r * 32 + lane;
+        pos[r] = 0;
+        if (i < cnt) {
+            const unsigned d = rs_digit(k[r], shift);
+            pos[r] = dig_excl[d] + counts[w][d] + rank[r];
+            skeys[pos[r]] = k[r];
+        }
+    }
+    __syncthreads();
+
+    // ---- write out: thread i, i + 256, ... of the sorted tile; runs of one digit are contiguous in the output
+    unsigned dst[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const unsigned i = (unsigned)j * RS_THREADS + tid;
+        dst[j] = 0;
+        if (i < cnt) {
+            const unsigned long long key = skeys[i];
+            dst[j] = gbase[rs_digit(key, shift)] + i;
+            keys_out[dst[j]] = key;
+        }
+    }
+    if (HAS_VALS) {      // the same permutation for the values, through the same shared-memory buffer
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; ++r) {
+            const unsigned i = (unsigned)w * RS_CHUNK + (unsigned)r * 32 + lane;
+            if (i < cnt) svals[pos[r]] = EARLY_VALS ? v[r] : vals[tile0 + i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            const unsigned i = (unsigned)j * RS_THREADS + tid;
+            if (i < cnt) vals_out[dst[j]] = svals[i];
+        }
     }
 }
 
-inline size_t radix_sort_temp_bytes(size_t n) { return (((n + RS_TILE - 1) / RS_TILE) * 256 + 256) * sizeof(unsigned); }
+inline size_t radix_sort_temp_bytes(size_t n)
+{
+    const size_t ntiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
+    return (size_t)RS_MAX_PASSES * 256 * sizeof(unsigned) + 64 + ntiles * 256 * sizeof(unsigned long long);
+}
 
-// Stable sort of n (key, value) pairs by key.  Result ends in keys_a / vals_a (8 ping-pong passes).
-// vals_a == nullptr sorts keys only.  `temp` holds radix_sort_temp_bytes(n).  begin_bit/end_bit (multiples
-// of 8) restrict the passes when the caller knows which key bits can differ.
-inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b,
+// Stable sort of n (key, value) pairs by key.  Result ends in keys_a / vals_a.  vals_a == nullptr sorts keys only.
+// `temp` holds radix_sort_temp_bytes(n).  begin_bit/end_bit (multiples of 8) restrict the passes when the caller
+// knows which key bits can differ.  Fully asynchronous on `st` (graph-capturable).
+static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b,
                                   size_t n, void *temp, cudaStream_t st, int begin_bit = 0, int end_bit = 64, int *launches = nullptr)
 {
-    if (n == 0) return cudaSuccess;
-    const unsigned nblocks = (unsigned)((n + RS_TILE - 1) / RS_TILE);
-    unsigned *hist = (unsigned *)temp;
+    if (n == 0 || end_bit <= begin_bit) return cudaSuccess;
+    const int pass0 = begin_bit / 8, npasses = (end_bit - begin_bit + 7) / 8;
+    if (begin_bit % 8 || npasses > RS_MAX_PASSES) return cudaErrorInvalidValue;
+    const bool small = n <= (size_t)RS_SMALL_TILE_MAX_N;
+    const size_t tile = (size_t)RS_THREADS * (small ? RS_ROWS_SMALL : RS_ROWS_LARGE), ntiles = (n + tile - 1) / tile;
+    unsigned *hist = (unsigned *)temp;                                    // [npasses][256]
+    unsigned *ticket = hist + RS_MAX_PASSES * 256;                        // [npasses]
+    unsigned long long *status = (unsigned long long *)((char *)temp + (size_t)RS_MAX_PASSES * 256 * sizeof(unsigned) + 64);
+    cudaError_t e = cudaMemsetAsync(temp, 0, radix_sort_temp_bytes(n), st);
+    if (e != cudaSuccess) return e;
+    size_t hgrid = (n + 8 * RS_THREADS - 1) / (8 * RS_THREADS);             // >= 8 keys per thread, at most 8 CTAs per SM
+    if (hgrid > 148 * 8) hgrid = 148 * 8;
+    os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, pass0, npasses, hist);
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
-    int passes = 0;
-    for (int shift = begin_bit; shift < end_bit; shift += 8) {
-        rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, nblocks);
-        rs_scan_kernel<<<1, 1024, 0, st>>>(hist, (size_t)nblocks * 256);
-        if (vals_a)
-            rs_scatter_kernel<true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, shift, hist, nblocks, kout, vout);
-        else
-            rs_scatter_kernel<false><<<nblocks, RS_THREADS, 0, st>>>(kin, nullptr, n, shift, hist, nblocks, kout, nullptr);
+    for (int p = 0; p < npasses; ++p) {
+        const int shift = 8 * (pass0 + p);
+#define RS_LAUNCH(V, R)                                                                                                   \
+    os_pass_kernel<V, R><<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, vin, n, shift, (unsigned)p, hist + p * 256, ticket + p, \
+                                                                  status, kout, vout)
+        if (vals_a) { if (small) RS_LAUNCH(true, RS_ROWS_SMALL); else RS_LAUNCH(true, RS_ROWS_LARGE); }
+        else        { if (small) RS_LAUNCH(false, RS_ROWS_SMALL); else RS_LAUNCH(false, RS_ROWS_LARGE); }
+#undef RS_LAUNCH
         unsigned long long *tk = kin; kin = kout; kout = tk;
         unsigned *tv = vin; vin = vout; vout = tv;
-        ++passes;
     }
-    if (launches) *launches += 3 * passes;
-    if (passes & 1) {   // odd number of passes: bring the result back to the first buffer
-        cudaError_t e = cudaMemcpyAsync(keys_a, keys_b, n * 8, cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return e;
+    if (launches) *launches += 1 + npasses;
+    if (npasses & 1) {   // odd number of passes: bring the result back to the first buffer
+        if ((e = cudaMemcpyAsync(keys_a, keys_b, n * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
         if (vals_a && (e = cudaMemcpyAsync(vals_a, vals_b, n * 4, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
     }
+    return cudaGetLastError();
+}
+
+// ---- exclusive prefix sum of 32-bit counters, single pass (chained scan with decoupled look-back) ----------------
+// Used by the Barnes-Hut build (cells per body -> node offsets).  A CTA takes the next tile of 2048 counters (ticket
+// order), publishes the tile's sum, and warp 0 looks back over 32 predecessors at a time until it meets a tile whose
+// inclusive prefix is known.  One read and one write of the data.
+constexpr int SC_ITEMS = 8, SC_TILE = RS_THREADS * SC_ITEMS;
+
+inline size_t exclusive_scan_temp_bytes(size_t n) { return 64 + ((n + SC_TILE - 1) / SC_TILE) * sizeof(unsigned long long); }
+
+static __global__ void __launch_bounds__(RS_THREADS)
+scan_excl_kernel(const unsigned *__restrict__ in, unsigned *__restrict__ out, size_t n, unsigned *__restrict__ ticket,
+                 unsigned long long *status)
+{
+    __shared__ unsigned warp_sums[RS_WARPS];
+    __shared__ unsigned s_tile, s_excl;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const size_t i0 = (size_t)tile * SC_TILE + (size_t)tid * SC_ITEMS;
+    unsigned x[SC_ITEMS];
+    if (i0 + SC_ITEMS <= n) {                            // in and out come from cudaMalloc: 16-byte aligned rows
+        const uint4 a = *reinterpret_cast<const uint4 *>(in + i0), b = *reinterpret_cast<const uint4 *>(in + i0 + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SC_ITEMS; ++j) x[j] = (i0 + j < n) ? in[i0 + j] : 0u;
+    }
+    unsigned sum = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) sum += x[j];
+    unsigned total = 0;
+    const unsigned before = rs_block_excl_scan(sum, warp_sums, &total);
+    if (tid < 32) {                                      // warp 0: publish, look back, publish the inclusive prefix
+        if (lane == 0) rs_st_status(status + tile, rs_pack(tile == 0 ? 2u : 1u, total));
+        unsigned excl = 0;
+        long long t = (long long)tile - 1;
+        while (t >= 0) {
+            const long long tj = t - lane;
+            unsigned long long v = rs_pack(2u, 0u);       // before tile 0: an empty inclusive prefix
+            if (tj >= 0) {
+                do { v = rs_ld_status(status + tj); } while ((v >> 32) == 0ull);
+            }
+            const unsigned is_prefix = ((unsigned)(v >> 32) == 2u) ? 1u : 0u;
+            const unsigned mask = __ballot_sync(0xffffffffu, is_prefix);
+            const int first = mask ? __ffs(mask) - 1 : 31;
+            unsigned c = (lane <= first) ? (unsigned)v : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            excl += c;
+            if (mask) break;
+            t -= 32;
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (tile > 0) rs_st_status(status + tile, rs_pack(2u, excl + total));
+        }
+    }
+    __syncthreads();
+    unsigned run = s_excl + before;
+    if (i0 + SC_ITEMS <= n) {
+        uint4 a, b;
+        a.x = run; run += x[0]; a.y = run; run += x[1]; a.z = run; run += x[2]; a.w = run; run += x[3];
+        b.x = run; run += x[4]; b.y = run; run += x[5]; b.z = run; run += x[6]; b.w = run;
+        *reinterpret_cast<uint4 *>(out + i0) = a;
+        *reinterpret_cast<uint4 *>(out + i0 + 4) = b;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SC_ITEMS; ++j) {
+            if (i0 + j < n) out[i0 + j] = run;
+            run += x[j];
+        }
+    }
+}
+
+// out[i] = in[0] + ... + in[i-1] for i in [0, n).  `temp` holds exclusive_scan_temp_bytes(n).  Asynchronous on `st`.
+static inline cudaError_t exclusive_scan_u32(const unsigned *in, unsigned *out, size_t n, void *temp, cudaStream_t st, int *launches = nullptr)
+{
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(temp, 0, exclusive_scan_temp_bytes(n), st);
+    if (e != cudaSuccess) return e;
+    scan_excl_kernel<<<(unsigned)((n + SC_TILE - 1) / SC_TILE), RS_THREADS, 0, st>>>(in, out, n, (unsigned *)temp,
+                                                                                    (unsigned long long *)((char *)temp + 64));
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

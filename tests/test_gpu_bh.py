@@ -85,11 +85,13 @@ def test_bh_acc_bitexact_vs_oracle_seeded(n, seed, theta):
     assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, theta, 1.0)))
 
 
-def test_bh_hand_written_sort_bitexact():
+@pytest.mark.parametrize("sort_impl", [1, 2])
+def test_bh_sort_implementations_bitexact(sort_impl):
+    """the hand-written single-pass sort + scan (default) and cub's give the same tree"""
     b = ic.spinning_disc(50000, seed=23, scale=700.0)
     b["mass"] = np.random.default_rng(23).uniform(0.1, 3.0, 50000).astype(np.float32)
     b[100]["pos"] = b[7]["pos"]            # coincident pair: merged in index order -> needs a STABLE sort
-    with bh_sim(b, theta=1.0, eps=1.0, sort_impl=1) as s:
+    with bh_sim(b, theta=1.0, eps=1.0, sort_impl=sort_impl) as s:
         s.attract()
         out = s.download()["acc"].copy()
     assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, 1.0, 1.0)))

@@ -2,6 +2,7 @@
 // (and timing against cub::DeviceRadixSort for reference).  Exit code 0 = all cases identical.
 #include "../nbodysim_b200/csrc/radix_sort.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -31,10 +32,15 @@ static int run_case(size_t n, int mode, bool with_vals)
     CK(cudaMalloc(&tmp, radix_sort_temp_bytes(n)));
     CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0));
-    CK(radix_sort_u64(ka, kb, with_vals ? va : nullptr, vb, n, tmp, 0));
-    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    float ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up; best of the rest
+        CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
+        CK(cudaEventRecord(e0));
+        CK(radix_sort_u64(ka, kb, with_vals ? va : nullptr, vb, n, tmp, 0));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < ms) ms = t;
+    }
     std::vector<unsigned long long> ko(n); std::vector<unsigned> vo(n);
     CK(cudaMemcpy(ko.data(), ka, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(vo.data(), va, n * 4, cudaMemcpyDeviceToHost));
     int bad = 0;
@@ -44,14 +50,19 @@ static int run_case(size_t n, int mode, bool with_vals)
     // cub for the timing comparison
     float cms = 0;
     {
-        CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
         size_t tb = 0; void *ct = nullptr;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, ka, kb, va, vb, (int)n, 0, 64);
         CK(cudaMalloc(&ct, tb));
-        CK(cudaEventRecord(e0));
-        cub::DeviceRadixSort::SortPairs(ct, tb, ka, kb, va, vb, (int)n, 0, 64);
-        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-        CK(cudaEventElapsedTime(&cms, e0, e1));
+        cms = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
+            CK(cudaEventRecord(e0));
+            if (with_vals) cub::DeviceRadixSort::SortPairs(ct, tb, ka, kb, va, vb, (int)n, 0, 64);
+            else cub::DeviceRadixSort::SortKeys(ct, tb, ka, kb, (int)n, 0, 64);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            float t; CK(cudaEventElapsedTime(&t, e0, e1));
+            if (rep > 0 && t < cms) cms = t;
+        }
         cudaFree(ct);
     }
     printf("n=%9zu mode=%d vals=%d : %s   own %.3f ms   cub %.3f ms\n", n, mode, (int)with_vals, bad ? "MISMATCH" : "ok", ms, cms);
@@ -59,13 +70,58 @@ static int run_case(size_t n, int mode, bool with_vals)
     return bad;
 }
 
-int main()
+static int run_scan_case(size_t n)
+{
+    std::mt19937 rng((unsigned)n);
+    std::vector<unsigned> h(n), ref(n), got(n);
+    for (auto &x : h) x = rng() % 5;
+    unsigned run = 0;
+    for (size_t i = 0; i < n; ++i) { ref[i] = run; run += h[i]; }
+    unsigned *in, *out; void *tmp;
+    CK(cudaMalloc(&in, n * 4 + 4)); CK(cudaMalloc(&out, n * 4 + 4)); CK(cudaMalloc(&tmp, exclusive_scan_temp_bytes(n)));
+    CK(cudaMemcpy(in, h.data(), n * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        CK(exclusive_scan_u32(in, out, n, tmp, 0));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < ms) ms = t;
+    }
+    CK(cudaMemcpy(got.data(), out, n * 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (size_t i = 0; i < n && bad < 5; ++i) if (got[i] != ref[i]) { ++bad; printf("  scan mismatch at %zu: %u vs %u\n", i, got[i], ref[i]); }
+    size_t tb = 0; void *ct = nullptr; float cms = 1e30f;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n);
+    CK(cudaMalloc(&ct, tb));
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        cub::DeviceScan::ExclusiveSum(ct, tb, in, out, (int)n);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < cms) cms = t;
+    }
+    printf("scan n=%9zu : %s   own %.3f ms   cub %.3f ms\n", n, bad ? "MISMATCH" : "ok", ms, cms);
+    cudaFree(in); cudaFree(out); cudaFree(tmp); cudaFree(ct);
+    return bad;
+}
+
+int main(int argc, char **argv)
 {
     int bad = 0;
+    if (argc > 1) {   // single case: sort_check N [mode] [with_vals]
+        bad = run_case(strtoull(argv[1], nullptr, 10), argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atoi(argv[3]) != 0 : true);
+        return bad ? 1 : 0;
+    }
     for (size_t n : {1ul, 2ul, 31ul, 33ul, 511ul, 4096ul, 4097ul, 25000ul, 100003ul, 1000000ul, 4194304ul})
         for (int mode = 0; mode < 4; ++mode) bad += run_case(n, mode, true);
     bad += run_case(77777, 0, false);
     bad += run_case(1000000, 3, false);
+    bad += run_case(1000000, 0, false);
+    bad += run_case(16777216, 0, true);
+    bad += run_case(16777216, 1, true);
+    for (size_t n : {1ul, 7ul, 2047ul, 2048ul, 2049ul, 25001ul, 1000001ul, 4194305ul, 33554432ul}) bad += run_scan_case(n);
     printf(bad ? "FAILED\n" : "ALL OK\n");
     return bad ? 1 : 0;
 }
