@@ -1090,6 +1090,6 @@ const char *nbody_gpu_strerror(int code)
 
 const char *nbody_gpu_last_error(const nbody_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
 
-const char *nbody_gpu_version(void) { return "nbody_gpu 0.3 (sm_100a; all-pairs f32 fast[plain|uniform-mass]/refcompat, f64; Barnes-Hut quadtree)"; }
+const char *nbody_gpu_version(void) { return "nbody_gpu 0.4 (sm_100a; all-pairs f32 fast[plain|uniform-mass]/refcompat, f64; Barnes-Hut quadtree/octree; peer exchange)"; }
 
 } // extern "C"
