@@ -169,13 +169,14 @@ bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned 
     if ((unsigned)leafd > *max_depth) atomicMax(max_depth, (unsigned)leafd);   // racy pre-check only skips no-ops
 }
 
-// node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag
-// Two 16-byte records per node so that a visit costs two vector loads:
-//   data = (x, y, mass, size*size)          aux = (z bits [octree], next, depth | leaf << 8, 0)
+// node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag ; parent.
+// ONE 32-byte record per node, 32-byte aligned, so that a visit touches one sector (two 16-byte vector loads):
+//   data = (x, y, mass, size*size)          aux = (z bits [octree], next, depth | leaf << 8, parent)
 struct BhNodes {
-    float4 *data;
-    uint4 *aux;
+    float4 *rec;         // 2 x 16 bytes per node
     float4 *quad;        // cx, cy, size, cz (diagnostics / parity tests)
+    __device__ __forceinline__ float4 *data(unsigned c) const { return rec + 2 * (size_t)c; }
+    __device__ __forceinline__ uint4 *aux(unsigned c) const { return reinterpret_cast<uint4 *>(rec + 2 * (size_t)c + 1); }
 };
 
 // ---- 5. emit the pre-order node array -------------------------------------------------------------
@@ -205,14 +206,22 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
             const unsigned c = off + (unsigned)(d - firstd);
             if (c < cap) {
                 const bool is_leaf = (d == leafd);
-                nodes.data[c] = make_float4(is_leaf ? x : 0.f, is_leaf ? y : 0.f, is_leaf ? mass : 0.f, __fmul_rn(size, size));
+                *nodes.data(c) = make_float4(is_leaf ? x : 0.f, is_leaf ? y : 0.f, is_leaf ? mass : 0.f, __fmul_rn(size, size));
                 nodes.quad[c] = make_float4(cx, cy, size, cz);
                 // skip pointer: first sorted body after s whose depth-d prefix differs
                 unsigned nx = 0;
                 if (d > 0) {
                     const int sh = 64 - BITS * d;
                     const unsigned long long p = k >> sh;
-                    size_t lo = s + 1, hi = n;           // first j in (s, n) with (keys[j] >> sh) > p
+                    // first j in (s, n) with (keys[j] >> sh) > p.  Most cells are deep and span a handful of
+                    // bodies, so gallop away from s (1, 2, 4, ... bodies) before bisecting the last stride.
+                    size_t lo = s + 1, hi = n, step = 1;
+                    while (lo < hi) {
+                        const size_t probe = (lo + step - 1 < hi) ? lo + step - 1 : hi - 1;
+                        if ((keys[probe] >> sh) > p) { hi = probe; break; }
+                        lo = probe + 1;
+                        step <<= 1;
+                    }
                     while (lo < hi) {
                         const size_t mid = (lo + hi) >> 1;
                         if ((keys[mid] >> sh) > p) hi = mid; else lo = mid + 1;
@@ -227,7 +236,14 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                 else if (d > 1) {
                     const int shp = 64 - BITS * (d - 1);
                     const unsigned long long pp = k >> shp;
-                    size_t lo = 0, hi = s;               // first j in [0, s] with (keys[j] >> shp) >= pp
+                    // first j in [0, s] with (keys[j] >> shp) >= pp: gallop backwards from s, then bisect
+                    size_t lo = 0, hi = s, step = 1;
+                    while (lo < hi) {
+                        const size_t probe = (hi >= lo + step) ? hi - step : lo;
+                        if ((keys[probe] >> shp) < pp) { lo = probe + 1; break; }
+                        hi = probe;
+                        step <<= 1;
+                    }
                     while (lo < hi) {
                         const size_t mid = (lo + hi) >> 1;
                         if ((keys[mid] >> shp) >= pp) hi = mid; else lo = mid + 1;
@@ -235,7 +251,7 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                     par = offs[lo] + (unsigned)(d - 1 - (int)first[lo]);
                 }
                 if (par != 0xffffffffu && par < cap) atomicAdd(&arrive[par], 1u);   // low byte: number of children
-                nodes.aux[c] = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx, (unsigned)d | (is_leaf ? 256u : 0u), par);
+                *nodes.aux(c) = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx, (unsigned)d | (is_leaf ? 256u : 0u), par);
             }
         }
         if (d < leafd) {
@@ -258,13 +274,13 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
 template <int DIMS>
 __device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned c, unsigned m, unsigned level)
 {
-    const unsigned end = __ldcg(&nodes.aux[c]).y;
+    const unsigned end = __ldcg(nodes.aux(c)).y;
     float px = 0.f, py = 0.f, pz = 0.f, mass = 0.f;
     unsigned ch = c + 1;                                   // children in quadrant order
     for (unsigned i = 0; i < BhT<DIMS>::NCHILD && ch != end && ch < m; ++i) {
-        const uint4 a = __ldcg(&nodes.aux[ch]);
+        const uint4 a = __ldcg(nodes.aux(ch));
         if ((a.z & 255u) != level + 1u) break;
-        const float4 d = __ldcg(&nodes.data[ch]);
+        const float4 d = __ldcg(nodes.data(ch));
         px = __fadd_rn(px, __fmul_rn(d.x, d.z));
         py = __fadd_rn(py, __fmul_rn(d.y, d.z));
         if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(__uint_as_float(a.x), d.z));
@@ -278,10 +294,10 @@ __device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned
         py = __fmul_rn(py, inv);
         if (DIMS == 3) pz = __fmul_rn(pz, inv);
     }
-    float4 d = __ldcg(&nodes.data[c]);
+    float4 d = __ldcg(nodes.data(c));
     d.x = px; d.y = py; d.z = mass;
-    __stcg(&nodes.data[c], d);
-    if (DIMS == 3) __stcg(reinterpret_cast<float *>(&nodes.aux[c]), pz);
+    __stcg(nodes.data(c), d);
+    if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(c)), pz);
 }
 
 template <int DIMS>
@@ -295,7 +311,7 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
     const unsigned m = min(offs[n], cap);
     unsigned c = offs[s] + (unsigned)(leaf[s] - first[s]);           // this body's leaf cell
     while (c < m) {
-        const uint4 a = __ldcg(&nodes.aux[c]);
+        const uint4 a = __ldcg(nodes.aux(c));
         const unsigned par = a.w;
         if (par == 0xffffffffu || par >= m) break;                     // reached the root
         __threadfence();                                               // my cell is complete before I announce it
@@ -305,6 +321,16 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
         bh_propagate_cell<DIMS>(nodes, par, m, (a.z & 255u) - 1u);
         c = par;
     }
+}
+
+// one node record = one 256-bit load (sm_100: LDG.E.256); the array is read-only while the walk runs
+__device__ __forceinline__ void bh_load_node(const BhNodes &nodes, unsigned i, float4 &nd, uint4 &na)
+{
+    unsigned r0, r1, r2, r3;
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(na.x), "=r"(na.y), "=r"(na.z), "=r"(na.w)
+                 : "l"(nodes.rec + 2 * (size_t)i));
+    nd = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
 }
 
 __device__ __forceinline__ float bh_quake(float number)
@@ -356,8 +382,9 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
     float ax = 0.f, ay = 0.f, az = 0.f;
     unsigned i = 0;
     do {
-        const float4 nd = nodes.data[i];
-        const uint4 na = nodes.aux[i];
+        float4 nd;
+        uint4 na;
+        bh_load_node(nodes, i, nd, na);
         if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
         else i = i + 1;
     } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (reported by node_count)
@@ -387,11 +414,15 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
     const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
     float ax = 0.f, ay = 0.f, az = 0.f;
     constexpr unsigned DONE = 0xffffffffu;
+    // (Staging batches of 32 consecutive records in shared memory was tried and is SLOWER, 7.3 vs 6.2 ms at 1M
+    //  bodies: the warp-uniform loads below already hit L1, the walk is issue-bound, and a batch is rarely used up
+    //  before the walk skips past it.)
     unsigned resume = mine ? 0u : DONE;
     unsigned i = __reduce_min_sync(0xffffffffu, resume);
     while (i < cap) {                                        // DONE (and an overflowed tree) end the walk
-        const float4 nd = nodes.data[i];                     // warp-uniform loads: two 16-byte records per node
-        const uint4 na = nodes.aux[i];
+        float4 nd;                                           // warp-uniform load: one 32-byte record per node
+        uint4 na;
+        bh_load_node(nodes, i, nd, na);
         if (resume == i) {
             if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az))
                 resume = na.y ? na.y : DONE;
@@ -417,8 +448,8 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     BH_ALLOC(root, sizeof(BhRoot)) BH_ALLOC(box, 32)
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
-    BH_ALLOC(node_data, (size_t)node_cap * 16) BH_ALLOC(node_quad, (size_t)node_cap * 16)
-    BH_ALLOC(node_aux, (size_t)node_cap * 16) BH_ALLOC(node_arrive, (size_t)node_cap * 4)
+    BH_ALLOC(node_data, (size_t)node_cap * 32) BH_ALLOC(node_quad, (size_t)node_cap * 16)
+    BH_ALLOC(node_arrive, (size_t)node_cap * 4)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
@@ -431,7 +462,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_aux, node_arrive, temp};
+    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_arrive, temp};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -439,7 +470,7 @@ void BhWorkspace::release()
 static BhNodes bh_nodes(const BhWorkspace &w)
 {
     BhNodes nd;
-    nd.data = (float4 *)w.node_data; nd.aux = (uint4 *)w.node_aux; nd.quad = (float4 *)w.node_quad;
+    nd.rec = (float4 *)w.node_data; nd.quad = (float4 *)w.node_quad;
     return nd;
 }
 
@@ -533,19 +564,20 @@ cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float ep
 cudaError_t BhWorkspace::download_nodes(float *f8, unsigned *u2, size_t cap, cudaStream_t st)
 {
     const size_t m = std::min<size_t>(std::min<size_t>(cap, n_nodes), node_cap);
-    std::vector<float4> d(m), q(m);
-    std::vector<uint4> a(m);
+    std::vector<float4> rec(2 * m), q(m);
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(d.data(), node_data, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(rec.data(), node_data, m * 32, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(q.data(), node_quad, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(a.data(), node_aux, m * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     for (size_t i = 0; i < m; ++i) {
+        const float4 d = rec[2 * i];
+        uint4 a;
+        memcpy(&a, &rec[2 * i + 1], 16);
         float z;
-        memcpy(&z, &a[i].x, 4);
-        f8[8 * i + 0] = d[i].x; f8[8 * i + 1] = d[i].y; f8[8 * i + 2] = (dims == 3) ? z : 0.f; f8[8 * i + 3] = d[i].z;
+        memcpy(&z, &a.x, 4);
+        f8[8 * i + 0] = d.x; f8[8 * i + 1] = d.y; f8[8 * i + 2] = (dims == 3) ? z : 0.f; f8[8 * i + 3] = d.z;
         f8[8 * i + 4] = q[i].x; f8[8 * i + 5] = q[i].y; f8[8 * i + 6] = (dims == 3) ? q[i].w : 0.f; f8[8 * i + 7] = q[i].z;
-        u2[2 * i + 0] = a[i].y; u2[2 * i + 1] = a[i].z;
+        u2[2 * i + 0] = a.y; u2[2 * i + 1] = a.z;
     }
     return cudaSuccess;
 }
