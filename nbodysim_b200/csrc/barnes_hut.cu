@@ -346,6 +346,21 @@ template <int DIMS, bool REFCOMPAT>
 __device__ __forceinline__ bool bh_visit(const float4 nd, float ndz, bool is_leaf, float px, float py, float pz, float t_sq,
                                          float e_sq, int fix_near_leaves, float &ax, float &ay, float &az)
 {
+    if (!REFCOMPAT) {
+        // accurate-rsqrt mode has no bit-for-bit counterpart in the reference: fused multiply-adds, and a select
+        // instead of a branch around the interaction (the walk is instruction-issue-bound, profiles/)
+        const float fx = nd.x - px, fy = nd.y - py, fz = (DIMS == 3) ? ndz - pz : 0.f;
+        float r_sq = fmaf(fx, fx, fy * fy);
+        if (DIMS == 3) r_sq = fmaf(fz, fz, r_sq);
+        const bool far_ = nd.w < r_sq * t_sq;
+        if (!(far_ || is_leaf)) return false;
+        const float inv = rsqrt_approx(r_sq + e_sq);
+        const float s3 = ((far_ || fix_near_leaves) && r_sq > 0.f) ? nd.z * inv * inv * inv : 0.f;
+        ax = fmaf(fx, s3, ax);
+        ay = fmaf(fy, s3, ay);
+        if (DIMS == 3) az = fmaf(fz, s3, az);
+        return true;
+    }
     const float dx = __fsub_rn(nd.x, px), dy = __fsub_rn(nd.y, py), dz = (DIMS == 3) ? __fsub_rn(ndz, pz) : 0.f;
     float d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
     if (DIMS == 3) d_sq = __fadd_rn(d_sq, __fmul_rn(dz, dz));
@@ -404,7 +419,7 @@ template <int DIMS, bool REFCOMPAT>
 __global__ void __launch_bounds__(128)
 bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                     float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-                    float *__restrict__ accp, unsigned cap)
+                    float *__restrict__ accp, unsigned cap, unsigned window)
 {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = s < n;
@@ -417,17 +432,20 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
     // (Staging batches of 32 consecutive records in shared memory was tried and is SLOWER, 7.3 vs 6.2 ms at 1M
     //  bodies: the warp-uniform loads below already hit L1, the walk is issue-bound, and a batch is rarely used up
     //  before the walk skips past it.)
+    // `window`: a lane takes its next node whenever that node lies fewer than `window` records ahead of the
+    // slowest lane, so one step's loads fall into `window` consecutive 32-byte records (window = 1: every active
+    // lane reads the same record).  Lanes that accepted a cell keep going while a neighbour descends into it.
     unsigned resume = mine ? 0u : DONE;
     unsigned i = __reduce_min_sync(0xffffffffu, resume);
     while (i < cap) {                                        // DONE (and an overflowed tree) end the walk
-        float4 nd;                                           // warp-uniform load: one 32-byte record per node
-        uint4 na;
-        bh_load_node(nodes, i, nd, na);
-        if (resume == i) {
+        if (resume - i < window) {                           // unsigned: false for DONE
+            float4 nd;
+            uint4 na;
+            bh_load_node(nodes, resume, nd, na);
             if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az))
                 resume = na.y ? na.y : DONE;
             else
-                resume = i + 1;
+                resume = resume + 1;
         }
         i = __reduce_min_sync(0xffffffffu, resume);
     }
@@ -543,8 +561,8 @@ static void bh_walk_t(const BhWorkspace &w, const float *posm, size_t n, float t
     const unsigned *idx = (const unsigned *)w.idx;
     const BhNodes nd = bh_nodes(w);
     if (w.warp_walk) {
-        if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap);
-        else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap);
+        if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window);
+        else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window);
     } else {
         if (refcompat) bh_walk_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap);
         else bh_walk_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap);

@@ -123,6 +123,8 @@ struct BhWorkspace {
     size_t temp_bytes = 0;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
+    unsigned walk_window = 256;  // warp-cooperative walk: how many records ahead of the slowest lane a lane may run
+                                 // (sweep on B200, tools/bh_window_sweep.py: 256 is best or within 1 % of best everywhere)
     bool own_sort = false;       // hand-written radix sort (radix_sort.cuh) instead of cub::DeviceRadixSort
     cudaError_t alloc(size_t n, int dims);
     cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);

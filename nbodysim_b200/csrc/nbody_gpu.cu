@@ -233,6 +233,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
         CU(d.bh.alloc(ctx->n, ctx->p.dims));
         d.bh.warp_walk = ctx->p.bh_walk == 2 || (ctx->p.bh_walk == 0 && (ctx->p.dims == 3 || ctx->p.theta < 0.7f));
         d.bh.own_sort = (ctx->p.sort_impl != 2);
+        if (const char *ww = getenv("NBODY_BH_WALK_WINDOW")) d.bh.walk_window = (unsigned)std::max(1, atoi(ww));   // tuning override
     }
     return NBODY_OK;
 }
