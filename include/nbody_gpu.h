@@ -76,8 +76,7 @@ typedef struct nbody_params {
     int32_t  fuse_integrator; /* -1 = auto; 0 = separate integrator kernel; 1 (with j_splits = 1) = kick-drift fused
                                  into the force kernel's epilogue (2048-target tiles) */
     int32_t  use_graph;       /* -1 = auto (launch-bound sizes: n <= 32768, Barnes-Hut n <= 262144), 0 = never, 1 = always:
-                                 replay pairs of steps from a CUDA graph in nbody_gpu_step calls of >= 8 steps (one GPU,
-                                 no collision pass) */
+                                 replay pairs of steps from a CUDA graph in nbody_gpu_step calls of >= 8 steps (one GPU) */
     int32_t  force_variant;   /* fast fp32 kernel: -1 = auto, 0 = always the general-mass form (12 fp32
                                  lane-ops per interaction).  auto uses the uniform-mass form (11 lane-ops;
                                  m factored out of the sum, same per-pair arithmetic otherwise) when

@@ -78,9 +78,10 @@ __global__ void __launch_bounds__(256)
 col_pairs_kernel(const float *__restrict__ posm, const float *__restrict__ vel,
                  const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals,
                  const unsigned *__restrict__ counters_in, unsigned char *__restrict__ hot, int pass,
-                 unsigned long long *__restrict__ pairs, unsigned pair_cap, unsigned *__restrict__ counters)
+                 unsigned long long *__restrict__ pairs, unsigned pair_cap, unsigned *__restrict__ counters, int idx_bits)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counters_in[2]) return;                            // overflow: the pass is abandoned (nbody_gpu_collide_stats reports it)
     const unsigned ne = counters_in[0];
     if (e >= ne) return;
     const unsigned long long key = keys[e];
@@ -98,7 +99,7 @@ col_pairs_kernel(const float *__restrict__ posm, const float *__restrict__ vel,
             if (overlap) { hot[ia] = 1; hot[ib] = 1; }
         } else if (overlap || hot[ia] || hot[ib]) {
             const unsigned p = atomicAdd(&counters[1], 1u);
-            if (p < pair_cap) pairs[p] = ((unsigned long long)first << 32) | second;
+            if (p < pair_cap) pairs[p] = ((unsigned long long)first << idx_bits) | second;   // sorts as (first, second)
             else atomicExch(&counters[2], 1u);
         }
     }
@@ -147,12 +148,14 @@ __device__ void col_resolve(float *posm, float *vel, unsigned i, unsigned j, uns
 }
 
 __global__ void col_resolve_kernel(float *posm, float *vel, const unsigned long long *__restrict__ pairs,
-                                   unsigned pair_cap, unsigned *counters)
+                                   unsigned pair_cap, unsigned *counters, int idx_bits)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (counters[2]) { counters[3] = 0; return; }
     const unsigned np = min(counters[1], pair_cap);
     unsigned resolved = 0;
-    for (unsigned p = 0; p < np; ++p) col_resolve(posm, vel, (unsigned)(pairs[p] >> 32), (unsigned)pairs[p], &resolved);
+    for (unsigned p = 0; p < np; ++p)
+        col_resolve(posm, vel, (unsigned)(pairs[p] >> idx_bits), (unsigned)(pairs[p] & ((1ull << idx_bits) - 1ull)), &resolved);
     counters[3] = resolved;
 }
 
@@ -184,47 +187,58 @@ void CollideWorkspace::release()
     *this = CollideWorkspace();
 }
 
-// One collision pass over the first n bodies, in place on posm / vel.  Reads two counters back (cell
-// entries, candidate pairs) so that the sorts cover only live items and an empty candidate list -- the
-// common case -- costs nothing further.
+// One collision pass over the first n bodies, in place on posm / vel.  Fully asynchronous: the numbers of cell
+// entries and candidate pairs stay on the device -- the grids are sized for the buffers' capacities, the kernels
+// and sorts read the live counts (CTAs beyond them exit at once) -- so the pass neither stalls the stream for a
+// read-back nor prevents a whole Simulation::step() from being captured in a CUDA graph.
 cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches)
 {
     if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
     cudaError_t e;
     unsigned *cnt = (unsigned *)counters;
-    unsigned h[4] = {0, 0, 0, 0};
     if ((e = cudaMemsetAsync(cnt, 0, 16, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(hot, 0, n, st)) != cudaSuccess) return e;
     const unsigned gn = (unsigned)((n + 255) / 256);
     col_entries_kernel<<<gn, 256, 0, st>>>(posm, vel, (unsigned)n, (unsigned long long *)keys_in, (unsigned *)vals_in, entry_cap, cnt);
     if (launches) *launches += 1;
-    if ((e = stats(st, h)) != cudaSuccess) return e;
-    if (h[2] || h[0] == 0) return cudaSuccess;                  // overflow is reported by nbody_gpu_collide_stats
-    const unsigned ne = h[0], ge = (ne + 255) / 256;
+    // Only the GROUPING of equal cell hashes matters to the pair discovery (pairs are put in canonical order by the
+    // second sort), and the hashes are sign-extended 32-bit values: sorting their low 32 bits groups them.
+    // A pair key packs (first, second) into 2 x idx_bits bits, so small scenes need 4 digit passes instead of 8.
+    int idx_bits = 1;
+    while (((size_t)1 << idx_bits) < n) ++idx_bits;
+    const int pair_bits = std::min(64, ((2 * idx_bits + 7) / 8) * 8);
     size_t tb = temp_bytes;
     if (own_sort) {
         if ((e = radix_sort_u64((unsigned long long *)keys_in, (unsigned long long *)keys, (unsigned *)vals_in, (unsigned *)vals,
-                                ne, temp, st, 0, 64, launches)) != cudaSuccess) return e;
+                                entry_cap, temp, st, 0, 32, launches, cnt + 0)) != cudaSuccess) return e;
         std::swap(keys_in, keys);
         std::swap(vals_in, vals);
-    } else if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
-                                                    (const unsigned *)vals_in, (unsigned *)vals, (int)ne, 0, 64, st)) != cudaSuccess) return e;
+    } else {   // library comparison path: needs the count on the host
+        unsigned h[4];
+        if ((e = stats(st, h)) != cudaSuccess) return e;
+        if (h[2] || h[0] == 0) return cudaSuccess;
+        if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long *)keys_in, (unsigned long long *)keys,
+                                                 (const unsigned *)vals_in, (unsigned *)vals, (int)h[0], 0, 64, st)) != cudaSuccess) return e;
+    }
+    const unsigned ge = (entry_cap + 255) / 256;
     for (int pass = 0; pass < 2; ++pass)
         col_pairs_kernel<<<ge, 256, 0, st>>>(posm, vel, (const unsigned long long *)keys, (const unsigned *)vals, cnt,
-                                             (unsigned char *)hot, pass, (unsigned long long *)pairs_in, pair_cap, cnt);
-    if (launches) *launches += 2 + 1;
-    if ((e = stats(st, h)) != cudaSuccess) return e;
-    if (h[2] || h[1] == 0) return cudaSuccess;
-    const unsigned np = std::min(h[1], pair_cap);
+                                             (unsigned char *)hot, pass, (unsigned long long *)pairs_in, pair_cap, cnt, idx_bits);
+    if (launches) *launches += 2;
     tb = temp_bytes;
     if (own_sort) {
-        if ((e = radix_sort_u64((unsigned long long *)pairs_in, (unsigned long long *)pairs, nullptr, nullptr, np, temp, st,
-                                0, 64, launches)) != cudaSuccess) return e;
+        if ((e = radix_sort_u64((unsigned long long *)pairs_in, (unsigned long long *)pairs, nullptr, nullptr, pair_cap, temp, st,
+                                0, pair_bits, launches, cnt + 1)) != cudaSuccess) return e;
         std::swap(pairs_in, pairs);
-    } else if ((e = cub::DeviceRadixSort::SortKeys(temp, tb, (const unsigned long long *)pairs_in, (unsigned long long *)pairs,
-                                                   (int)np, 0, 64, st)) != cudaSuccess) return e;
-    col_resolve_kernel<<<1, 32, 0, st>>>(posm, vel, (const unsigned long long *)pairs, pair_cap, cnt);
-    if (launches) *launches += 1 + 1;
+    } else {
+        unsigned h[4];
+        if ((e = stats(st, h)) != cudaSuccess) return e;
+        if (h[2] || h[1] == 0) return cudaSuccess;
+        if ((e = cub::DeviceRadixSort::SortKeys(temp, tb, (const unsigned long long *)pairs_in, (unsigned long long *)pairs,
+                                                (int)std::min(h[1], pair_cap), 0, 64, st)) != cudaSuccess) return e;
+    }
+    col_resolve_kernel<<<1, 32, 0, st>>>(posm, vel, (const unsigned long long *)pairs, pair_cap, cnt, idx_bits);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

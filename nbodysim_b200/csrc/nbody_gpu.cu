@@ -826,9 +826,11 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
 {
     if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
     // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
-    // (the Barnes-Hut build is fully asynchronous -- sort, scan and the COM pass included -- so it
-    //  captures too; the collision pass reads counters back and does not)
-    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->p.collide && !ctx->profile_next && nsteps >= 8;
+    // (the Barnes-Hut build and the collision pass are fully asynchronous -- sorts, scan, COM pass, pair
+    //  discovery and resolve keep their counters on the device -- so they capture too; only the library-sort
+    //  comparison path of the collision pass reads counters back)
+    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !(ctx->p.collide && ctx->p.sort_impl == 2) &&
+                          !ctx->profile_next && nsteps >= 8;
     const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && (ctx->n_padded <= 32768 || (ctx->bh && ctx->n_padded <= 262144)));
     if (graph_ok && want) {
         int rc = step_with_graph(ctx, dt, nsteps);

@@ -59,8 +59,10 @@ __device__ __forceinline__ unsigned rs_block_excl_scan(unsigned v, unsigned *war
 
 // hist[p][d] += number of keys whose digit of pass (pass0 + p) is d
 static __global__ void __launch_bounds__(RS_THREADS)
-os_hist_kernel(const unsigned long long *__restrict__ keys, size_t n, int pass0, int npasses, unsigned *__restrict__ hist)
+os_hist_kernel(const unsigned long long *__restrict__ keys, size_t n, const unsigned *__restrict__ n_dev, int pass0, int npasses,
+               unsigned *__restrict__ hist)
 {
+    if (n_dev) n = (*n_dev < n) ? *n_dev : n;             // live item count kept on the device (n is its bound)
     __shared__ unsigned sh[RS_MAX_PASSES][256];
     for (int p = 0; p < npasses; ++p) sh[p][threadIdx.x] = 0;
     __syncthreads();
@@ -95,7 +97,8 @@ constexpr int RS_LOOKBACK_WINDOW = 4;                     // predecessors' statu
 
 template <bool HAS_VALS, int RS_ROWS>
 static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
-os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, int shift, unsigned pass,
+os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, const unsigned *__restrict__ n_dev,
+               int shift, unsigned pass,
                const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, unsigned long long *status,
                unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
 {
@@ -109,12 +112,14 @@ os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__re
     __shared__ unsigned s_tile;
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (n_dev) n = (*n_dev < n) ? *n_dev : n;             // live item count kept on the device (n is its bound)
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int q = 0; q < RS_WARPS; ++q) counts[q][tid] = 0;
     __syncthreads();
     const unsigned tile = s_tile;
     const size_t tile0 = (size_t)tile * RS_TILE;
+    if (tile0 >= n) return;                               // grid sized for the bound: nothing left for this CTA
     const unsigned cnt = (unsigned)((n - tile0 < (size_t)RS_TILE) ? (n - tile0) : (size_t)RS_TILE);
 
     // ---- every key has the same digit (e.g. the unused high bytes of small keys): the pass is the identity
@@ -254,9 +259,12 @@ inline size_t radix_sort_temp_bytes(size_t n)
 
 // Stable sort of n (key, value) pairs by key.  Result ends in keys_a / vals_a.  vals_a == nullptr sorts keys only.
 // `temp` holds radix_sort_temp_bytes(n).  begin_bit/end_bit (multiples of 8) restrict the passes when the caller
-// knows which key bits can differ.  Fully asynchronous on `st` (graph-capturable).
+// knows which key bits can differ.  With `n_dev` the number of live items is read from device memory by the kernels
+// (n is then only the bound the grids are sized for), so a producer's counter never has to travel to the host.
+// Fully asynchronous on `st` (graph-capturable).
 static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b,
-                                  size_t n, void *temp, cudaStream_t st, int begin_bit = 0, int end_bit = 64, int *launches = nullptr)
+                                  size_t n, void *temp, cudaStream_t st, int begin_bit = 0, int end_bit = 64, int *launches = nullptr,
+                                  const unsigned *n_dev = nullptr)
 {
     if (n == 0 || end_bit <= begin_bit) return cudaSuccess;
     const int pass0 = begin_bit / 8, npasses = (end_bit - begin_bit + 7) / 8;
@@ -270,13 +278,13 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
     if (e != cudaSuccess) return e;
     size_t hgrid = (n + 8 * RS_THREADS - 1) / (8 * RS_THREADS);             // >= 8 keys per thread, at most 8 CTAs per SM
     if (hgrid > 148 * 8) hgrid = 148 * 8;
-    os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, pass0, npasses, hist);
+    os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, n_dev, pass0, npasses, hist);
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
     for (int p = 0; p < npasses; ++p) {
         const int shift = 8 * (pass0 + p);
 #define RS_LAUNCH(V, R)                                                                                                   \
-    os_pass_kernel<V, R><<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, vin, n, shift, (unsigned)p, hist + p * 256, ticket + p, \
+    os_pass_kernel<V, R><<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, vin, n, n_dev, shift, (unsigned)p, hist + p * 256, ticket + p, \
                                                                   status, kout, vout)
         if (vals_a) { if (small) RS_LAUNCH(true, RS_ROWS_SMALL); else RS_LAUNCH(true, RS_ROWS_LARGE); }
         else        { if (small) RS_LAUNCH(false, RS_ROWS_SMALL); else RS_LAUNCH(false, RS_ROWS_LARGE); }

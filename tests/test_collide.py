@@ -114,6 +114,25 @@ def test_gpu_full_reference_step_bitexact_vs_golden(sort_impl):
 
 
 @pytest.mark.gpu
+def test_gpu_full_step_with_collisions_graph_replay_is_bit_identical():
+    """the collision pass keeps its counters on the device, so whole steps (BH + integrate + collide) replay from a
+    CUDA graph: 24 steps of a collision-dense scene, graph replay against plain launches"""
+    b = scene(3000, 1500, 25, 4)
+    b["vel"] = np.random.default_rng(5).normal(0.0, 30.0, (3000, 2)).astype(np.float32)
+    outs = []
+    for use_graph in (0, 1):
+        with Simulation(b, dt=0.01, dims=2, theta=1.0, eps=1.0, collide=1, use_graph=use_graph,
+                        force_algo=capi.FORCE_BARNES_HUT, rsqrt_mode=capi.RSQRT_REFCOMPAT,
+                        integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
+            s.step(24)
+            outs.append(s.bodies.copy())
+            assert s.info()["graph"] == use_graph
+            assert s.collide_stats()[0] > 0
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(outs[0][f]), bits(outs[1][f])), f
+
+
+@pytest.mark.gpu
 def test_gpu_collide_inert_for_zero_radii_and_rejected_in_3d():
     import ctypes as C
     from nbodysim_b200 import ic
