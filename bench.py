@@ -160,7 +160,10 @@ def cpu_reference_rate(n, seconds, bodies=None):
 
     m0 = max(cores, 64)
     t0 = run(m0)                                      # calibration (also warms caches / threads)
-    m = int(min(max(m0, m0 * seconds / max(t0, 1e-6)), 65536, n))
+    m1 = int(min(max(m0, m0 * 1.5 / max(t0, 1e-6)), 65536, n))   # second stage: ~1.5 s, thread start-up amortised
+    m1 = max(cores, (m1 // cores) * cores)
+    t1 = run(m1)
+    m = int(min(max(m0, m1 * seconds / max(t1, 1e-6)), 65536, n))
     m = max(cores, (m // cores) * cores)
     return {"m": m, "n": n, "run": run, "kind": kind, "cores": cores,
             "threads_used": cores if R is not None else min(cores, int(os.environ.get("OMP_NUM_THREADS", cores)))}
