@@ -30,7 +30,7 @@ static void usage(const char *a0)
             "usage: %s [--n N] [--steps K] [--dt DT] [--eps E] [--ic plummer|sphere|galaxy|disc|reference]\n"
             "          [--seed S] [--dims 2|3] [--gpus G] [--precision f32|f64]\n"
             "          [--rsqrt fast|refcompat] [--clamp on|off] [--boundary on|off]\n"
-            "          [--algo allpairs|bh] [--theta T] [--collide on|off] [--exchange auto|nccl]\n"
+            "          [--algo allpairs|bh] [--theta T] [--near-leaves on|off] [--collide on|off] [--exchange auto|nccl]\n"
             "          [--energy-every M] [--in snapshot] [--out snapshot] [--splits S]\n",
             a0);
 }
@@ -67,6 +67,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--boundary")) { NEED(); o_boundary = !strcmp(v, "on"); }
         else if (!strcmp(a, "--algo")) { NEED(); o_algo = !strcmp(v, "bh"); }
         else if (!strcmp(a, "--theta")) { NEED(); p.theta = (float)atof(v); }
+        else if (!strcmp(a, "--near-leaves")) { NEED(); p.bh_fix_near_leaves = !strcmp(v, "on"); }
         else if (!strcmp(a, "--collide")) { NEED(); o_collide = !strcmp(v, "on"); }
         else if (!strcmp(a, "--exchange")) { NEED(); p.exchange = !strcmp(v, "nccl") ? 1 : 0; }
         else if (!strcmp(a, "--energy-every")) { NEED(); energy_every = atoi(v); }
