@@ -11,6 +11,11 @@
  * copy where the reference copies `simulation->bodies` for the renderer (main.cpp:623-627) with
  * `nbody_gpu_download`.  INTEGRATION.md shows the exact patch.
  *
+ * Environment variables read at nbody_gpu_init (tuning / safety, never required):
+ *   NBODY_PEER_TIMEOUT_S   seconds a rank waits for a peer's positions in the cross-process exchange before the
+ *                          context fails with NBODY_ESTATE instead of spinning for ever (default 120)
+ *   NBODY_BH_WALK_WINDOW   lane window of the warp-cooperative Barnes-Hut walk (default 256; 1 = lock-step lanes)
+ *
  * Plain C: pointers and sizes only, no C++/torch types.  All functions return 0 on success or a
  * negative NBODY_E* code; they never throw, never call exit().  A context is used by one host
  * thread at a time (the reference drives step() from a single simulation thread, main.cpp:612-635).
