@@ -171,10 +171,11 @@ bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned 
 
 // node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag ; parent.
 // ONE 32-byte record per node, 32-byte aligned, so that a visit touches one sector (two 16-byte vector loads):
-//   data = (x, y, mass, size*size)          aux = (z bits [octree], next, depth | leaf << 8, parent)
+//   data = (x, y, mass, size*size)          aux = (z bits [octree], next, depth | leaf << 8 | quadrant << 9, parent)
 struct BhNodes {
     float4 *rec;         // 2 x 16 bytes per node
     float4 *quad;        // cx, cy, size, cz (diagnostics / parity tests)
+    float4 *slots;       // COM pass: (x, y, z, mass) of each completed child, [parent][quadrant]
     __device__ __forceinline__ float4 *data(unsigned c) const { return rec + 2 * (size_t)c; }
     __device__ __forceinline__ uint4 *aux(unsigned c) const { return reinterpret_cast<uint4 *>(rec + 2 * (size_t)c + 1); }
 };
@@ -250,8 +251,12 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                     }
                     par = offs[lo] + (unsigned)(d - 1 - (int)first[lo]);
                 }
-                if (par != 0xffffffffu && par < cap) atomicAdd(&arrive[par], 1u);   // low byte: number of children
-                *nodes.aux(c) = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx, (unsigned)d | (is_leaf ? 256u : 0u), par);
+                // quadrant of this cell inside its parent = the key bits of level d
+                const unsigned qd = (d > 0) ? ((unsigned)(k >> (64 - BITS * d)) & (BhT<DIMS>::NCHILD - 1u)) : 0u;
+                // arrive[parent]: low byte = number of children, bits 16.. = which quadrants are occupied
+                if (par != 0xffffffffu && par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + qd)));
+                *nodes.aux(c) = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? z : 0.f), nx,
+                                           (unsigned)d | (is_leaf ? 256u : 0u) | (qd << 9), par);
             }
         }
         if (d < leafd) {
@@ -266,59 +271,64 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
 }
 
 // ---- 6. centres of mass (Quadtree::propagate, :236-258) -------------------------------------------------
-// One launch, no level barriers: the thread of every leaf climbs towards the root; at each cell it adds one
-// arrival (high bits of arrive[], the low byte holds the number of children counted by the emit kernel) and
-// stops unless it is the LAST child to arrive, in which case all children are complete and it sums them in
-// quadrant order -- `pos += child.pos * child.mass; mass += child.mass`, then `pos *= 1/mass` -- exactly the
-// reference's arithmetic and order.  Children written by other SMs are read with L1-bypassing loads.
-template <int DIMS>
-__device__ __forceinline__ void bh_propagate_cell(const BhNodes &nodes, unsigned c, unsigned m, unsigned level)
-{
-    const unsigned end = __ldcg(nodes.aux(c)).y;
-    float px = 0.f, py = 0.f, pz = 0.f, mass = 0.f;
-    unsigned ch = c + 1;                                   // children in quadrant order
-    for (unsigned i = 0; i < BhT<DIMS>::NCHILD && ch != end && ch < m; ++i) {
-        const uint4 a = __ldcg(nodes.aux(ch));
-        if ((a.z & 255u) != level + 1u) break;
-        const float4 d = __ldcg(nodes.data(ch));
-        px = __fadd_rn(px, __fmul_rn(d.x, d.z));
-        py = __fadd_rn(py, __fmul_rn(d.y, d.z));
-        if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(__uint_as_float(a.x), d.z));
-        mass = __fadd_rn(mass, d.z);
-        if (a.y == 0) break;
-        ch = a.y;
-    }
-    if (mass > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
-        const float inv = __fdiv_rn(1.0f, mass);
-        px = __fmul_rn(px, inv);
-        py = __fmul_rn(py, inv);
-        if (DIMS == 3) pz = __fmul_rn(pz, inv);
-    }
-    float4 d = __ldcg(nodes.data(c));
-    d.x = px; d.y = py; d.z = mass;
-    __stcg(nodes.data(c), d);
-    if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(c)), pz);
-}
-
+// One launch, no level barriers: the thread of every leaf climbs towards the root.  A completed node deposits
+// (position, mass) into its parent's slot for its quadrant, then adds one arrival to the parent (bits 8..15 of
+// arrive[]; the low byte holds the number of children and bits 16.. the occupied quadrants, both counted by the
+// emit kernel) and stops unless it is the LAST child to arrive.  The last arriver reads the occupied slots --
+// independent loads of one contiguous line, no sibling chasing -- and sums them in quadrant order:
+// `pos += child.pos * child.mass; mass += child.mass`, then `pos *= 1/mass` -- exactly the reference's arithmetic
+// and order (its empty leaves only ever add +0).  Slots written by other SMs are read with L1-bypassing loads.
 template <int DIMS>
 __global__ void __launch_bounds__(256)
 bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned char *__restrict__ first,
                     const unsigned char *__restrict__ leaf, const unsigned *__restrict__ count, unsigned *__restrict__ arrive,
                     unsigned cap)
 {
+    constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n || count[s] == 0) return;
     const unsigned m = min(offs[n], cap);
-    unsigned c = offs[s] + (unsigned)(leaf[s] - first[s]);           // this body's leaf cell
-    while (c < m) {
-        const uint4 a = __ldcg(nodes.aux(c));
+    unsigned c = offs[s] + (unsigned)(leaf[s] - first[s]);           // this body's leaf cell (emitted by the previous launch)
+    if (c >= m) return;
+    uint4 a = __ldcg(nodes.aux(c));
+    const float4 d0 = __ldcg(nodes.data(c));
+    float x = d0.x, y = d0.y, z = (DIMS == 3) ? __uint_as_float(a.x) : 0.f, mass = d0.z;
+    for (;;) {
         const unsigned par = a.w;
         if (par == 0xffffffffu || par >= m) break;                     // reached the root
-        __threadfence();                                               // my cell is complete before I announce it
+        const unsigned q = (a.z >> 9) & (NCHILD - 1u);
+        __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, z, mass));
+        __threadfence();                                               // my deposit is visible before I announce it
         const unsigned old = atomicAdd(&arrive[par], 0x100u);
-        if ((old >> 8) + 1u != (old & 0xffu)) break;                   // a sibling will arrive later and do the work
+        if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;         // a sibling will arrive later and do the work
         __threadfence();
-        bh_propagate_cell<DIMS>(nodes, par, m, (a.z & 255u) - 1u);
+        const unsigned mask = (old >> 16) & 0xffu;
+        float4 ch[NCHILD];
+#pragma unroll
+        for (unsigned k = 0; k < NCHILD; ++k)
+            ch[k] = ((mask >> k) & 1u) ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+#pragma unroll
+        for (unsigned k = 0; k < NCHILD; ++k) {
+            if ((mask >> k) & 1u) {                                    // children in quadrant order
+                px = __fadd_rn(px, __fmul_rn(ch[k].x, ch[k].w));
+                py = __fadd_rn(py, __fmul_rn(ch[k].y, ch[k].w));
+                if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch[k].z, ch[k].w));
+                ms = __fadd_rn(ms, ch[k].w);
+            }
+        }
+        if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
+            const float inv = __fdiv_rn(1.0f, ms);
+            px = __fmul_rn(px, inv);
+            py = __fmul_rn(py, inv);
+            if (DIMS == 3) pz = __fmul_rn(pz, inv);
+        }
+        a = __ldcg(nodes.aux(par));
+        float4 dp = __ldcg(nodes.data(par));
+        dp.x = px; dp.y = py; dp.z = ms;
+        __stcg(nodes.data(par), dp);
+        if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(par)), pz);
+        x = px; y = py; z = pz; mass = ms;
         c = par;
     }
 }
@@ -468,6 +478,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
     BH_ALLOC(node_data, (size_t)node_cap * 32) BH_ALLOC(node_quad, (size_t)node_cap * 16)
     BH_ALLOC(node_arrive, (size_t)node_cap * 4)
+    BH_ALLOC(node_slots, (size_t)node_cap * (dims == 3 ? 8 : 4) * 16)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
@@ -480,7 +491,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_arrive, temp};
+    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_arrive, node_slots, temp};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -488,7 +499,7 @@ void BhWorkspace::release()
 static BhNodes bh_nodes(const BhWorkspace &w)
 {
     BhNodes nd;
-    nd.rec = (float4 *)w.node_data; nd.quad = (float4 *)w.node_quad;
+    nd.rec = (float4 *)w.node_data; nd.quad = (float4 *)w.node_quad; nd.slots = (float4 *)w.node_slots;
     return nd;
 }
 
@@ -595,7 +606,7 @@ cudaError_t BhWorkspace::download_nodes(float *f8, unsigned *u2, size_t cap, cud
         memcpy(&z, &a.x, 4);
         f8[8 * i + 0] = d.x; f8[8 * i + 1] = d.y; f8[8 * i + 2] = (dims == 3) ? z : 0.f; f8[8 * i + 3] = d.z;
         f8[8 * i + 4] = q[i].x; f8[8 * i + 5] = q[i].y; f8[8 * i + 6] = (dims == 3) ? q[i].w : 0.f; f8[8 * i + 7] = q[i].z;
-        u2[2 * i + 0] = a.y; u2[2 * i + 1] = a.z;
+        u2[2 * i + 0] = a.y; u2[2 * i + 1] = a.z & 0x1ffu;   // depth | leaf << 8 (the quadrant bits stay internal)
     }
     return cudaSuccess;
 }

@@ -117,7 +117,7 @@ struct BhWorkspace {
     unsigned node_cap = 0, n_nodes = 0;
     void *root = nullptr, *box = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
-    void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr;   // node_data: one 32-byte record per node
+    void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr, *node_slots = nullptr;   // node_data: one 32-byte record per node
     int dims = 2;                // 2 = the reference's quadtree, 3 = octree
     void *temp = nullptr;
     size_t temp_bytes = 0;
