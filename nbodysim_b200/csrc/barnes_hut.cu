@@ -48,8 +48,10 @@ template <int DIMS> struct BhT {
 struct BhRoot { float cx, cy, cz, size; };
 
 // ---- 1. bounding box -------------------------------------------------------------------------
-// floats map to unsigned keys whose integer order equals the float order, so min/max reduce with
-// integer atomics; box[0..2] = minima x,y,z ; box[3..5] = maxima (encoded), reset by bh_reset_kernel.
+// floats map to unsigned keys whose integer order equals the float order, so min/max reduce with integer
+// atomics.  box[0..2] hold the minima x,y,z as the COMPLEMENT of that key and box[3..5] the maxima, so that
+// both reduce with atomicMax and "no body seen yet" is 0 for all six words: the per-step reset is part of the
+// one memset that also clears the sort / scan scratch and the arrival counters.
 __device__ __forceinline__ unsigned f2ord(float f)
 {
     const unsigned u = __float_as_uint(f);
@@ -58,14 +60,6 @@ __device__ __forceinline__ unsigned f2ord(float f)
 __device__ __forceinline__ float ord2f(unsigned k)
 {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-__global__ void bh_reset_kernel(unsigned *box, unsigned *count_tail)
-{
-    box[0] = box[1] = box[2] = 0xffffffffu;   // running minima
-    box[3] = box[4] = box[5] = 0u;            // running maxima
-    count_tail[0] = 0;                        // count[n]   : terminates the exclusive scan
-    count_tail[1] = 0;                        // count[n+1] : deepest leaf level
 }
 
 template <int DIMS>
@@ -87,23 +81,27 @@ __global__ void __launch_bounds__(256) bh_bbox_kernel(const float *__restrict__ 
             mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
             mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
         }
-        if ((threadIdx.x & 31) == 0) { atomicMin(&box[c], f2ord(mn[c])); atomicMax(&box[3 + c], f2ord(mx[c])); }
+        if ((threadIdx.x & 31) == 0) { atomicMax(&box[c], ~f2ord(mn[c])); atomicMax(&box[3 + c], f2ord(mx[c])); }
     }
 }
 
+// Quad::new_containing, Quad.hpp:40-44: center = (min+max)*0.5f ; size = max over the axes of the extent.
+// Evaluated by every thread of the keys kernel (six cached words, a handful of operations) instead of a
+// one-thread kernel of its own.
 template <int DIMS>
-__global__ void bh_root_kernel(const unsigned *box, BhRoot *root)
+__device__ __forceinline__ BhRoot bh_root_from_box(const unsigned *__restrict__ box)
 {
-    // Quad::new_containing, Quad.hpp:40-44: center = (min+max)*0.5f ; size = max over the axes of the extent
     float c[3] = {0.f, 0.f, 0.f}, size = 0.f;
 #pragma unroll
     for (int a = 0; a < DIMS; ++a) {
-        const float lo = ord2f(box[a]), hi = ord2f(box[3 + a]);
+        const float lo = ord2f(~box[a]), hi = ord2f(box[3 + a]);
         c[a] = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
         const float ext = __fsub_rn(hi, lo);
         size = (a == 0) ? ext : fmaxf(size, ext);
     }
-    root->cx = c[0]; root->cy = c[1]; root->cz = c[2]; root->size = size;
+    BhRoot r;
+    r.cx = c[0]; r.cy = c[1]; r.cz = c[2]; r.size = size;
+    return r;
 }
 
 // Quad::find_quadrant (Quad.hpp:47-49) and Quad::into_quadrant (Quad.hpp:51-57), one level down.
@@ -121,21 +119,31 @@ __device__ __forceinline__ unsigned bh_descend(float x, float y, float z, float 
 }
 
 // ---- 2. quadrant-path keys -----------------------------------------------------------------------
-template <int DIMS>
+// Also: the root quad (kept for the emit kernel) and, with FOLD_HIST, the digit histograms of the radix sort that
+// follows -- the keys are counted where they are produced instead of being read again by a histogram kernel.
+template <int DIMS, bool FOLD_HIST>
 __global__ void __launch_bounds__(256)
-bh_keys_kernel(const float *__restrict__ posm, size_t n, const BhRoot *__restrict__ root,
-               unsigned long long *__restrict__ keys, unsigned *__restrict__ idx)
+bh_keys_kernel(const float *__restrict__ posm, size_t n, const unsigned *__restrict__ box, BhRoot *__restrict__ root_out,
+               unsigned long long *__restrict__ keys, unsigned *__restrict__ idx, unsigned *__restrict__ sort_hist)
 {
+    __shared__ unsigned sh[FOLD_HIST ? RS_MAX_PASSES : 1][256];
+    if (FOLD_HIST) rs_hist_clear(sh);
+    const BhRoot root = bh_root_from_box<DIMS>(box);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t g = blk_index(i, 0);
-    const float x = posm[g], y = posm[g + BLK], z = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
-    float cx = root->cx, cy = root->cy, cz = root->cz, size = root->size;
-    unsigned long long k = 0;
+    if (i == 0) *root_out = root;
+    if (i < n) {
+        const size_t g = blk_index(i, 0);
+        const float x = posm[g], y = posm[g + BLK], z = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
+        float cx = root.cx, cy = root.cy, cz = root.cz, size = root.size;
+        unsigned long long k = 0;
 #pragma unroll 4
-    for (int l = 0; l < BhT<DIMS>::LEVELS; ++l) k = (k << BhT<DIMS>::BITS) | bh_descend<DIMS>(x, y, z, cx, cy, cz, size);
-    keys[i] = k << BhT<DIMS>::ALIGN;
-    idx[i] = (unsigned)i;
+        for (int l = 0; l < BhT<DIMS>::LEVELS; ++l) k = (k << BhT<DIMS>::BITS) | bh_descend<DIMS>(x, y, z, cx, cy, cz, size);
+        k <<= BhT<DIMS>::ALIGN;
+        keys[i] = k;
+        idx[i] = (unsigned)i;
+        if (FOLD_HIST) rs_hist_add_key(sh, k);
+    }
+    if (FOLD_HIST) rs_hist_flush(sh, sort_hist);
 }
 
 template <int DIMS>
@@ -150,10 +158,11 @@ __device__ __forceinline__ int lcp_levels(unsigned long long a, unsigned long lo
 template <int DIMS>
 __global__ void __launch_bounds__(256)
 bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned *__restrict__ count,
-                unsigned char *__restrict__ first, unsigned char *__restrict__ leaf, unsigned *__restrict__ max_depth)
+                unsigned char *__restrict__ first, unsigned char *__restrict__ leaf)
 {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    if (s == 0) count[n] = 0;                                // terminates the exclusive scan over count[0..n]
     const unsigned long long k = keys[s];
     if (s > 0 && keys[s - 1] == k) { count[s] = 0; first[s] = 0; leaf[s] = 0; return; }
     const int lp = (s > 0) ? lcp_levels<DIMS>(keys[s - 1], k) : -1;
@@ -165,8 +174,6 @@ bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned 
     count[s] = (unsigned)(leafd - firstd + 1);
     first[s] = (unsigned char)firstd;
     leaf[s] = (unsigned char)leafd;
-    // deepest leaf of the tree: bounds the levels of the COM pass
-    if ((unsigned)leafd > *max_depth) atomicMax(max_depth, (unsigned)leafd);   // racy pre-check only skips no-ops
 }
 
 // node record: com/body position, mass, size^2 ; next (0 = end of walk) ; depth | leaf flag ; parent.
@@ -473,17 +480,26 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     dims = dims_;
     node_cap = (unsigned)std::min<size_t>(4 * n + 1024, 0x7fffffffu);
 #define BH_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
-    BH_ALLOC(root, sizeof(BhRoot)) BH_ALLOC(box, 32)
+    BH_ALLOC(root, sizeof(BhRoot))
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
     BH_ALLOC(node_data, (size_t)node_cap * 32) BH_ALLOC(node_quad, (size_t)node_cap * 16)
-    BH_ALLOC(node_arrive, (size_t)node_cap * 4)
     BH_ALLOC(node_slots, (size_t)node_cap * (dims == 3 ? 8 : 4) * 16)
-    size_t t1 = 0, t2 = 0;
+    // everything that must be zero at the start of a build lives in ONE region cleared by one memset per step:
+    // bounding box | radix-sort scratch (histograms, tickets, status words) | scan scratch | arrival counters
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_sort = 256, o_scan = o_sort + up(radix_sort_temp_bytes(n)), o_arrive = o_scan + up(exclusive_scan_temp_bytes(n + 1));
+    zero_bytes = o_arrive + (size_t)node_cap * 4;
+    BH_ALLOC(zero_region, zero_bytes)
+    box = zero_region;
+    sort_temp = (char *)zero_region + o_sort;
+    scan_temp = (char *)zero_region + o_scan;
+    node_arrive = (char *)zero_region + o_arrive;
+    size_t t1 = 0, t2 = 0;   // scratch of the library comparison path (sort_impl = 2)
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
-    temp_bytes = std::max(std::max(std::max(t1, t2), radix_sort_temp_bytes(n)), exclusive_scan_temp_bytes(n + 1));
+    temp_bytes = std::max(t1, t2);
     BH_ALLOC(temp, temp_bytes)
 #undef BH_ALLOC
     return cudaSuccess;
@@ -491,7 +507,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, box, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_arrive, node_slots, temp};
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, zero_region, temp};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -509,26 +525,28 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     cudaError_t e;
     const unsigned g256 = (unsigned)((n + 255) / 256), g128 = (unsigned)((n + 127) / 128);
     unsigned *cnt = (unsigned *)w.count;
-    bh_reset_kernel<<<1, 1, 0, st>>>((unsigned *)w.box, cnt + n);
+    // one memset: bounding box, sort and scan scratch, arrival counters (at most min(node_cap, 4n + 1024) cells)
+    if ((e = cudaMemsetAsync(w.zero_region, 0, w.zero_bytes, st)) != cudaSuccess) return e;
     bh_bbox_kernel<DIMS><<<std::min(g256, 4u * 148u), 256, 0, st>>>(posm, n, (unsigned *)w.box);
-    bh_root_kernel<DIMS><<<1, 1, 0, st>>>((const unsigned *)w.box, (BhRoot *)w.root);
-    bh_keys_kernel<DIMS><<<g256, 256, 0, st>>>(posm, n, (const BhRoot *)w.root, (unsigned long long *)w.keys_in, (unsigned *)w.idx_in);
     size_t tb = w.temp_bytes;
     if (w.own_sort) { // stable LSD sort; the result lands back in the first buffer pair -> swap roles
+        bh_keys_kernel<DIMS, true><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
+                                                         (unsigned *)w.idx_in, (unsigned *)w.sort_temp);
         if ((e = radix_sort_u64((unsigned long long *)w.keys_in, (unsigned long long *)w.keys, (unsigned *)w.idx_in, (unsigned *)w.idx,
-                                n, w.temp, st, 0, 64, launches)) != cudaSuccess) return e;
+                                n, w.sort_temp, st, 0, 64, launches, nullptr, true)) != cudaSuccess) return e;
         std::swap(w.keys_in, w.keys);
         std::swap(w.idx_in, w.idx);
-    } else if ((e = cub::DeviceRadixSort::SortPairs(w.temp, tb, (const unsigned long long *)w.keys_in, (unsigned long long *)w.keys,
-                                                    (const unsigned *)w.idx_in, (unsigned *)w.idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
-    bh_count_kernel<DIMS><<<g256, 256, 0, st>>>((const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first,
-                                                (unsigned char *)w.leaf, cnt + n + 1);
+    } else {
+        bh_keys_kernel<DIMS, false><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
+                                                          (unsigned *)w.idx_in, nullptr);
+        if ((e = cub::DeviceRadixSort::SortPairs(w.temp, tb, (const unsigned long long *)w.keys_in, (unsigned long long *)w.keys,
+                                                 (const unsigned *)w.idx_in, (unsigned *)w.idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
+    }
+    bh_count_kernel<DIMS><<<g256, 256, 0, st>>>((const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first, (unsigned char *)w.leaf);
     tb = w.temp_bytes;
     if (w.own_sort) {
-        if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.temp, st, launches)) != cudaSuccess) return e;
+        if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.scan_temp, st, launches, true)) != cudaSuccess) return e;
     } else if ((e = cub::DeviceScan::ExclusiveSum(w.temp, tb, (const unsigned *)w.count, (unsigned *)w.offs, (int)n + 1, st)) != cudaSuccess) return e;
-    // arrival counters of at most min(node_cap, 4n + 1024) cells (a tree over n bodies has < that many in practice)
-    if ((e = cudaMemsetAsync(w.node_arrive, 0, (size_t)w.node_cap * 4, st)) != cudaSuccess) return e;
     bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
                                                (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,
                                                (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, w.node_cap);
@@ -536,7 +554,7 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
                                                     (const unsigned char *)w.leaf, (const unsigned *)w.count, (unsigned *)w.node_arrive,
                                                     w.node_cap);
     w.count_valid = false;
-    if (launches) *launches += 7 + (w.own_sort ? 0 : 3);     // own kernels (+ the library's sort/scan passes, counted as 3;
+    if (launches) *launches += 5 + (w.own_sort ? 0 : 3);     // own kernels (+ the library's sort/scan passes, counted as 3;
                                                              //  the hand-written sort and scan count their own launches)
     return cudaGetLastError();
 }

@@ -119,8 +119,11 @@ struct BhWorkspace {
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
     void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr, *node_slots = nullptr;   // node_data: one 32-byte record per node
     int dims = 2;                // 2 = the reference's quadtree, 3 = octree
-    void *temp = nullptr;
+    void *temp = nullptr;        // scratch of the library comparison path
     size_t temp_bytes = 0;
+    // cleared by one memset at the start of every build: box | sort scratch | scan scratch | arrival counters
+    void *zero_region = nullptr, *sort_temp = nullptr, *scan_temp = nullptr;
+    size_t zero_bytes = 0;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
     unsigned walk_window = 256;  // warp-cooperative walk: how many records ahead of the slowest lane a lane may run

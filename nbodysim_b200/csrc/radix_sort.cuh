@@ -57,6 +57,27 @@ __device__ __forceinline__ unsigned rs_block_excl_scan(unsigned v, unsigned *war
     return before + incl - v;
 }
 
+// For a kernel that PRODUCES the keys (256 threads per CTA): count the 8 digits of every key it writes into a
+// shared histogram and add the CTA's counts to the sort's global histograms (the first 8 x 256 words of `temp`).
+__device__ __forceinline__ void rs_hist_clear(unsigned (*sh)[256])
+{
+    for (int p = 0; p < RS_MAX_PASSES; ++p) sh[p][threadIdx.x] = 0;
+    __syncthreads();
+}
+__device__ __forceinline__ void rs_hist_add_key(unsigned (*sh)[256], unsigned long long k)
+{
+#pragma unroll
+    for (int p = 0; p < RS_MAX_PASSES; ++p) atomicAdd(&sh[p][(unsigned)(k >> (8 * p)) & 255u], 1u);
+}
+__device__ __forceinline__ void rs_hist_flush(unsigned (*sh)[256], unsigned *__restrict__ hist)
+{
+    __syncthreads();
+    for (int p = 0; p < RS_MAX_PASSES; ++p) {
+        const unsigned c = sh[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * 256 + threadIdx.x], c);
+    }
+}
+
 // hist[p][d] += number of keys whose digit of pass (pass0 + p) is d
 static __global__ void __launch_bounds__(RS_THREADS)
 os_hist_kernel(const unsigned long long *__restrict__ keys, size_t n, const unsigned *__restrict__ n_dev, int pass0, int npasses,
@@ -264,7 +285,7 @@ inline size_t radix_sort_temp_bytes(size_t n)
 // Fully asynchronous on `st` (graph-capturable).
 static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b,
                                   size_t n, void *temp, cudaStream_t st, int begin_bit = 0, int end_bit = 64, int *launches = nullptr,
-                                  const unsigned *n_dev = nullptr)
+                                  const unsigned *n_dev = nullptr, bool hist_ready = false)
 {
     if (n == 0 || end_bit <= begin_bit) return cudaSuccess;
     const int pass0 = begin_bit / 8, npasses = (end_bit - begin_bit + 7) / 8;
@@ -274,11 +295,13 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
     unsigned *hist = (unsigned *)temp;                                    // [npasses][256]
     unsigned *ticket = hist + RS_MAX_PASSES * 256;                        // [npasses]
     unsigned long long *status = (unsigned long long *)((char *)temp + (size_t)RS_MAX_PASSES * 256 * sizeof(unsigned) + 64);
-    cudaError_t e = cudaMemsetAsync(temp, 0, radix_sort_temp_bytes(n), st);
-    if (e != cudaSuccess) return e;
+    // hist_ready: the caller zeroed `temp` and the producer of the keys already accumulated the digit histograms
+    // of these passes into it (rs_hist_add_key / rs_hist_flush): one memset, one kernel and one read of the keys less
+    cudaError_t e = cudaSuccess;
+    if (!hist_ready && (e = cudaMemsetAsync(temp, 0, radix_sort_temp_bytes(n), st)) != cudaSuccess) return e;
     size_t hgrid = (n + 8 * RS_THREADS - 1) / (8 * RS_THREADS);             // >= 8 keys per thread, at most 8 CTAs per SM
     if (hgrid > 148 * 8) hgrid = 148 * 8;
-    os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, n_dev, pass0, npasses, hist);
+    if (!hist_ready) os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, n_dev, pass0, npasses, hist);
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
     for (int p = 0; p < npasses; ++p) {
@@ -292,7 +315,7 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
         unsigned long long *tk = kin; kin = kout; kout = tk;
         unsigned *tv = vin; vin = vout; vout = tv;
     }
-    if (launches) *launches += 1 + npasses;
+    if (launches) *launches += (hist_ready ? 0 : 1) + npasses;
     if (npasses & 1) {   // odd number of passes: bring the result back to the first buffer
         if ((e = cudaMemcpyAsync(keys_a, keys_b, n * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
         if (vals_a && (e = cudaMemcpyAsync(vals_a, vals_b, n * 4, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
@@ -375,11 +398,12 @@ scan_excl_kernel(const unsigned *__restrict__ in, unsigned *__restrict__ out, si
 }
 
 // out[i] = in[0] + ... + in[i-1] for i in [0, n).  `temp` holds exclusive_scan_temp_bytes(n).  Asynchronous on `st`.
-static inline cudaError_t exclusive_scan_u32(const unsigned *in, unsigned *out, size_t n, void *temp, cudaStream_t st, int *launches = nullptr)
+static inline cudaError_t exclusive_scan_u32(const unsigned *in, unsigned *out, size_t n, void *temp, cudaStream_t st, int *launches = nullptr,
+                                              bool temp_zeroed = false)
 {
     if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(temp, 0, exclusive_scan_temp_bytes(n), st);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    if (!temp_zeroed && (e = cudaMemsetAsync(temp, 0, exclusive_scan_temp_bytes(n), st)) != cudaSuccess) return e;
     scan_excl_kernel<<<(unsigned)((n + SC_TILE - 1) / SC_TILE), RS_THREADS, 0, st>>>(in, out, n, (unsigned *)temp,
                                                                                     (unsigned long long *)((char *)temp + 64));
     if (launches) *launches += 1;
