@@ -633,6 +633,11 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         set_err(nullptr, "nbody_gpu_init: invalid parameter");
         return NBODY_EINVAL;
     }
+    if (p->exchange < 0 || p->exchange > 2 || p->sort_impl < 0 || p->sort_impl > 2 || p->bh_walk < 0 || p->bh_walk > 2 ||
+        !(p->theta >= 0.0f) || p->world < 0 || p->ngpus < 0) {
+        set_err(nullptr, "nbody_gpu_init: exchange, sort_impl and bh_walk take 0..2; theta, world and ngpus must not be negative");
+        return NBODY_EINVAL;
+    }
     if (p->force_algo != NBODY_FORCE_ALLPAIRS && p->force_algo != NBODY_FORCE_BARNES_HUT) {
         set_err(nullptr, "nbody_gpu_init: unknown force_algo %d", p->force_algo);
         return NBODY_EINVAL;

@@ -64,6 +64,11 @@ def test_error_paths_without_gpu():
     assert lib.nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 0) == capi.EINVAL
     p.dims = 5
     assert lib.nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 4) == capi.EINVAL
+    for field, bad in (("exchange", 3), ("sort_impl", -1), ("bh_walk", 7), ("theta", -1.0), ("force_algo", 9), ("precision", 4)):
+        lib.nbody_params_default(C.byref(p))
+        setattr(p, field, bad)
+        assert lib.nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 4) == capi.EINVAL, field
+        assert lib.nbody_gpu_last_error(None) != b""
     assert lib.nbody_gpu_step(None, 0.01, 1) == capi.EINVAL
     assert lib.nbody_gpu_download(None, b.ctypes.data, 4, 7) == capi.EINVAL
     lib.nbody_gpu_shutdown(None)  # must be a no-op
