@@ -140,8 +140,11 @@ typedef struct nbody_info {
     uint32_t reserved0;
     uint64_t kernel_launches; /* kernels of this library launched so far (all local GPUs) */
     uint64_t interactions;    /* pair interactions evaluated so far by this process */
-    float    last_force_ms;   /* device time of the force kernel(s) of the last profiled step */
+    float    last_force_ms;   /* device time of the force kernel(s) of the last profiled step (Barnes-Hut: tree build + walk) */
     float    last_integ_ms;   /* device time of the integrator kernel of the last profiled step */
+    float    last_bh_build_ms;/* Barnes-Hut: the tree-build part of last_force_ms (keys, sort, cells, centres of mass) */
+    float    last_collide_ms; /* device time of the collision pass of the last profiled step (collide = 1) */
+    uint64_t last_bh_visits;  /* Barnes-Hut: node records visited by the walk of the last profiled step, all targets */
 } nbody_info;
 
 /* Fill *p with the reference's shipped parameters (Simulation.hpp:59,120-124; G=1, dims=2,
@@ -174,7 +177,10 @@ int nbody_gpu_sync(nbody_ctx *ctx);
 int nbody_gpu_download(nbody_ctx *ctx, nbody_body_t *bodies, size_t n, unsigned fields);
 
 /* Replace the whole body state from host memory (positions, velocities, masses), e.g. after the
- * host ran Simulation::collide() on the downloaded bodies. n must equal the n given to init. */
+ * host ran Simulation::collide() on the downloaded bodies. n must equal the n given to init.
+ * One process per GPU (world > 1): collective -- every rank calls it, and only this rank's shard
+ * [shard_start, shard_start + shard_count) of `bodies` is read and copied to the device (the mirror image of
+ * nbody_gpu_download); the packed shard reaches the other ranks over NVLink through the exchange. */
 int nbody_gpu_upload(nbody_ctx *ctx, const nbody_body_t *bodies, size_t n);
 
 /* Double-precision read-back of the shard (3 doubles per body each; any pointer may be NULL):

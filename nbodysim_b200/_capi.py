@@ -81,6 +81,9 @@ class NbodyInfo(C.Structure):
         ("interactions", C.c_uint64),
         ("last_force_ms", C.c_float),
         ("last_integ_ms", C.c_float),
+        ("last_bh_build_ms", C.c_float),
+        ("last_collide_ms", C.c_float),
+        ("last_bh_visits", C.c_uint64),
     ]
 
     def as_dict(self):

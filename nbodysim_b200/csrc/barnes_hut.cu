@@ -16,7 +16,7 @@
 //   1. bounding box -> root quad                                       (Quad::new_containing)
 //   2. per body, the quadrant path by the SAME fp32 recursion -> 64-bit key, 2 bits per level,
 //      32 levels (Z-order == find_quadrant bit order, Quad.hpp:47-49)
-//   3. stable radix sort of (key, body)                                (radix_sort.cuh; cub::DeviceRadixSort selectable)
+//   3. stable radix sort of (key, body)                                (radix_sort.cuh, hand-written)
 //   4. cells owned by each sorted body = the path cells that first appear with it; exclusive scan
 //      -> depth-first pre-order node array WITHOUT the reference's empty leaves (they contribute +-0)
 //   5. skip pointers (`next`) by binary search on the sorted keys; first child = index + 1
@@ -27,8 +27,6 @@
 // bodies (`pos == existing_pos`, masses added in index order); the reference would subdivide
 // further if their positions differ beyond that depth.
 #include "kernels.h"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include "radix_sort.cuh"
 #include <cstring>
 
@@ -194,10 +192,12 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                const unsigned *__restrict__ idx, size_t n, const BhRoot *__restrict__ root,
                const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
                const unsigned char *__restrict__ first, const unsigned char *__restrict__ leaf,
-               BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap)
+               BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap, unsigned *status)
 {
     constexpr int BITS = BhT<DIMS>::BITS;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // more cells than reserved: the tree is truncated, so raise the context's sticky (host-visible) status word
+    if (s == 0 && offs[n] > cap && status) *reinterpret_cast<volatile unsigned *>(status) = 1u;
     if (s >= n || count[s] == 0) return;
     const unsigned long long k = keys[s];
     const unsigned body = idx[s];
@@ -403,7 +403,7 @@ template <int DIMS, bool REFCOMPAT>
 __global__ void __launch_bounds__(128)
 bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-               float *__restrict__ accp, unsigned cap)
+               float *__restrict__ accp, unsigned cap, unsigned long long *visits)
 {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -412,16 +412,18 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
     const size_t g = blk_index(body, 0);
     const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
     float ax = 0.f, ay = 0.f, az = 0.f;
-    unsigned i = 0;
+    unsigned i = 0, nvis = 0;
     do {
         float4 nd;
         uint4 na;
         bh_load_node(nodes, i, nd, na);
+        ++nvis;
         if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
         else i = i + 1;
-    } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (reported by node_count)
+    } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (raises the status word)
     const size_t l = blk_index(body - shard_start, 0);
     accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = az;
+    if (visits) atomicAdd(visits, (unsigned long long)nvis);   // profiled steps only: node records visited (roofline)
 }
 
 // Warp-cooperative walk.  The 32 lanes of a warp hold 32 targets that are neighbours in Z-order; the
@@ -436,7 +438,7 @@ template <int DIMS, bool REFCOMPAT>
 __global__ void __launch_bounds__(128)
 bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                     float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-                    float *__restrict__ accp, unsigned cap, unsigned window)
+                    float *__restrict__ accp, unsigned cap, unsigned window, unsigned long long *visits)
 {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = s < n;
@@ -452,13 +454,14 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
     // `window`: a lane takes its next node whenever that node lies fewer than `window` records ahead of the
     // slowest lane, so one step's loads fall into `window` consecutive 32-byte records (window = 1: every active
     // lane reads the same record).  Lanes that accepted a cell keep going while a neighbour descends into it.
-    unsigned resume = mine ? 0u : DONE;
+    unsigned resume = mine ? 0u : DONE, nvis = 0;
     unsigned i = __reduce_min_sync(0xffffffffu, resume);
     while (i < cap) {                                        // DONE (and an overflowed tree) end the walk
         if (resume - i < window) {                           // unsigned: false for DONE
             float4 nd;
             uint4 na;
             bh_load_node(nodes, resume, nd, na);
+            ++nvis;
             if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az))
                 resume = na.y ? na.y : DONE;
             else
@@ -470,15 +473,21 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
         const size_t l = blk_index(body - shard_start, 0);
         accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = az;
     }
+    if (visits && nvis) atomicAdd(visits, (unsigned long long)nvis);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-cudaError_t BhWorkspace::alloc(size_t n, int dims_)
+// Cells: a body owns the cells of its path that first appear with it -- about 2.8 n for well-separated bodies (the
+// reference's shipped scene: 69,681 cells for 25,000 bodies), up to 32 n when many bodies are much closer to a
+// neighbour than to everything else (each such pair hangs from a chain of single-child cells).  `node_factor` x n
+// cells are reserved (default 4; environment NBODY_BH_NODE_FACTOR); a tree that needs more raises the context's
+// sticky status instead of being truncated silently.
+cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor)
 {
     cudaError_t e;
     n_cap = n;
     dims = dims_;
-    node_cap = (unsigned)std::min<size_t>(4 * n + 1024, 0x7fffffffu);
+    node_cap = (unsigned)std::min<size_t>((size_t)(std::max(1.0, std::min(node_factor, 33.0)) * (double)n) + 1024, 0x7fffffffu);
 #define BH_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
     BH_ALLOC(root, sizeof(BhRoot))
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
@@ -495,19 +504,13 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_)
     sort_temp = (char *)zero_region + o_sort;
     scan_temp = (char *)zero_region + o_scan;
     node_arrive = (char *)zero_region + o_arrive;
-    size_t t1 = 0, t2 = 0;   // scratch of the library comparison path (sort_impl = 2)
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
-                                    (unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 64);
-    cub::DeviceScan::ExclusiveSum(nullptr, t2, (unsigned *)nullptr, (unsigned *)nullptr, (int)n + 1);
-    temp_bytes = std::max(t1, t2);
-    BH_ALLOC(temp, temp_bytes)
 #undef BH_ALLOC
     return cudaSuccess;
 }
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, zero_region, temp};
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, zero_region};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -528,34 +531,23 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     // one memset: bounding box, sort and scan scratch, arrival counters (at most min(node_cap, 4n + 1024) cells)
     if ((e = cudaMemsetAsync(w.zero_region, 0, w.zero_bytes, st)) != cudaSuccess) return e;
     bh_bbox_kernel<DIMS><<<std::min(g256, 4u * 148u), 256, 0, st>>>(posm, n, (unsigned *)w.box);
-    size_t tb = w.temp_bytes;
-    if (w.own_sort) { // stable LSD sort; the result lands back in the first buffer pair -> swap roles
-        bh_keys_kernel<DIMS, true><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
-                                                         (unsigned *)w.idx_in, (unsigned *)w.sort_temp);
-        if ((e = radix_sort_u64((unsigned long long *)w.keys_in, (unsigned long long *)w.keys, (unsigned *)w.idx_in, (unsigned *)w.idx,
-                                n, w.sort_temp, st, 0, 64, launches, nullptr, true)) != cudaSuccess) return e;
-        std::swap(w.keys_in, w.keys);
-        std::swap(w.idx_in, w.idx);
-    } else {
-        bh_keys_kernel<DIMS, false><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
-                                                          (unsigned *)w.idx_in, nullptr);
-        if ((e = cub::DeviceRadixSort::SortPairs(w.temp, tb, (const unsigned long long *)w.keys_in, (unsigned long long *)w.keys,
-                                                 (const unsigned *)w.idx_in, (unsigned *)w.idx, (int)n, 0, 64, st)) != cudaSuccess) return e;
-    }
+    // stable LSD sort; the result lands back in the first buffer pair -> swap roles
+    bh_keys_kernel<DIMS, true><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
+                                                     (unsigned *)w.idx_in, (unsigned *)w.sort_temp);
+    if ((e = radix_sort_u64((unsigned long long *)w.keys_in, (unsigned long long *)w.keys, (unsigned *)w.idx_in, (unsigned *)w.idx,
+                            n, w.sort_temp, st, 0, 64, launches, nullptr, true)) != cudaSuccess) return e;
+    std::swap(w.keys_in, w.keys);
+    std::swap(w.idx_in, w.idx);
     bh_count_kernel<DIMS><<<g256, 256, 0, st>>>((const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first, (unsigned char *)w.leaf);
-    tb = w.temp_bytes;
-    if (w.own_sort) {
-        if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.scan_temp, st, launches, true)) != cudaSuccess) return e;
-    } else if ((e = cub::DeviceScan::ExclusiveSum(w.temp, tb, (const unsigned *)w.count, (unsigned *)w.offs, (int)n + 1, st)) != cudaSuccess) return e;
+    if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.scan_temp, st, launches, true)) != cudaSuccess) return e;
     bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
                                                (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,
-                                               (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, w.node_cap);
+                                               (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, w.node_cap, w.status);
     bh_propagate_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned char *)w.first,
                                                     (const unsigned char *)w.leaf, (const unsigned *)w.count, (unsigned *)w.node_arrive,
                                                     w.node_cap);
     w.count_valid = false;
-    if (launches) *launches += 5 + (w.own_sort ? 0 : 3);     // own kernels (+ the library's sort/scan passes, counted as 3;
-                                                             //  the hand-written sort and scan count their own launches)
+    if (launches) *launches += 5;                            // the sort and the scan count their own launches
     return cudaGetLastError();
 }
 
@@ -584,26 +576,26 @@ cudaError_t BhWorkspace::node_count(size_t n, cudaStream_t st, unsigned *out)
 
 template <int DIMS>
 static void bh_walk_t(const BhWorkspace &w, const float *posm, size_t n, float t_sq, float e_sq, bool refcompat, int fix,
-                      size_t shard_start, size_t shard_count, float *accp, cudaStream_t st)
+                      size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, cudaStream_t st)
 {
     const unsigned g = (unsigned)((n + 127) / 128);
     const unsigned *idx = (const unsigned *)w.idx;
     const BhNodes nd = bh_nodes(w);
     if (w.warp_walk) {
-        if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window);
-        else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window);
+        if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
+        else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
     } else {
-        if (refcompat) bh_walk_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap);
-        else bh_walk_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap);
+        if (refcompat) bh_walk_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits);
+        else bh_walk_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits);
     }
 }
 
 cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
-                              size_t shard_start, size_t shard_count, float *accp, cudaStream_t st)
+                              size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, cudaStream_t st)
 {
     const float t_sq = theta * theta, e_sq = eps * eps;       // Quadtree ctor, Quadtree.hpp:19
-    if (dims == 3) bh_walk_t<3>(*this, posm, n, t_sq, e_sq, refcompat, fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, st);
-    else bh_walk_t<2>(*this, posm, n, t_sq, e_sq, refcompat, fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, st);
+    if (dims == 3) bh_walk_t<3>(*this, posm, n, t_sq, e_sq, refcompat, fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, visits, st);
+    else bh_walk_t<2>(*this, posm, n, t_sq, e_sq, refcompat, fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, visits, st);
     return cudaGetLastError();
 }
 

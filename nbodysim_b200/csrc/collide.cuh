@@ -1,0 +1,232 @@
+// collide.cuh -- phases of the collision pass (see collide.cu for the algorithm), as grid-stride device functions:
+// `gtid` of `gthreads` cooperating threads.  Shared by the one-kernel-per-phase path (collide.cu) and the
+// single-cluster step kernels of small scenes (small_scene.cu).
+#pragma once
+#include "kernels.h"
+#include "radix_sort.cuh"
+
+namespace nb {
+
+constexpr float COL_CELL = 600.0f;   // SpatialGrid::CELL_SIZE, Simulation.hpp:20
+
+// counters: [0] cell entries, [1] pairs kept (hot components), [2] overflow flag, [3] pairs resolved (narrow test
+// passed), [4] sweep pairs that overlap now
+struct ColArgs {
+    float *posm, *vel;                     // blocked SoA; radius rides in vel's 4th component
+    unsigned n;
+    unsigned long long *keys_in;           // cell entries as produced (hash, body) ...
+    unsigned *vals_in;
+    const unsigned long long *keys;        // ... and sorted by hash
+    const unsigned *vals;
+    unsigned entry_cap;
+    unsigned long long *pairs;             // pair keys as produced
+    unsigned pair_cap;
+    unsigned char *hot;                    // [0, n): body is in a pair that overlaps now ; [n, 2n): component label is hot
+    unsigned *parent;                      // union-find forest over the bodies
+    unsigned *counters;
+    unsigned *status;                      // host-visible sticky flags ([1] = collision buffers overflowed), may be null
+    int idx_bits, rooted;
+};
+
+__device__ __forceinline__ unsigned long long col_hash(int x, int y)
+{
+    const unsigned h = (((unsigned)x * 92837111u) ^ ((unsigned)y * 689287499u)) * 15485863u;
+    return (unsigned long long)(long long)(int)h;
+}
+
+struct ColBody { float x, y, r; };
+__device__ __forceinline__ ColBody col_load(const float *posm, const float *vel, unsigned i)
+{
+    const size_t g = blk_index(i, 0);
+    ColBody b;
+    b.x = posm[g]; b.y = posm[g + BLK]; b.r = vel[g + 3 * BLK];
+    return b;
+}
+
+__device__ __forceinline__ void col_overflow(const ColArgs &a)
+{
+    atomicExch(&a.counters[2], 1u);
+    if (a.status) *reinterpret_cast<volatile unsigned *>(a.status + 1) = 1u;
+}
+
+// ---- union-find (lock-free; a root is always the smallest index of its tree) ------------------------------------
+__device__ __forceinline__ unsigned uf_find(unsigned *parent, unsigned x)
+{
+    unsigned p = __ldcg(parent + x);
+    while (p != x) {                                       // path halving; the racing writes are benign (they only
+        const unsigned gp = __ldcg(parent + p);            // ever replace a parent by one of its ancestors)
+        if (gp != p) __stcg(parent + x, gp);
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(unsigned *parent, unsigned a, unsigned b)
+{
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const unsigned t = a; a = b; b = t; }   // hook the larger root under the smaller
+        if (atomicCAS(parent + a, a, b) == a) return;
+    }
+}
+
+// ---- phases ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void col_phase_init(const ColArgs &a, unsigned gtid, unsigned gthreads)
+{
+    if (gtid < 8) a.counters[gtid] = 0;
+    for (unsigned i = gtid; i < a.n; i += gthreads) { a.parent[i] = i; a.hot[i] = 0; a.hot[a.n + i] = 0; }
+}
+
+__device__ __forceinline__ void col_phase_entries(const ColArgs &a, unsigned gtid, unsigned gthreads)
+{
+    for (unsigned i = gtid; i < a.n; i += gthreads) {
+        const ColBody b = col_load(a.posm, a.vel, i);
+        // Simulation.hpp:228-233: AABB = pos -+ radius ; cell = static_cast<int>(coordinate / CELL_SIZE)
+        const int minX = __float2int_rz(__fdiv_rn(__fsub_rn(b.x, b.r), COL_CELL)), maxX = __float2int_rz(__fdiv_rn(__fadd_rn(b.x, b.r), COL_CELL));
+        const int minY = __float2int_rz(__fdiv_rn(__fsub_rn(b.y, b.r), COL_CELL)), maxY = __float2int_rz(__fdiv_rn(__fadd_rn(b.y, b.r), COL_CELL));
+        const long long cells = (long long)(maxX - minX + 1) * (long long)(maxY - minY + 1);
+        if (cells <= 0 || cells > 4096) { col_overflow(a); continue; }
+        const unsigned base = atomicAdd(&a.counters[0], (unsigned)cells);
+        if ((unsigned long long)base + (unsigned long long)cells > a.entry_cap) { col_overflow(a); continue; }
+        unsigned k = base;
+        for (int y = minY; y <= maxY; ++y)
+            for (int x = minX; x <= maxX; ++x) { a.keys_in[k] = col_hash(x, y); a.vals_in[k] = i; ++k; }
+    }
+}
+
+// x-interval overlap exactly as the sweep sees it (a start sorts before an end at the same x), pair
+// ordered by interval start, ties by body index (the reference's unstable sort leaves exact ties open)
+__device__ __forceinline__ bool col_sweep_pair(const ColBody &a, unsigned ia, const ColBody &b, unsigned ib,
+                                               unsigned &first, unsigned &second)
+{
+    const float amin = __fsub_rn(a.x, a.r), amax = __fadd_rn(a.x, a.r);
+    const float bmin = __fsub_rn(b.x, b.r), bmax = __fadd_rn(b.x, b.r);
+    if (fmaxf(amin, bmin) > fminf(amax, bmax)) return false;
+    const bool a_first = (amin < bmin) || (amin == bmin && ia < ib);
+    first = a_first ? ia : ib;
+    second = a_first ? ib : ia;
+    return true;
+}
+
+// Enumerate the sweep pairs (one thread per cell entry: the pairs it forms with the later entries of its cell).
+//   MODE 0  detect: mark the bodies of pairs that overlap now (Simulation.hpp:301: d.mag_sq() <= r*r) and count them
+//   MODE 1  connect: union the two bodies of every sweep pair            (only when something overlaps)
+//   MODE 2  emit: the pairs whose component is hot, keyed (component, first, second)
+template <int MODE>
+__device__ __forceinline__ void col_phase_pairs(const ColArgs &a, unsigned gtid, unsigned gthreads)
+{
+    if (__ldcg(a.counters + 2)) return;                   // overflow: the pass is abandoned (reported through status / sync)
+    if (MODE > 0 && __ldcg(a.counters + 4) == 0) return;  // nothing overlaps: no resolve can pass its test
+    const unsigned ne = __ldcg(a.counters + 0);
+    unsigned overlaps = 0;
+    for (unsigned e = gtid; e < ne; e += gthreads) {
+        const unsigned long long key = a.keys[e];
+        const unsigned ia = a.vals[e];
+        const ColBody A = col_load(a.posm, a.vel, ia);
+        for (unsigned f = e + 1; f < ne && a.keys[f] == key; ++f) {
+            const unsigned ib = a.vals[f];
+            if (ib == ia) continue;
+            const ColBody B = col_load(a.posm, a.vel, ib);
+            unsigned first, second;
+            if (!col_sweep_pair(A, ia, B, ib, first, second)) continue;
+            if (MODE == 0) {
+                const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
+                if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r))) { a.hot[ia] = 1; a.hot[ib] = 1; ++overlaps; }
+            } else if (MODE == 1) {
+                uf_union(a.parent, first, second);
+            } else {
+                const unsigned root = uf_find(a.parent, first);
+                if (a.hot[a.n + root]) {
+                    const unsigned p = atomicAdd(&a.counters[1], 1u);
+                    if (p < a.pair_cap) {
+                        unsigned long long k = ((unsigned long long)first << a.idx_bits) | second;      // sorts as (first, second)
+                        if (a.rooted) k |= (unsigned long long)root << (2 * a.idx_bits);                // ... inside its component
+                        a.pairs[p] = k;
+                    } else col_overflow(a);
+                }
+            }
+        }
+    }
+    if (MODE == 0 && overlaps) atomicAdd(&a.counters[4], overlaps);
+}
+
+// a component is hot when one of its bodies is in a pair that overlaps now
+__device__ __forceinline__ void col_phase_mark(const ColArgs &a, unsigned gtid, unsigned gthreads)
+{
+    if (__ldcg(a.counters + 2) || __ldcg(a.counters + 4) == 0) return;
+    for (unsigned i = gtid; i < a.n; i += gthreads)
+        if (a.hot[i]) a.hot[a.n + uf_find(a.parent, i)] = 1;
+}
+
+// Simulation::resolve, Simulation.hpp:293-346, unfused IEEE operations in the reference's order.
+__device__ __forceinline__ bool col_resolve(float *posm, float *vel, unsigned i, unsigned j)
+{
+    const size_t gi = blk_index(i, 0), gj = blk_index(j, 0);
+    float p1x = posm[gi], p1y = posm[gi + BLK], p2x = posm[gj], p2y = posm[gj + BLK];
+    const float dx = __fsub_rn(p2x, p1x), dy = __fsub_rn(p2y, p1y);
+    const float r = __fadd_rn(vel[gi + 3 * BLK], vel[gj + 3 * BLK]);
+    const float d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    const float r_sq = __fmul_rn(r, r);
+    if (d_sq > r_sq) return false;
+    float v1x = vel[gi], v1y = vel[gi + BLK], v2x = vel[gj], v2y = vel[gj + BLK];
+    const float vx = __fsub_rn(v2x, v1x), vy = __fsub_rn(v2y, v1y);
+    const float d_dot_v = __fadd_rn(__fmul_rn(dx, vx), __fmul_rn(dy, vy));
+    const float m1 = posm[gi + 3 * BLK], m2 = posm[gj + 3 * BLK];
+    const float msum = __fadd_rn(m1, m2);
+    const float w1 = __fdiv_rn(m2, msum), w2 = __fdiv_rn(m1, msum);
+    if (d_dot_v >= 0.0f && !(dx == 0.0f && dy == 0.0f)) {
+        const float k = __fsub_rn(__fdiv_rn(r, __fsqrt_rn(d_sq)), 1.0f);
+        const float tx = __fmul_rn(dx, k), ty = __fmul_rn(dy, k);
+        posm[gi] = __fsub_rn(p1x, __fmul_rn(tx, w1)); posm[gi + BLK] = __fsub_rn(p1y, __fmul_rn(ty, w1));
+        posm[gj] = __fadd_rn(p2x, __fmul_rn(tx, w2)); posm[gj + BLK] = __fadd_rn(p2y, __fmul_rn(ty, w2));
+        return true;
+    }
+    const float v_sq = __fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy));
+    float disc = __fsub_rn(__fmul_rn(d_dot_v, d_dot_v), __fmul_rn(v_sq, __fsub_rn(d_sq, r_sq)));
+    if (disc < 0.0f) disc = 0.0f;
+    const float t = __fdiv_rn(__fadd_rn(d_dot_v, __fsqrt_rn(disc)), v_sq);
+    p1x = __fsub_rn(p1x, __fmul_rn(v1x, t)); p1y = __fsub_rn(p1y, __fmul_rn(v1y, t));
+    p2x = __fsub_rn(p2x, __fmul_rn(v2x, t)); p2y = __fsub_rn(p2y, __fmul_rn(v2y, t));
+    const float ndx = __fsub_rn(p2x, p1x), ndy = __fsub_rn(p2y, p1y);
+    const float nd_dot_v = __fadd_rn(__fmul_rn(ndx, vx), __fmul_rn(ndy, vy));
+    const float nd_sq = __fadd_rn(__fmul_rn(ndx, ndx), __fmul_rn(ndy, ndy));
+    const float k = __fdiv_rn(__fmul_rn(1.5f, nd_dot_v), nd_sq);
+    const float tx = __fmul_rn(ndx, k), ty = __fmul_rn(ndy, k);
+    const float n1x = __fadd_rn(v1x, __fmul_rn(tx, w1)), n1y = __fadd_rn(v1y, __fmul_rn(ty, w1));
+    const float n2x = __fsub_rn(v2x, __fmul_rn(tx, w2)), n2y = __fsub_rn(v2y, __fmul_rn(ty, w2));
+    vel[gi] = n1x; vel[gi + BLK] = n1y; vel[gj] = n2x; vel[gj + BLK] = n2y;
+    posm[gi] = __fadd_rn(p1x, __fmul_rn(n1x, t)); posm[gi + BLK] = __fadd_rn(p1y, __fmul_rn(n1y, t));
+    posm[gj] = __fadd_rn(p2x, __fmul_rn(n2x, t)); posm[gj + BLK] = __fadd_rn(p2y, __fmul_rn(n2y, t));
+    return true;
+}
+
+// One thread per component: the thread whose pair starts a run of equal component labels walks the run in
+// (first, second) order.  Components share no body, so runs are independent; inside a run every resolve sees
+// what the previous one wrote (one thread, program order).
+__device__ __forceinline__ void col_phase_resolve(const ColArgs &a, const unsigned long long *__restrict__ pairs_sorted,
+                                                  unsigned gtid, unsigned gthreads)
+{
+    if (__ldcg(a.counters + 2)) return;
+    const unsigned np = min(__ldcg(a.counters + 1), a.pair_cap);
+    const int b = a.idx_bits, rs = a.rooted ? 2 * b : 63;
+    const unsigned long long imask = (1ull << b) - 1ull;
+    unsigned resolved = 0;
+    for (unsigned p = gtid; p < np; p += gthreads) {
+        const unsigned long long k0 = pairs_sorted[p];
+        const unsigned long long root = a.rooted ? (k0 >> rs) : 0ull;
+        if (p > 0 && (a.rooted ? (pairs_sorted[p - 1] >> rs) : 0ull) == root) continue;      // not the start of a run
+        unsigned q = p;
+        unsigned long long k = k0;
+        for (;;) {
+            if (col_resolve(a.posm, a.vel, (unsigned)((k >> b) & imask), (unsigned)(k & imask))) ++resolved;
+            if (++q >= np) break;
+            k = pairs_sorted[q];
+            if ((a.rooted ? (k >> rs) : 0ull) != root) break;
+        }
+    }
+    if (resolved) atomicAdd(&a.counters[3], resolved);
+}
+
+} // namespace nb

@@ -97,9 +97,10 @@ cudaError_t launch_wait_peer_flags(const unsigned long long *flags, int world, i
                                    unsigned long long timeout_ns, unsigned *status, cudaStream_t st);
 
 // AoS (reference Body, 64 B) <-> blocked SoA
-cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,
+// packs records [first, first + count) (global body indices; `aos` starts at record aos_first of the caller's array)
+cudaError_t launch_pack(const void *aos, size_t aos_first, size_t first, size_t count, size_t n, size_t shard_start,
                         size_t shard_count, void *posm, void *vel, void *acc, bool f64, int dims,
-                        cudaStream_t st);
+                        float check_mass, unsigned *status, cudaStream_t st);
 cudaError_t launch_unpack(void *aos, size_t n, size_t shard_start, size_t shard_count,
                           const void *posm, const void *vel, const void *acc, bool f64,
                           cudaStream_t st);
@@ -119,8 +120,7 @@ struct BhWorkspace {
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
     void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr, *node_slots = nullptr;   // node_data: one 32-byte record per node
     int dims = 2;                // 2 = the reference's quadtree, 3 = octree
-    void *temp = nullptr;        // scratch of the library comparison path
-    size_t temp_bytes = 0;
+    unsigned *status = nullptr;  // host-visible sticky flags ([0] = more cells than reserved), owned by the context
     // cleared by one memset at the start of every build: box | sort scratch | scan scratch | arrival counters
     void *zero_region = nullptr, *sort_temp = nullptr, *scan_temp = nullptr;
     size_t zero_bytes = 0;
@@ -128,26 +128,27 @@ struct BhWorkspace {
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
     unsigned walk_window = 256;  // warp-cooperative walk: how many records ahead of the slowest lane a lane may run
                                  // (sweep on B200, tools/bh_window_sweep.py: 256 is best or within 1 % of best everywhere)
-    bool own_sort = false;       // hand-written radix sort (radix_sort.cuh) instead of cub::DeviceRadixSort
-    cudaError_t alloc(size_t n, int dims);
+    cudaError_t alloc(size_t n, int dims, double node_factor);
     cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);
     void release();
     cudaError_t build(const float *posm, size_t n, cudaStream_t st, int *launches);
     cudaError_t walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
-                     size_t shard_start, size_t shard_count, float *accp, cudaStream_t st);
+                     size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, cudaStream_t st);
     cudaError_t download_nodes(float *f8, unsigned *u2, size_t cap, cudaStream_t st);
 };
 
 // collision pass (collide.cu)
+struct ColArgs;
 struct CollideWorkspace {
     size_t n_cap = 0;
     unsigned entry_cap = 0, pair_cap = 0;
     void *keys_in = nullptr, *keys = nullptr, *vals_in = nullptr, *vals = nullptr;
-    void *pairs_in = nullptr, *pairs = nullptr, *hot = nullptr, *counters = nullptr, *temp = nullptr;
+    void *pairs_in = nullptr, *pairs = nullptr, *hot = nullptr, *parent = nullptr, *counters = nullptr, *temp = nullptr;
     size_t temp_bytes = 0;
-    bool own_sort = false;
+    unsigned *status = nullptr;  // host-visible sticky flags ([1] = entry / pair buffers overflowed), owned by the context
     cudaError_t alloc(size_t n);
     void release();
+    ColArgs args(float *posm, float *vel, size_t n) const;
     cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches);
     cudaError_t stats(cudaStream_t st, unsigned out[4]);
 };

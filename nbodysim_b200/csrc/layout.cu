@@ -8,20 +8,27 @@
 
 namespace nb {
 
+// `aos` holds the records [aos_first, ...) of the caller's array: the whole array (aos_first = 0, first = 0, count =
+// n_padded: nbody_gpu_init) or only this rank's shard (aos_first = first = shard_start, count = shard_count: uploads
+// of a distributed context).  `check_mass` != 0: every real body must still have exactly this mass (the uniform-mass
+// force kernel is in use); a violation raises status[2].
 template <typename T>
 __global__ void __launch_bounds__(256)
-pack_kernel(const nbody_body_t *__restrict__ aos, size_t n, size_t n_padded, size_t shard_start,
-            size_t shard_count, T *__restrict__ posm, T *__restrict__ vel, T *__restrict__ acc, int dims)
+pack_kernel(const nbody_body_t *__restrict__ aos, size_t aos_first, size_t first, size_t count, size_t n, size_t shard_start,
+            size_t shard_count, T *__restrict__ posm, T *__restrict__ vel, T *__restrict__ acc, int dims,
+            float check_mass, unsigned *status)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_padded) return;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const size_t i = first + k;
     // each thread reads its 64-byte record as four 16-byte vectors (a warp covers 2 KiB contiguous)
     // zero-mass padding beyond n sits far away (1e18): it contributes exactly 0 to every sum, also in
     // the uniform-mass kernel, where (r^2)^-3/2 underflows to 0 instead of being multiplied by m = 0
     float4 p = make_float4(PAD_POS, PAD_POS, PAD_POS, 0), v = make_float4(0, 0, 0, 0), a = v, mr = v;
     if (i < n) {
-        const float4 *r = reinterpret_cast<const float4 *>(aos + i);
+        const float4 *r = reinterpret_cast<const float4 *>(aos + (i - aos_first));
         p = r[0]; v = r[1]; a = r[2]; mr = r[3];
+        if (check_mass != 0.f && mr.x != check_mass && status) *reinterpret_cast<volatile unsigned *>(status + 2) = 1u;
         // 2-D callers (the reference) leave the Vec2 tail padding indeterminate: never read z from it
         if (dims == 2) { p.z = 0.f; v.z = 0.f; a.z = 0.f; }
     }
@@ -66,19 +73,20 @@ unpack_f64_kernel(double *__restrict__ pos3, double *__restrict__ vel3, double *
     if (acc3) { acc3[3 * k] = acc[l]; acc3[3 * k + 1] = acc[l + BLK]; acc3[3 * k + 2] = acc[l + 2 * BLK]; }
 }
 
-cudaError_t launch_pack(const void *aos, size_t n, size_t n_padded, size_t shard_start,
+cudaError_t launch_pack(const void *aos, size_t aos_first, size_t first, size_t count, size_t n, size_t shard_start,
                         size_t shard_count, void *posm, void *vel, void *acc, bool f64, int dims,
-                        cudaStream_t st)
+                        float check_mass, unsigned *status, cudaStream_t st)
 {
-    const unsigned grid = (unsigned)((n_padded + 255) / 256);
+    if (count == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((count + 255) / 256);
     if (f64)
-        pack_kernel<double><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, n, n_padded, shard_start,
+        pack_kernel<double><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, aos_first, first, count, n, shard_start,
                                                   shard_count, (double *)posm, (double *)vel,
-                                                  (double *)acc, dims);
+                                                  (double *)acc, dims, check_mass, status);
     else
-        pack_kernel<float><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, n, n_padded, shard_start,
+        pack_kernel<float><<<grid, 256, 0, st>>>((const nbody_body_t *)aos, aos_first, first, count, n, shard_start,
                                                  shard_count, (float *)posm, (float *)vel,
-                                                 (float *)acc, dims);
+                                                 (float *)acc, dims, check_mass, status);
     return cudaGetLastError();
 }
 

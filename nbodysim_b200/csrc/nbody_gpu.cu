@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace nb;
@@ -35,10 +36,12 @@ struct Dev {
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev_pushed[2] = {nullptr, nullptr};   // P2P exchange: this GPU's integrate-and-push of step parity 0/1 is done
-    cudaEvent_t ev_integrated = nullptr, ev_gathered = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_integrated = nullptr, ev_gathered = nullptr, ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *posm[2] = {nullptr, nullptr};
     void *vel = nullptr, *acc = nullptr, *accp = nullptr, *aos = nullptr;
     double *energy5 = nullptr;
+    unsigned long long *walk_visits = nullptr;          // profiled Barnes-Hut steps: node records visited by the walk
+    unsigned *h_status = nullptr, *d_status = nullptr;   // pinned + mapped: [0] Barnes-Hut cell overflow, [1] collision buffer overflow
     ncclComm_t comm = nullptr;
     // cross-process exchange (one process per GPU): the peers' position buffers and flag arrays, mapped by CUDA IPC
     void *peer_posm[NBODY_MAX_GPUS][2] = {};
@@ -83,7 +86,8 @@ struct nbody_ctx {
     int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0, ctas_per_sm_small = 0;
     unsigned long long launches = 0, interactions = 0;
     int profile_next = 0;
-    float last_force_ms = 0.f, last_integ_ms = 0.f;
+    float last_force_ms = 0.f, last_integ_ms = 0.f, last_build_ms = 0.f, last_collide_ms = 0.f;
+    unsigned long long last_visits = 0;
     char err[512];
     nbody_ctx() { err[0] = 0; }
 };
@@ -217,7 +221,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaEventCreateWithFlags(&d.ev_integrated, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&d.ev_gathered, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) CU(cudaEventCreateWithFlags(&d.ev_pushed[k], cudaEventDisableTiming));
-    for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&d.ev_t[k]));
+    for (int k = 0; k < 6; ++k) CU(cudaEventCreate(&d.ev_t[k]));
     CU(cudaMalloc(&d.posm[0], full));
     CU(cudaMalloc(&d.posm[1], full));
     CU(cudaMalloc(&d.vel, shard));
@@ -225,14 +229,22 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaMalloc(&d.accp, shard * (size_t)std::max(1, d.nslots)));
     CU(cudaMalloc(&d.aos, ctx->n_padded * sizeof(nbody_body_t)));
     CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
+    CU(cudaMalloc(&d.walk_visits, sizeof(unsigned long long)));
+    // sticky overflow flags the kernels raise and sync / download / energy check: host memory mapped into the device
+    // address space, so checking them costs no copy
+    CU(cudaHostAlloc((void **)&d.h_status, 64, cudaHostAllocMapped));
+    memset(d.h_status, 0, 64);
+    CU(cudaHostGetDevicePointer((void **)&d.d_status, d.h_status, 0));
     if (ctx->p.collide) {
         CU(d.col.alloc(ctx->n));
-        d.col.own_sort = (ctx->p.sort_impl != 2);
+        d.col.status = d.d_status;
     }
     if (ctx->bh) {
-        CU(d.bh.alloc(ctx->n, ctx->p.dims));
+        double factor = 4.0;
+        if (const char *nf = getenv("NBODY_BH_NODE_FACTOR")) factor = atof(nf);
+        CU(d.bh.alloc(ctx->n, ctx->p.dims, factor));
+        d.bh.status = d.d_status;
         d.bh.warp_walk = ctx->p.bh_walk == 2 || (ctx->p.bh_walk == 0 && (ctx->p.dims == 3 || ctx->p.theta < 0.7f));
-        d.bh.own_sort = (ctx->p.sort_impl != 2);
         if (const char *ww = getenv("NBODY_BH_WALK_WINDOW")) d.bh.walk_window = (unsigned)std::max(1, atoi(ww));   // tuning override
     }
     return NBODY_OK;
@@ -240,19 +252,51 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
 
 int ipc_barrier(nbody_ctx *ctx);
 
-int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies)
+
+// Initial upload (`shard_only` = false): every local GPU receives and packs all n bodies.
+// Re-upload of a distributed context (`shard_only` = true, one process per GPU): only this rank's records cross
+// PCIe; the packed shard then reaches the other ranks over NVLink -- copies into the peers' mapped buffers (CUDA
+// IPC exchange) or one in-place ncclAllGather -- bracketed by stream-ordered barriers so that no rank's buffer is
+// written while a peer still reads it, and every rank's copies have landed before anyone proceeds.
+int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies, bool shard_only)
 {
+    const float check_mass = (ctx->uniform && shard_only) ? ctx->uniform_mass : 0.f;
+    if (shard_only && ctx->ipc) {
+        int rc = ipc_barrier(ctx);
+        if (rc != NBODY_OK) return rc;
+    }
     for (Dev &d : ctx->devs) {
         CU(cudaSetDevice(d.device));
-        CU(cudaMemcpyAsync(d.aos, bodies, ctx->n * sizeof(nbody_body_t), cudaMemcpyHostToDevice, d.stream));
         d.cur = 0;
-        CU(launch_pack(d.aos, ctx->n, ctx->n_padded, d.shard_start, d.shard_count, d.posm[0], d.vel,
-                       d.acc, ctx->f64, ctx->p.dims, d.stream));
-        ctx->launches++;
-        // padding must also be valid in the other buffer (masses are copied by the integrator only
-        // for the shard's own blocks, so seed both buffers with the full packed state)
-        CU(cudaMemcpyAsync(d.posm[1], d.posm[0], ctx->n_padded * 4 * ctx->esz, cudaMemcpyDeviceToDevice, d.stream));
         d.gathered_pending = false;
+        const size_t full_bytes = ctx->n_padded * 4 * ctx->esz;
+        if (!shard_only) {
+            CU(cudaMemcpyAsync(d.aos, bodies, ctx->n * sizeof(nbody_body_t), cudaMemcpyHostToDevice, d.stream));
+            CU(launch_pack(d.aos, 0, 0, ctx->n_padded, ctx->n, d.shard_start, d.shard_count, d.posm[0], d.vel,
+                           d.acc, ctx->f64, ctx->p.dims, 0.f, nullptr, d.stream));
+            ctx->launches++;
+            // padding must also be valid in the other buffer (masses are copied by the integrator only
+            // for the shard's own blocks, so seed both buffers with the full packed state)
+            CU(cudaMemcpyAsync(d.posm[1], d.posm[0], full_bytes, cudaMemcpyDeviceToDevice, d.stream));
+            continue;
+        }
+        const size_t real = d.shard_start < ctx->n ? std::min(ctx->n - d.shard_start, d.shard_count) : 0;
+        if (real) CU(cudaMemcpyAsync(d.aos, bodies + d.shard_start, real * sizeof(nbody_body_t), cudaMemcpyHostToDevice, d.stream));
+        CU(launch_pack(d.aos, d.shard_start, d.shard_start, d.shard_count, ctx->n, d.shard_start, d.shard_count, d.posm[0], d.vel,
+                       d.acc, ctx->f64, ctx->p.dims, check_mass, d.d_status, d.stream));
+        ctx->launches++;
+        const size_t shard_bytes = d.shard_count * 4 * ctx->esz, off = (size_t)d.rank * shard_bytes;
+        if (ctx->ipc) {
+            CU(cudaMemcpyAsync((char *)d.posm[1] + off, (char *)d.posm[0] + off, shard_bytes, cudaMemcpyDeviceToDevice, d.stream));
+            for (int r = 0; r < ctx->world; ++r) {
+                if (r == d.rank) continue;
+                for (int k = 0; k < 2; ++k)
+                    CU(cudaMemcpyAsync((char *)d.peer_posm[r][k] + off, (char *)d.posm[0] + off, shard_bytes, cudaMemcpyDefault, d.stream));
+            }
+        } else {
+            NC(nccl().AllGather((char *)d.posm[0] + off, d.posm[0], shard_bytes, NCCL_UINT8, d.comm, d.stream));
+            CU(cudaMemcpyAsync(d.posm[1], d.posm[0], full_bytes, cudaMemcpyDeviceToDevice, d.stream));
+        }
     }
     if (ctx->ipc) {   // no peer may push into this rank's buffers before they are packed (and vice versa)
         int rc = ipc_barrier(ctx);
@@ -261,6 +305,10 @@ int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies)
     for (Dev &d : ctx->devs) {
         CU(cudaSetDevice(d.device));
         CU(cudaStreamSynchronize(d.stream)); // `bodies` may be pageable and reused by the caller
+        if (d.h_status && ((volatile unsigned *)d.h_status)[2]) {
+            set_err(ctx, "nbody_gpu_upload: masses changed; re-create the context (uniform-mass kernel in use)");
+            return NBODY_ESTATE;
+        }
     }
     return NBODY_OK;
 }
@@ -298,7 +346,8 @@ ForceLaunch make_force(const nbody_ctx *c, const Dev &d, const Range &r, float d
 int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
 {
     const bool refc = !ctx->f64 && ctx->p.rsqrt_mode == NBODY_RSQRT_REFCOMPAT;
-    const bool guard = (ctx->p.eps == 0.0f);
+    // the kernel adds eps*eps (fp32) under flush-to-zero: guard against r^2 + eps^2 == 0 whenever that term can vanish
+    const bool guard = (ctx->p.eps * ctx->p.eps < 1.17549435e-38f);
     const int par_prev = (int)((ctx->step_index + 1) & 1);     // parity of the previous step's push events
     // remote positions of the previous step must have landed: NCCL allgather done, or every peer's push done
     auto wait_remote = [&](Dev &d) -> cudaError_t {
@@ -324,8 +373,12 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             if (d.gathered_pending) { CU(wait_remote(d)); waited = true; }
             int nl = 0;
             CU(d.bh.build((const float *)d.posm[d.cur], ctx->n, d.stream, &nl));
+            if (prof) {
+                CU(cudaEventRecord(d.ev_t[3], d.stream));
+                CU(cudaMemsetAsync(d.walk_visits, 0, sizeof(unsigned long long), d.stream));
+            }
             CU(d.bh.walk((const float *)d.posm[d.cur], ctx->n, ctx->p.theta, ctx->p.eps, refc, ctx->p.bh_fix_near_leaves != 0,
-                         d.shard_start, d.shard_count, (float *)d.accp, d.stream));
+                         d.shard_start, d.shard_count, (float *)d.accp, prof ? d.walk_visits : nullptr, d.stream));
             ctx->launches += (unsigned long long)nl + 1;
         }
         for (const Range &r : d.plan) {
@@ -391,6 +444,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             CU(ctx->f64 ? launch_integrate_f64(I, d.stream) : launch_integrate_f32(I, d.stream));
             ctx->launches++;
         }
+        if (prof) CU(cudaEventRecord(d.ev_t[4], d.stream));
         if (ctx->p.collide && !acc_only) { // Simulation::step(): iterate(dt) ; collide()
             int nl = 0;
             CU(d.col.run((float *)d.posm[d.cur ^ 1], (float *)d.vel, ctx->n, d.stream, &nl));
@@ -453,6 +507,19 @@ int sync_all(nbody_ctx *ctx)
         if (d.comm_stream) CU(cudaStreamSynchronize(d.comm_stream));
         CU(cudaStreamSynchronize(d.stream));
         d.gathered_pending = false;
+        if (d.h_status) {
+            const volatile unsigned *hs = d.h_status;
+            if (hs[0]) {
+                set_err(ctx, "Barnes-Hut tree needed more cells than reserved (%u): forces were truncated. Clustered bodies form long "
+                             "single-child chains; raise NBODY_BH_NODE_FACTOR (cells reserved per body, default 4, at most 33)", d.bh.node_cap);
+                return NBODY_ENOMEM;
+            }
+            if (hs[1]) {
+                set_err(ctx, "collision pass: cell-entry or pair buffer overflow (a body spans more than 4096 grid cells, or a dense "
+                             "clump produced more than %u pairs): the pass was abandoned for at least one step", d.col.pair_cap);
+                return NBODY_ESTATE;
+            }
+        }
         if (ctx->ipc) {
             unsigned status = 0;
             CU(cudaMemcpy(&status, d.ipc_words + 1, sizeof status, cudaMemcpyDeviceToHost));
@@ -570,13 +637,15 @@ void free_all(nbody_ctx *c)
         if (d.accp) cudaFree(d.accp);
         if (d.aos) cudaFree(d.aos);
         if (d.energy5) cudaFree(d.energy5);
+        if (d.walk_visits) cudaFree(d.walk_visits);
+        if (d.h_status) cudaFreeHost(d.h_status);
         d.bh.release();
         d.col.release();
         if (d.graph) cudaGraphExecDestroy(d.graph);
         if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
         if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
         for (int k = 0; k < 2; ++k) if (d.ev_pushed[k]) cudaEventDestroy(d.ev_pushed[k]);
-        for (int k = 0; k < 4; ++k) if (d.ev_t[k]) cudaEventDestroy(d.ev_t[k]);
+        for (int k = 0; k < 6; ++k) if (d.ev_t[k]) cudaEventDestroy(d.ev_t[k]);
         if (d.comm_stream) cudaStreamDestroy(d.comm_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
     }
@@ -658,6 +727,12 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     }
     const int world = multiproc ? p->world : nlocal;
     if (multiproc && (p->rank < 0 || p->rank >= p->world)) return NBODY_EINVAL;
+    if (multiproc && p->world > NBODY_MAX_GPUS && p->exchange != 1) {
+        // the peer exchange keeps per-rank tables of NBODY_MAX_GPUS entries (mapped buffers, flag words, kernel arguments)
+        set_err(nullptr, "nbody_gpu_init: world = %d exceeds NBODY_MAX_GPUS = %d; larger worlds need exchange = 1 (ncclAllGather)",
+                p->world, NBODY_MAX_GPUS);
+        return NBODY_EINVAL;
+    }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -788,7 +863,7 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     if (multiproc && p->exchange != 1) {
         if ((rc = setup_ipc(ctx)) != NBODY_OK) return fail(rc);
     }
-    if ((rc = upload_state(ctx, bodies)) != NBODY_OK) return fail(rc);
+    if ((rc = upload_state(ctx, bodies, false)) != NBODY_OK) return fail(rc);
     *out = ctx;
     return NBODY_OK;
 }
@@ -832,10 +907,8 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
     if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
     // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
     // (the Barnes-Hut build and the collision pass are fully asynchronous -- sorts, scan, COM pass, pair
-    //  discovery and resolve keep their counters on the device -- so they capture too; only the library-sort
-    //  comparison path of the collision pass reads counters back)
-    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !(ctx->p.collide && ctx->p.sort_impl == 2) &&
-                          !ctx->profile_next && nsteps >= 8;
+    //  discovery and resolve keep their counters on the device -- so they capture too)
+    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->profile_next && nsteps >= 8;
     const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && (ctx->n_padded <= 32768 || (ctx->bh && ctx->n_padded <= 262144)));
     if (graph_ok && want) {
         int rc = step_with_graph(ctx, dt, nsteps);
@@ -850,7 +923,14 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
             CU(cudaSetDevice(d.device));
             CU(cudaEventSynchronize(d.ev_t[2]));
             CU(cudaEventElapsedTime(&ctx->last_force_ms, d.ev_t[0], d.ev_t[1]));
-            CU(cudaEventElapsedTime(&ctx->last_integ_ms, d.ev_t[1], d.ev_t[2]));
+            CU(cudaEventElapsedTime(&ctx->last_integ_ms, d.ev_t[1], d.ev_t[4]));
+            CU(cudaEventElapsedTime(&ctx->last_collide_ms, d.ev_t[4], d.ev_t[2]));
+            ctx->last_build_ms = 0.f;
+            ctx->last_visits = 0;
+            if (ctx->bh) {
+                CU(cudaEventElapsedTime(&ctx->last_build_ms, d.ev_t[0], d.ev_t[3]));
+                CU(cudaMemcpy(&ctx->last_visits, d.walk_visits, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            }
             ctx->profile_next = 0;
         }
     }
@@ -888,17 +968,34 @@ int nbody_gpu_download(nbody_ctx *ctx, nbody_body_t *bodies, size_t n, unsigned 
         CU(cudaStreamSynchronize(d.stream));
     }
     if (fields != NBODY_FIELD_ALL) {
+        // merge the requested fields from the pinned staging copy; the caller's other fields stay untouched.
+        // Memory-bound host work: split over a few threads when the shard is large (a viewer polling positions).
         const bool z = ctx->p.dims == 3;
-        for (Dev &d : ctx->devs) {
-            if (d.shard_start >= ctx->n) continue;
-            const size_t i1 = std::min(ctx->n, d.shard_start + d.shard_count);
-            for (size_t i = d.shard_start; i < i1; ++i) {
-                const nbody_body_t &s = ctx->h_stage[i];
+        const nbody_body_t *stage = ctx->h_stage;
+        auto merge = [=](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) {
+                const nbody_body_t &s = stage[i];
                 nbody_body_t &t = bodies[i];
                 if (fields & NBODY_FIELD_POS) { t.pos[0] = s.pos[0]; t.pos[1] = s.pos[1]; if (z) t.pos_z = s.pos_z; }
                 if (fields & NBODY_FIELD_VEL) { t.vel[0] = s.vel[0]; t.vel[1] = s.vel[1]; if (z) t.vel_z = s.vel_z; }
                 if (fields & NBODY_FIELD_ACC) { t.acc[0] = s.acc[0]; t.acc[1] = s.acc[1]; if (z) t.acc_z = s.acc_z; }
             }
+        };
+        for (Dev &d : ctx->devs) {
+            if (d.shard_start >= ctx->n) continue;
+            const size_t i0 = d.shard_start, i1 = std::min(ctx->n, d.shard_start + d.shard_count), cnt = i1 - i0;
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const size_t nt = std::min<size_t>(std::min<size_t>(hw, 8), cnt / 131072);
+            if (nt <= 1) { merge(i0, i1); continue; }
+            std::vector<std::thread> pool;
+            try {
+                for (size_t t = 1; t < nt; ++t) pool.emplace_back(merge, i0 + cnt * t / nt, i0 + cnt * (t + 1) / nt);
+            } catch (...) {               // could not start a thread: this one does the rest
+                const size_t done = pool.size() + 1;
+                merge(i0 + cnt * done / nt, i1);
+            }
+            merge(i0, i0 + cnt / nt);
+            for (std::thread &th : pool) th.join();
         }
     }
     return NBODY_OK;
@@ -909,14 +1006,17 @@ int nbody_gpu_upload(nbody_ctx *ctx, const nbody_body_t *bodies, size_t n)
     if (!ctx || !bodies || n != ctx->n) return NBODY_EINVAL;
     int rc = sync_all(ctx);
     if (rc != NBODY_OK) return rc;
-    if (ctx->uniform) { // the uniform-mass kernel stays valid only while the masses stay as uploaded
+    // one process per GPU: only this rank's shard is read and crosses PCIe; the exchange carries it to the peers.
+    // (the uniform-mass kernel stays valid only while the masses stay as uploaded: checked by the pack kernel)
+    if (ctx->p.world > 1) return upload_state(ctx, bodies, true);
+    if (ctx->uniform) {
         for (size_t i = 0; i < n; ++i)
             if (bodies[i].mass != ctx->uniform_mass) {
                 set_err(ctx, "nbody_gpu_upload: masses changed; re-create the context (uniform-mass kernel in use)");
                 return NBODY_ESTATE;
             }
     }
-    return upload_state(ctx, bodies);
+    return upload_state(ctx, bodies, false);
 }
 
 int nbody_gpu_download_f64(nbody_ctx *ctx, double *pos3, double *vel3, double *acc3, size_t n)
@@ -1004,17 +1104,25 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->ctas_per_sm = ctx->ctas_per_sm;
     info->fused = d0.fused ? 1 : 0;
     info->uniform_mass = ctx->uniform ? 1 : 0;
-    if (ctx->bh) {
-        unsigned m = 0;
-        cudaSetDevice(ctx->devs[0].device);
-        ctx->devs[0].bh.node_count(ctx->n, ctx->devs[0].stream, &m);
-        info->bh_nodes = m;
-    }
     info->graph = (d0.graph != nullptr) ? 1 : 0;
     info->kernel_launches = ctx->launches;
     info->interactions = ctx->interactions;
     info->last_force_ms = ctx->last_force_ms;
     info->last_integ_ms = ctx->last_integ_ms;
+    info->last_bh_build_ms = ctx->last_build_ms;
+    info->last_collide_ms = ctx->last_collide_ms;
+    info->last_bh_visits = ctx->last_visits;
+    if (ctx->bh) {
+        unsigned m = 0;
+        cudaSetDevice(ctx->devs[0].device);
+        const cudaError_t ne = ctx->devs[0].bh.node_count(ctx->n, ctx->devs[0].stream, &m);
+        info->bh_nodes = m;
+        if (ne == cudaErrorMemoryAllocation) {
+            set_err(ctx, "Barnes-Hut tree needs %u cells, %u reserved (raise NBODY_BH_NODE_FACTOR)", m, ctx->devs[0].bh.node_cap);
+            return NBODY_ENOMEM;
+        }
+        if (ne != cudaSuccess) { set_err(ctx, "node_count: %s", cudaGetErrorString(ne)); return NBODY_ECUDA; }
+    }
     return NBODY_OK;
 }
 

@@ -22,6 +22,10 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "targets x" in cb["sample"]
     assert "workload" in d["config"] and d["config"]["n"] == 8192
+    # the reference's real per-step path (Simulation::step on its own 25,000-body scene) rides in the same line
+    bh = d["bh"]
+    assert bh["n"] == 25000 and bh["ms_per_step"] > 0 and bh["cpu_baseline"]["kind"] in ("reference", "port")
+    assert bh["e2e"]["value"] == bh["ms_per_step"]
 
 
 def test_reference_arm_other_ranks_exit_silently():

@@ -69,6 +69,11 @@ def test_error_paths_without_gpu():
         setattr(p, field, bad)
         assert lib.nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 4) == capi.EINVAL, field
         assert lib.nbody_gpu_last_error(None) != b""
+    # the cross-process peer exchange keeps tables of NBODY_MAX_GPUS entries: larger worlds must ask for NCCL
+    lib.nbody_params_default(C.byref(p))
+    p.world, p.rank, p.exchange = 17, 3, 0
+    assert lib.nbody_gpu_init(C.byref(ctx), C.byref(p), b.ctypes.data, 4) == capi.EINVAL
+    assert b"NBODY_MAX_GPUS" in lib.nbody_gpu_last_error(None)
     assert lib.nbody_gpu_step(None, 0.01, 1) == capi.EINVAL
     assert lib.nbody_gpu_download(None, b.ctypes.data, 4, 7) == capi.EINVAL
     lib.nbody_gpu_shutdown(None)  # must be a no-op

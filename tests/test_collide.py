@@ -98,6 +98,52 @@ def test_gpu_collide_equals_oracle_canonical_order(n, L, rmax, seed):
     assert np.array_equal(bits(out["pos"]), bits(want["pos"])) and np.array_equal(bits(out["vel"]), bits(want["vel"]))
 
 
+def chain_scene():
+    """A-B-C-D: only A and B overlap at first; resolving (A,B) pushes B into C, resolving (B,C) pushes C into D.
+    All x intervals overlap (sweep pairs exist), offsets in y keep the later pairs apart until their turn."""
+    c = empty_bodies(6)
+    c["pos"] = [[0, 0], [15, 0], [30, 14], [45, 28], [300, 300], [310, 300.5]]      # + one ordinary overlapping pair
+    c["radius"] = 10.0
+    c["mass"] = [1.0, 1.0, 1.0, 1.0, 2.0, 3.0]
+    c["vel"] = [[0, 0], [0, 0], [0, 0], [0, 0], [1, 0], [-1, 0]]
+    return c
+
+
+def test_oracle_chain_propagates_through_four_bodies():
+    b = chain_scene()
+    out, npairs, nres = O.orc_collide(b)
+    assert nres == 4                                    # (A,B), (B,C), (C,D) and the ordinary pair
+    assert not np.array_equal(out["pos"][3], b["pos"][3])     # D moved although neither C nor D touched anything at first
+
+
+@pytest.mark.gpu
+def test_gpu_chain_of_four_equals_oracle():
+    """the kept pairs must be closed over chains (connected components of the sweep-pair graph), not
+    just one hop away from an overlapping pair"""
+    b = chain_scene()
+    want, _, nres = O.orc_collide(b)
+    with Simulation(b, dims=2, eps=1.0, collide=1) as s:
+        s.collide()
+        out = s.bodies.copy()
+        _, res = s.collide_stats()
+    assert res == nres == 4
+    assert np.array_equal(bits(out["pos"]), bits(want["pos"])) and np.array_equal(bits(out["vel"]), bits(want["vel"]))
+
+
+@pytest.mark.gpu
+def test_gpu_collision_buffer_overflow_is_reported():
+    """a body spanning more than 4096 grid cells abandons the pass: sync / download must say so"""
+    from nbodysim_b200.simulation import NbodyError
+
+    b = scene(500, 1500, 25, 4)
+    b["radius"][7] = 1.0e5
+    with Simulation(b, dims=2, eps=1.0, collide=1) as s:
+        s.collide()
+        with pytest.raises(NbodyError) as ei:
+            s.sync()
+        assert ei.value.code == capi.ESTATE and "overflow" in str(ei.value)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sort_impl", [0, 2])
 def test_gpu_full_reference_step_bitexact_vs_golden(sort_impl):

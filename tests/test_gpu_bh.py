@@ -228,3 +228,38 @@ def test_octree_fast_accuracy_and_energy():
         s.step(200)
         k1, w1, _ = s.energy()
     assert abs((k1 + w1 - k0 - w0) / (k0 + w0)) < 1e-3
+
+
+def close_pairs_scene(n_pairs=600, seed=31):
+    """every body has a twin two ulps away: each pair hangs from a chain of ~20 single-child cells, so the tree needs
+    far more than the default 4 cells per body"""
+    r = np.random.default_rng(seed)
+    from nbodysim_b200.bodies import empty_bodies
+
+    b = empty_bodies(2 * n_pairs)
+    p = r.uniform(500.0, 1000.0, (n_pairs, 2)).astype(np.float32)
+    b["pos"][0::2] = p
+    b["pos"][1::2] = np.nextafter(np.nextafter(p, np.float32(2000)), np.float32(2000))
+    b["mass"] = r.uniform(0.5, 2.0, 2 * n_pairs).astype(np.float32)
+    return b
+
+
+def test_bh_cell_overflow_is_reported_and_capacity_can_be_raised(monkeypatch):
+    """a tree that needs more cells than reserved must not truncate forces silently"""
+    from nbodysim_b200.simulation import NbodyError
+
+    b = close_pairs_scene()
+    ncells = oracle_preorder(O.orc_bh_build(b)).shape[0]
+    assert ncells > 4 * b.shape[0] + 1024
+    monkeypatch.delenv("NBODY_BH_NODE_FACTOR", raising=False)
+    with bh_sim(b, theta=1.0, eps=1.0) as s:
+        s.attract()
+        with pytest.raises(NbodyError) as ei:
+            s.sync()
+        assert ei.value.code == capi.ENOMEM and "NBODY_BH_NODE_FACTOR" in str(ei.value)
+    monkeypatch.setenv("NBODY_BH_NODE_FACTOR", "33")
+    with bh_sim(b, theta=1.0, eps=1.0) as s:
+        s.attract()
+        out = s.download()["acc"].copy()
+        assert s.info()["bh_nodes"] == ncells
+    assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, 1.0, 1.0)))

@@ -84,3 +84,19 @@ def test_c_driver_no_argument_run_is_the_reference_simulation(tmp_path):
     inside = (want["pos"].astype(np.float64) ** 2).sum(1) < (0.79e5) ** 2     # beyond: expf differs by an ulp
     assert np.array_equal(bits(got["pos"][inside]), bits(want["pos"][inside]))
     np.testing.assert_allclose(got["pos"], want["pos"], rtol=2e-6, atol=1e-3)
+
+
+def test_viewer_hand_off_threads():
+    """host/nbody_viewer_feed.c: simulation thread (step, then download under the lock = `SHARED_BODIES =
+    simulation->bodies`, main.cpp:612-635) next to a 60 Hz consumer thread; no torn or failed frames"""
+    import json
+
+    exe = os.path.join(ROOT, "host", "_build", "nbody_viewer_feed")
+    if not os.path.exists(exe):
+        pytest.skip("host/_build/nbody_viewer_feed not built (make host)")
+    r = subprocess.run([exe, "--seconds", "1.5"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["failed"] == 0 and d["bad_frames"] == 0 and d["n"] == 25000
+    assert d["steps"] >= 100 and d["render_frames"] >= 30          # >= ~70 steps/s and the 60 Hz consumer kept running
+    assert d["publish_ms"] < 5.0
