@@ -26,8 +26,9 @@
 // Limits: bodies whose positions agree in all 32 levels are merged like the reference's coincident
 // bodies (`pos == existing_pos`, masses added in index order); the reference would subdivide
 // further if their positions differ beyond that depth.
-#include "kernels.h"
+#include "force_f32_fast.cuh"      // integrate_body_f32
 #include "radix_sort.cuh"
+#include "cluster_prims.cuh"
 #include <cstring>
 
 namespace nb {
@@ -340,6 +341,261 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
     }
 }
 
+// ---- the whole build as ONE cluster kernel (small scenes) ----------------------------------------------------------------
+// Same tree, same bits as the launch-per-phase build above (tests compare both with the oracle); what changes is the
+// execution model: one thread-block cluster walks through the phases, separated by hardware cluster barriers.
+//   box -> root | keys | 8-digit stable radix sort (cluster_prims.cuh) | cells per body + scan -> node offsets |
+//   chains: every body emits the cells of its path that first appear with it | per CELL: skip pointer, parent and
+//   quadrant (gallop + bisect on the sorted keys -- one thread per cell, so the few large cells near the root no
+//   longer serialise in the thread of body 0) | centres of mass level by level, deepest first: a finished cell
+//   deposits (position, mass) in its parent's slot for its quadrant, the next level sums its occupied slots in
+//   quadrant order -- Quadtree::propagate's arithmetic and order, with a cluster barrier per level instead of
+//   atomics-and-fences per cell.
+struct BhClusterArgs {
+    const float *posm;
+    unsigned n, cap;
+    BhRoot *root;
+    unsigned long long *keys_a, *keys_b;      // the sorted keys end up in keys_a / idx_a
+    unsigned *idx_a, *idx_b;
+    unsigned *count, *offs;                   // n + 1 words each
+    unsigned char *first, *leaf;
+    unsigned *owner;                          // per cell: the sorted body that owns it
+    unsigned *occ;                            // per cell: occupied quadrants (bit q)
+    BhNodes nodes;
+    unsigned *status;
+};
+
+template <int DIMS>
+__global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const BhClusterArgs a)
+{
+    constexpr int BITS = BhT<DIMS>::BITS, LEVELS = BhT<DIMS>::LEVELS;
+    constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    ClSmem &sm = *reinterpret_cast<ClSmem *>(cl_smem_raw);
+    const unsigned rank = cl_rank(), nc = cl_size(), tid = threadIdx.x, lane = tid & 31;
+    const unsigned gtid = rank * CL_THREADS + tid, gthreads = nc * CL_THREADS;
+    const unsigned n = a.n;
+
+    // ---- bounding box -> root quad (Quad::new_containing, Quad.hpp:40-44); same order-preserving keys as bh_bbox_kernel
+    {
+        unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+        for (unsigned i = gtid; i < n; i += gthreads) {
+            const size_t g = blk_index(i, 0);
+#pragma unroll
+            for (int c = 0; c < DIMS; ++c) { const unsigned k = f2ord(a.posm[g + c * BLK]); lo[c] = min(lo[c], k); hi[c] = max(hi[c], k); }
+        }
+        if (tid < 6) sm.xchg[8 + tid] = (tid < 3) ? 0xffffffffu : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < DIMS; ++c) {
+            lo[c] = __reduce_min_sync(0xffffffffu, lo[c]);
+            hi[c] = __reduce_max_sync(0xffffffffu, hi[c]);
+            if (lane == 0) { atomicMin(&sm.xchg[8 + c], lo[c]); atomicMax(&sm.xchg[11 + c], hi[c]); }
+        }
+        cl_sync();
+        if (tid < 6) {
+            unsigned v = (tid < 3) ? 0xffffffffu : 0u;
+            for (unsigned c = 0; c < nc; ++c) { const unsigned r = cl_ld_u32(&sm.xchg[8 + tid], c); v = (tid < 3) ? min(v, r) : max(v, r); }
+            sm.misc[4 + tid] = (tid < 3) ? ~v : v;          // bh_root_from_box expects the minima complemented
+        }
+        __syncthreads();
+    }
+    const BhRoot root = bh_root_from_box<DIMS>(&sm.misc[4]);
+    if (gtid == 0) *a.root = root;
+
+    // ---- quadrant-path keys; clear the occupancy words
+    for (unsigned i = gtid; i < n; i += gthreads) {
+        const size_t g = blk_index(i, 0);
+        const float x = a.posm[g], y = a.posm[g + BLK], z = (DIMS == 3) ? a.posm[g + 2 * BLK] : 0.f;
+        float cx = root.cx, cy = root.cy, cz = root.cz, size = root.size;
+        unsigned long long k = 0;
+#pragma unroll 4
+        for (int l = 0; l < LEVELS; ++l) k = (k << BITS) | bh_descend<DIMS>(x, y, z, cx, cy, cz, size);
+        k <<= BhT<DIMS>::ALIGN;
+        __stcg(a.keys_a + i, k);
+        __stcg(a.idx_a + i, i);
+    }
+    for (unsigned c = gtid; c < a.cap; c += gthreads) a.occ[c] = 0u;
+    cl_sync();
+
+    // ---- stable sort of (key, body); the result is brought back to the a-buffers
+    unsigned long long *keys = a.keys_a;
+    unsigned *idx = a.idx_a;
+    if (cl_radix_sort<true>(sm, a.keys_a, a.keys_b, a.idx_a, a.idx_b, n, 0, 64)) {
+        for (unsigned i = gtid; i < n; i += gthreads) { __stcg(a.keys_a + i, __ldcg(a.keys_b + i)); __stcg(a.idx_a + i, __ldcg(a.idx_b + i)); }
+        cl_sync();
+    }
+
+    // ---- cells owned by each sorted body (see bh_count_kernel), deepest leaf, exclusive scan -> node offsets
+    unsigned maxd = 0;
+    for (unsigned s = gtid; s < n; s += gthreads) {
+        const unsigned long long k = __ldcg(keys + s);
+        unsigned cnt = 0, firstd = 0, leafd = 0;
+        if (!(s > 0 && __ldcg(keys + s - 1) == k)) {
+            const int lp = (s > 0) ? lcp_levels<DIMS>(__ldcg(keys + s - 1), k) : -1;
+            unsigned t = s + 1;
+            while (t < n && __ldcg(keys + t) == k) ++t;                  // skip the run of coincident bodies
+            const int ln = (t < n) ? lcp_levels<DIMS>(k, __ldcg(keys + t)) : -1;
+            leafd = (lp < 0 && ln < 0) ? 0u : (unsigned)(max(lp, ln) + 1);
+            firstd = (unsigned)(lp + 1);
+            cnt = leafd - firstd + 1;
+        }
+        a.count[s] = cnt; a.first[s] = (unsigned char)firstd; a.leaf[s] = (unsigned char)leafd;
+        maxd = max(maxd, leafd);
+    }
+    if (gtid == 0) a.count[n] = 0;
+    if (tid == 0) sm.xchg[1] = 0;
+    __syncthreads();
+    maxd = __reduce_max_sync(0xffffffffu, maxd);
+    if (lane == 0) atomicMax(&sm.xchg[1], maxd);
+    cl_sync();                                                            // count[] complete, per-CTA maxima published
+    {
+        unsigned m = 0;
+        for (unsigned c = 0; c < nc; ++c) m = max(m, cl_ld_u32(&sm.xchg[1], c));
+        maxd = m;
+    }
+    const unsigned ncells = cl_excl_scan(sm, a.count, a.offs, n + 1);     // offs[n] = number of cells; ends with a barrier
+    const unsigned m_cells = min(ncells, a.cap);
+    if (gtid == 0 && ncells > a.cap && a.status) *reinterpret_cast<volatile unsigned *>(a.status) = 1u;
+
+    // ---- chains: position / mass of the leaf, size^2, cell geometry, owner
+    for (unsigned s = gtid; s < n; s += gthreads) {
+        const unsigned cnt = a.count[s];
+        if (cnt == 0) continue;
+        const unsigned long long k = __ldcg(keys + s);
+        const unsigned body = __ldcg(idx + s);
+        const size_t g = blk_index(body, 0);
+        const float x = a.posm[g], y = a.posm[g + BLK], z = (DIMS == 3) ? a.posm[g + 2 * BLK] : 0.f;
+        float mass = a.posm[g + 3 * BLK];                              // coincident bodies merge in body-index order (insert() :56-60)
+        for (unsigned t = s + 1; t < n && __ldcg(keys + t) == k; ++t) mass = __fadd_rn(mass, a.posm[blk_index(__ldcg(idx + t), 0) + 3 * BLK]);
+        const int firstd = a.first[s], leafd = a.leaf[s];
+        const unsigned off = __ldcg(a.offs + s);
+        float cx = root.cx, cy = root.cy, cz = root.cz, size = root.size;
+        for (int d = 0; d <= leafd; ++d) {
+            if (d >= firstd) {
+                const unsigned c = off + (unsigned)(d - firstd);
+                if (c < a.cap) {
+                    const bool is_leaf = (d == leafd);
+                    __stcg(a.nodes.data(c), make_float4(is_leaf ? x : 0.f, is_leaf ? y : 0.f, is_leaf ? mass : 0.f, __fmul_rn(size, size)));
+                    a.nodes.quad[c] = make_float4(cx, cy, size, cz);
+                    // aux is completed by the per-cell phase; the leaf's z rides in aux.x
+                    if (DIMS == 3) __stcg(reinterpret_cast<float *>(a.nodes.aux(c)), is_leaf ? z : 0.f);
+                    a.owner[c] = s;
+                }
+            }
+            if (d < leafd) {
+                const unsigned q = (unsigned)(k >> (64 - BITS * (d + 1))) & (NCHILD - 1u);
+                const float ns = __fmul_rn(size, 0.5f);
+                cx = __fadd_rn(cx, __fmul_rn((q & 1u) ? 0.5f : -0.5f, ns));
+                cy = __fadd_rn(cy, __fmul_rn((q & 2u) ? 0.5f : -0.5f, ns));
+                if (DIMS == 3) cz = __fadd_rn(cz, __fmul_rn((q & 4u) ? 0.5f : -0.5f, ns));
+                size = ns;
+            }
+        }
+    }
+    cl_sync();
+
+    // ---- per cell: skip pointer (first sorted body after the cell's span), parent, quadrant (see bh_emit_kernel)
+    for (unsigned c = gtid; c < m_cells; c += gthreads) {
+        const unsigned s = __ldcg(a.owner + c);
+        const unsigned long long k = __ldcg(keys + s);
+        const int firstd = a.first[s], leafd = a.leaf[s];
+        const int d = firstd + (int)(c - __ldcg(a.offs + s));
+        unsigned nx = 0;
+        if (d > 0) {
+            const int sh = 64 - BITS * d;
+            const unsigned long long p = k >> sh;
+            unsigned lo = s + 1, hi = n, step = 1;                       // first j in (s, n) with (keys[j] >> sh) > p
+            while (lo < hi) {
+                const unsigned probe = (lo + step - 1 < hi) ? lo + step - 1 : hi - 1;
+                if ((__ldcg(keys + probe) >> sh) > p) { hi = probe; break; }
+                lo = probe + 1;
+                step <<= 1;
+            }
+            while (lo < hi) {
+                const unsigned mid = (lo + hi) >> 1;
+                if ((__ldcg(keys + mid) >> sh) > p) hi = mid; else lo = mid + 1;
+            }
+            nx = (lo < n) ? __ldcg(a.offs + lo) : 0u;
+        }
+        unsigned par = 0xffffffffu;
+        if (d > firstd) par = c - 1;
+        else if (d == 1) par = 0u;
+        else if (d > 1) {
+            const int shp = 64 - BITS * (d - 1);
+            const unsigned long long pp = k >> shp;
+            unsigned lo = 0, hi = s, step = 1;                           // first j in [0, s] with (keys[j] >> shp) >= pp
+            while (lo < hi) {
+                const unsigned probe = (hi >= lo + step) ? hi - step : lo;
+                if ((__ldcg(keys + probe) >> shp) < pp) { lo = probe + 1; break; }
+                hi = probe;
+                step <<= 1;
+            }
+            while (lo < hi) {
+                const unsigned mid = (lo + hi) >> 1;
+                if ((__ldcg(keys + mid) >> shp) >= pp) hi = mid; else lo = mid + 1;
+            }
+            par = __ldcg(a.offs + lo) + (unsigned)(d - 1 - (int)a.first[lo]);
+        }
+        const unsigned qd = (d > 0) ? ((unsigned)(k >> (64 - BITS * d)) & (NCHILD - 1u)) : 0u;
+        if (par != 0xffffffffu && par < a.cap) atomicOr(&a.occ[par], 1u << qd);
+        uint4 *ax = a.nodes.aux(c);
+        reinterpret_cast<unsigned *>(ax)[1] = nx;
+        reinterpret_cast<unsigned *>(ax)[2] = (unsigned)d | ((d == leafd) ? 256u : 0u) | (qd << 9);
+        reinterpret_cast<unsigned *>(ax)[3] = par;
+        if (DIMS != 3) reinterpret_cast<unsigned *>(ax)[0] = 0u;
+    }
+    cl_sync();
+
+    // ---- centres of mass, deepest level first (Quadtree::propagate, :236-258)
+    for (int lvl = (int)maxd; lvl >= 0; --lvl) {
+        for (unsigned s = gtid; s < n; s += gthreads) {
+            if (a.count[s] == 0) continue;
+            const int firstd = a.first[s], leafd = a.leaf[s];
+            if (lvl < firstd || lvl > leafd) continue;
+            const unsigned c = __ldcg(a.offs + s) + (unsigned)(lvl - firstd);
+            if (c >= m_cells) continue;
+            float x, y, z = 0.f, mass;
+            const uint4 ax = __ldcg(a.nodes.aux(c));
+            if (lvl == leafd) {
+                const float4 d0 = __ldcg(a.nodes.data(c));
+                x = d0.x; y = d0.y; mass = d0.z;
+                if (DIMS == 3) z = __uint_as_float(ax.x);
+            } else {
+                const unsigned mask = __ldcg(a.occ + c);
+                float4 ch[NCHILD];
+#pragma unroll
+                for (unsigned q = 0; q < NCHILD; ++q)
+                    ch[q] = ((mask >> q) & 1u) ? __ldcg(&a.nodes.slots[(size_t)c * NCHILD + q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+#pragma unroll
+                for (unsigned q = 0; q < NCHILD; ++q) {
+                    if ((mask >> q) & 1u) {                              // children in quadrant order
+                        px = __fadd_rn(px, __fmul_rn(ch[q].x, ch[q].w));
+                        py = __fadd_rn(py, __fmul_rn(ch[q].y, ch[q].w));
+                        if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch[q].z, ch[q].w));
+                        ms = __fadd_rn(ms, ch[q].w);
+                    }
+                }
+                if (ms > 0.f) {                                          // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
+                    const float inv = __fdiv_rn(1.0f, ms);
+                    px = __fmul_rn(px, inv);
+                    py = __fmul_rn(py, inv);
+                    if (DIMS == 3) pz = __fmul_rn(pz, inv);
+                }
+                float4 dp = __ldcg(a.nodes.data(c));
+                dp.x = px; dp.y = py; dp.z = ms;
+                __stcg(a.nodes.data(c), dp);
+                if (DIMS == 3) __stcg(reinterpret_cast<float *>(a.nodes.aux(c)), pz);
+                x = px; y = py; z = pz; mass = ms;
+            }
+            const unsigned par = ax.w;
+            if (par != 0xffffffffu && par < m_cells) __stcg(&a.nodes.slots[(size_t)par * NCHILD + ((ax.z >> 9) & (NCHILD - 1u))], make_float4(x, y, z, mass));
+        }
+        cl_sync();
+    }
+}
+
 // one node record = one 256-bit load (sm_100: LDG.E.256); the array is read-only while the walk runs
 __device__ __forceinline__ void bh_load_node(const BhNodes &nodes, unsigned i, float4 &nd, uint4 &na)
 {
@@ -399,12 +655,44 @@ __device__ __forceinline__ bool bh_visit(const float4 nd, float ndz, bool is_lea
     return true;
 }
 
-template <int DIMS, bool REFCOMPAT>
-__global__ void __launch_bounds__(128)
+// ---- the per-thread walk ----------------------------------------------------------------------------------------------
+// One thread per target, targets in Z-order.  A walk is a chain of DEPENDENT node-record loads -- which record comes
+// next is known only after the opening test on the current one -- and at the reference's size (25,000 targets = 782
+// warps on 148 SMs) nothing hides their latency: the kernel's time is (longest chain in a warp) x (one L2 round trip).
+// The pre-order layout makes the chain mostly sequential (i -> i+1 when a cell is opened or a leaf is passed; a
+// jump i -> next[i] only when a far branch is accepted), so each thread keeps a private WINDOW of WIN consecutive
+// records (WIN x 32 bytes, aligned) in shared memory, filled by cp.async (LDGSTS: global -> shared without staging
+// registers), and consumes records from it until the walk leaves the window: one round trip per window instead of
+// one per record.  With PREFETCH the next sequential window is requested into a second buffer while the current one
+// is consumed.  The order of visits and of the fp32 additions is exactly Quadtree::acc's -- bit-exact as before.
+// shared-memory layout: chunk-major float4 [chunk][thread] -- a quarter-warp's LDS.128 covers all 32 banks whatever
+// chunk each lane reads.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// fused kick-drift epilogue (one GPU, small scenes): the walk thread integrates its own target -- scattered 4-byte
+// accesses, which at a few ten thousand bodies cost less than another launch
+struct BhFuse {
+    float *posm_next, *vel, *acc;
+    float G;
+    IntegParams ip;
+};
+
+constexpr int WALK_THREADS = 128;
+
+template <int DIMS, bool REFCOMPAT, bool FUSE, int WIN, bool PREFETCH>
+__global__ void __launch_bounds__(WALK_THREADS)
 bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-               float *__restrict__ accp, unsigned cap, unsigned long long *visits)
+               float *__restrict__ accp, unsigned cap, unsigned long long *visits, const BhFuse fz)
 {
+    constexpr int CH = 2 * WIN;                              // 16-byte chunks per window
+    __shared__ float4 cache[PREFETCH ? 2 : 1][CH][WALK_THREADS];
+    const int t = threadIdx.x;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const unsigned body = idx[s];                           // targets in Z-order: neighbouring threads walk alike
@@ -412,18 +700,48 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
     const size_t g = blk_index(body, 0);
     const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
     float ax = 0.f, ay = 0.f, az = 0.f;
-    unsigned i = 0, nvis = 0;
-    do {
-        float4 nd;
-        uint4 na;
-        bh_load_node(nodes, i, nd, na);
-        ++nvis;
-        if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
-        else i = i + 1;
-    } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (raises the status word)
-    const size_t l = blk_index(body - shard_start, 0);
-    accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = az;
+    unsigned i = 0, nvis = 0, base = 0;
+    int cur = 0;
+    auto fill = [&](int buf, unsigned b0) {
+        const float4 *src = nodes.rec + (size_t)b0 * 2;      // the array is padded by WIN records: a window never leaves it
+#pragma unroll
+        for (int c = 0; c < CH; ++c) cp_async16(&cache[buf][c][t], src + c);
+        cp_async_commit();
+    };
+    fill(0, 0);
+    for (;;) {
+        if (PREFETCH) { fill(cur ^ 1, base + WIN); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        do {                                                 // consume records while the walk stays inside the window
+            const unsigned c0 = (i - base) * 2;
+            const float4 nd = cache[cur][c0][t];
+            const uint4 na = *reinterpret_cast<const uint4 *>(&cache[cur][c0 + 1][t]);
+            ++nvis;
+            if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
+            else i = i + 1;
+        } while (i != 0 && i - base < (unsigned)WIN);       // pre-order: the walk only ever moves forward; 0 = end
+        if (i == 0 || i >= cap) break;                       // i >= cap only if the tree overflowed its reservation (status word)
+        const unsigned nb = i & ~(unsigned)(WIN - 1);
+        if (PREFETCH && nb == base + WIN) { cur ^= 1; base = nb; continue; }      // already on its way
+        if (PREFETCH) cp_async_wait<0>();                    // the discarded prefetch must land before its buffer is refilled
+        base = nb;
+        fill(cur, base);
+    }
+    if (PREFETCH) cp_async_wait<0>();
     if (visits) atomicAdd(visits, (unsigned long long)nvis);   // profiled steps only: node records visited (roofline)
+    if (!FUSE) {
+        const size_t l = blk_index(body - shard_start, 0);
+        accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = az;
+        return;
+    }
+    // Simulation::iterate after attract(): the same integrate_body_f32 as the stand-alone integrator, same operand order
+    const float gx = ax * fz.G, gy = ay * fz.G, gz = az * fz.G;
+    float qx = px, qy = py, qz = (DIMS == 3) ? pz : posm[g + 2 * BLK];
+    float vx = fz.vel[g], vy = fz.vel[g + BLK], vz = fz.vel[g + 2 * BLK];
+    integrate_body_f32(qx, qy, qz, vx, vy, vz, gx, gy, gz, fz.ip);
+    fz.posm_next[g] = qx; fz.posm_next[g + BLK] = qy; fz.posm_next[g + 2 * BLK] = qz; fz.posm_next[g + 3 * BLK] = posm[g + 3 * BLK];
+    fz.vel[g] = vx; fz.vel[g + BLK] = vy; fz.vel[g + 2 * BLK] = vz;
+    fz.acc[g] = gx; fz.acc[g + BLK] = gy; fz.acc[g + 2 * BLK] = gz;
 }
 
 // Warp-cooperative walk.  The 32 lanes of a warp hold 32 targets that are neighbours in Z-order; the
@@ -482,18 +800,28 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
 // neighbour than to everything else (each such pair hangs from a chain of single-child cells).  `node_factor` x n
 // cells are reserved (default 4; environment NBODY_BH_NODE_FACTOR); a tree that needs more raises the context's
 // sticky status instead of being truncated silently.
-cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor)
+// cluster_mode: 0 = the single-cluster build for scenes of up to cluster_max_n bodies (if the device can host the
+// cluster), 1 = never, 2 = required (cudaErrorNotSupported otherwise)
+cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int cluster_mode, size_t cluster_max_n)
 {
     cudaError_t e;
     n_cap = n;
     dims = dims_;
+    cluster_ctas = 0;
+    if (cluster_mode != 1) {
+        const int avail = cluster_ctas_available(dims_);
+        const size_t lim = std::min<size_t>((size_t)avail * CL_MAX_CHUNK, cluster_mode == 2 ? (size_t)-1 : cluster_max_n);
+        if (avail > 0 && n <= lim) cluster_ctas = avail;
+        else if (cluster_mode == 2) return cudaErrorNotSupported;
+    }
     node_cap = (unsigned)std::min<size_t>((size_t)(std::max(1.0, std::min(node_factor, 33.0)) * (double)n) + 1024, 0x7fffffffu);
 #define BH_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
     BH_ALLOC(root, sizeof(BhRoot))
     BH_ALLOC(keys_in, n * 8) BH_ALLOC(keys, n * 8) BH_ALLOC(idx_in, n * 4) BH_ALLOC(idx, n * 4)
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
-    BH_ALLOC(node_data, (size_t)node_cap * 32) BH_ALLOC(node_quad, (size_t)node_cap * 16)
+    BH_ALLOC(node_data, ((size_t)node_cap + 16) * 32) BH_ALLOC(node_quad, (size_t)node_cap * 16)
     BH_ALLOC(node_slots, (size_t)node_cap * (dims == 3 ? 8 : 4) * 16)
+    BH_ALLOC(node_owner, (size_t)node_cap * 4)
     // everything that must be zero at the start of a build lives in ONE region cleared by one memset per step:
     // bounding box | radix-sort scratch (histograms, tickets, status words) | scan scratch | arrival counters
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -510,7 +838,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor)
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, zero_region};
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_owner, zero_region};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -551,11 +879,68 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     return cudaGetLastError();
 }
 
+// How many CTAs the single-cluster kernels run with on this device: 16 (non-portable size) if a cluster of 16 can be
+// resident, else 8; 0 if not even that (then only the launch-per-phase path exists).
+template <typename K>
+static int cluster_ctas_for(K kernel, size_t smem)
+{
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const bool np_ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!np_ok) cudaGetLastError();
+    for (int nc = np_ok ? 16 : 8; nc >= 8; nc -= 8) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)nc); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)nc; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) == cudaSuccess && nclusters >= 1) return nc;
+        cudaGetLastError();
+    }
+    return 0;
+}
+
+template <typename K, typename A>
+static cudaError_t launch_cluster(K kernel, int nc, size_t smem, const A &args, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)nc); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = (unsigned)nc; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
+int BhWorkspace::cluster_ctas_available(int dims_)
+{
+    return dims_ == 3 ? cluster_ctas_for(bh_build_cluster_kernel<3>, sizeof(ClSmem)) : cluster_ctas_for(bh_build_cluster_kernel<2>, sizeof(ClSmem));
+}
+
 // Build the tree of the first n bodies of `posm`.  Fully asynchronous (no host read-back): the node count
 // stays on the device (offs[n]); n_nodes is fetched lazily by node_count().
 cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int *launches)
 {
     if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
+    if (cluster_ctas > 0 && n <= (size_t)cluster_ctas * CL_MAX_CHUNK) {        // small scene: the whole build is one cluster kernel
+        BhClusterArgs a;
+        a.posm = posm; a.n = (unsigned)n; a.cap = node_cap; a.root = (BhRoot *)root;
+        a.keys_a = (unsigned long long *)keys_in; a.keys_b = (unsigned long long *)keys;
+        a.idx_a = (unsigned *)idx_in; a.idx_b = (unsigned *)idx;
+        a.count = (unsigned *)count; a.offs = (unsigned *)offs; a.first = (unsigned char *)first; a.leaf = (unsigned char *)leaf;
+        a.owner = (unsigned *)node_owner; a.occ = (unsigned *)node_arrive; a.nodes = bh_nodes(*this); a.status = status;
+        const cudaError_t e = dims == 3 ? launch_cluster(bh_build_cluster_kernel<3>, cluster_ctas, sizeof(ClSmem), a, st)
+                                        : launch_cluster(bh_build_cluster_kernel<2>, cluster_ctas, sizeof(ClSmem), a, st);
+        if (e != cudaSuccess) return e;
+        std::swap(keys_in, keys);                                              // the sorted pairs are in the a-buffers
+        std::swap(idx_in, idx);
+        count_valid = false;
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     return dims == 3 ? bh_build_t<3>(*this, posm, n, st, launches) : bh_build_t<2>(*this, posm, n, st, launches);
 }
 
@@ -574,28 +959,48 @@ cudaError_t BhWorkspace::node_count(size_t n, cudaStream_t st, unsigned *out)
     return n_nodes > node_cap ? cudaErrorMemoryAllocation : cudaSuccess;   // pathological depth: more cells than reserved
 }
 
-template <int DIMS>
+template <int DIMS, bool FUSE>
 static void bh_walk_t(const BhWorkspace &w, const float *posm, size_t n, float t_sq, float e_sq, bool refcompat, int fix,
-                      size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, cudaStream_t st)
+                      size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, const BhFuse &fz, cudaStream_t st)
 {
     const unsigned g = (unsigned)((n + 127) / 128);
     const unsigned *idx = (const unsigned *)w.idx;
     const BhNodes nd = bh_nodes(w);
-    if (w.warp_walk) {
+    if (w.warp_walk && !FUSE) {
         if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
         else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
-    } else {
-        if (refcompat) bh_walk_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits);
-        else bh_walk_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits);
+        return;
     }
+#define BH_WALK(RC, WIN, PF) bh_walk_kernel<DIMS, RC, FUSE, WIN, PF><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz)
+    // window variant: 0 = 4 records, 1 = 8 records, 2 = 4 records + prefetch (tuning: NBODY_BH_WALK_VARIANT)
+    switch (w.walk_variant * 2 + (refcompat ? 1 : 0)) {
+    case 0: BH_WALK(false, 4, false); break;
+    case 1: BH_WALK(true, 4, false); break;
+    case 2: BH_WALK(false, 8, false); break;
+    case 3: BH_WALK(true, 8, false); break;
+    case 4: BH_WALK(false, 4, true); break;
+    default: BH_WALK(true, 4, true); break;
+    }
+#undef BH_WALK
 }
 
+// `fuse` != nullptr: the walk threads also integrate their targets (kick-drift; one GPU, whole array = one shard)
 cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
-                              size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, cudaStream_t st)
+                              size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits,
+                              const BhFuseArgs *fuse, cudaStream_t st)
 {
     const float t_sq = theta * theta, e_sq = eps * eps;       // Quadtree ctor, Quadtree.hpp:19
-    if (dims == 3) bh_walk_t<3>(*this, posm, n, t_sq, e_sq, refcompat, fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, visits, st);
-    else bh_walk_t<2>(*this, posm, n, t_sq, e_sq, refcompat, fix_near_leaves ? 1 : 0, shard_start, shard_count, accp, visits, st);
+    const int fix = fix_near_leaves ? 1 : 0;
+    BhFuse fz;
+    memset(&fz, 0, sizeof fz);
+    if (fuse) { fz.posm_next = fuse->posm_next; fz.vel = fuse->vel; fz.acc = fuse->acc; fz.G = fuse->G; fz.ip = fuse->ip; }
+    if (fuse) {
+        if (dims == 3) bh_walk_t<3, true>(*this, posm, n, t_sq, e_sq, refcompat, fix, shard_start, shard_count, accp, visits, fz, st);
+        else bh_walk_t<2, true>(*this, posm, n, t_sq, e_sq, refcompat, fix, shard_start, shard_count, accp, visits, fz, st);
+    } else {
+        if (dims == 3) bh_walk_t<3, false>(*this, posm, n, t_sq, e_sq, refcompat, fix, shard_start, shard_count, accp, visits, fz, st);
+        else bh_walk_t<2, false>(*this, posm, n, t_sq, e_sq, refcompat, fix, shard_start, shard_count, accp, visits, fz, st);
+    }
     return cudaGetLastError();
 }
 

@@ -23,6 +23,8 @@
 // The phases are written as grid-stride device functions so that the same code runs either as one kernel
 // per phase (any n) or inside the single-cluster kernel of small scenes (cluster barriers between phases).
 #include "collide.cuh"
+#include "cluster_prims.cuh"
+#include <cstring>
 
 namespace nb {
 
@@ -55,9 +57,73 @@ __global__ void __launch_bounds__(128) col_resolve_kernel(ColArgs a, const unsig
     col_phase_resolve(a, pairs_sorted, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-cudaError_t CollideWorkspace::alloc(size_t n)
+// ---- the whole pass as ONE cluster kernel (small scenes): the same phases, separated by cluster barriers; a step
+// without overlapping pairs -- the common case -- ends after the detect phase.
+__global__ void __launch_bounds__(CL_THREADS, 1)
+col_cluster_kernel(ColArgs a, unsigned long long *keys_b, unsigned *vals_b, unsigned long long *pairs_b, int key_bits)
+{
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    ClSmem &sm = *reinterpret_cast<ClSmem *>(cl_smem_raw);
+    const unsigned nc = cl_size();
+    const unsigned gtid = cl_rank() * CL_THREADS + threadIdx.x, gthreads = nc * CL_THREADS;
+    col_phase_init(a, gtid, gthreads);
+    cl_sync();
+    col_phase_entries(a, gtid, gthreads);
+    cl_sync();
+    const unsigned ne = min(__ldcg(a.counters + 0), a.entry_cap);
+    if (ne > nc * CL_MAX_CHUNK && gtid == 0) col_overflow(a);            // more cell entries than the cluster sort holds
+    if (__ldcg(a.counters + 2) || ne > nc * CL_MAX_CHUNK) return;         // uniform: every thread reads the same words
+    if (cl_radix_sort<true>(sm, a.keys_in, keys_b, a.vals_in, vals_b, ne, 0, 32)) { a.keys = keys_b; a.vals = vals_b; }
+    else { a.keys = a.keys_in; a.vals = a.vals_in; }
+    col_phase_pairs<0>(a, gtid, gthreads);
+    cl_sync();
+    if (__ldcg(a.counters + 4) == 0) return;                              // nothing overlaps: no resolve could pass its test
+    col_phase_pairs<1>(a, gtid, gthreads);
+    cl_sync();
+    col_phase_mark(a, gtid, gthreads);
+    cl_sync();
+    col_phase_pairs<2>(a, gtid, gthreads);
+    cl_sync();
+    const unsigned np = __ldcg(a.counters + 1);
+    if ((np > a.pair_cap || np > nc * CL_MAX_CHUNK) && gtid == 0) col_overflow(a);
+    if (__ldcg(a.counters + 2) || np > a.pair_cap || np > nc * CL_MAX_CHUNK) return;
+    const unsigned long long *sorted = cl_radix_sort<false>(sm, a.pairs, pairs_b, nullptr, nullptr, np, 0, key_bits) ? pairs_b : a.pairs;
+    col_phase_resolve(a, sorted, gtid, gthreads);
+}
+
+int CollideWorkspace::cluster_ctas_available()
+{
+    auto kernel = col_cluster_kernel;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClSmem)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const bool np_ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!np_ok) cudaGetLastError();
+    for (int nc = np_ok ? 16 : 8; nc >= 8; nc -= 8) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)nc); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClSmem);
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)nc; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) == cudaSuccess && nclusters >= 1) return nc;
+        cudaGetLastError();
+    }
+    return 0;
+}
+
+// cluster_mode as BhWorkspace::alloc
+cudaError_t CollideWorkspace::alloc(size_t n, int cluster_mode, size_t cluster_max_n)
 {
     cudaError_t e;
+    cluster_ctas = 0;
+    if (cluster_mode != 1) {
+        const int avail = cluster_ctas_available();
+        // the cell entries (about one per body, more for bodies that straddle cells) must fit the cluster sort
+        const size_t lim = std::min<size_t>((size_t)avail * CL_MAX_CHUNK / 2, cluster_mode == 2 ? (size_t)-1 : cluster_max_n);
+        if (avail > 0 && n <= lim) cluster_ctas = avail;
+        else if (cluster_mode == 2) return cudaErrorNotSupported;
+    }
     entry_cap = (unsigned)std::min<size_t>(4 * n + 4096, 0x7fffffffu);
     pair_cap = (unsigned)std::min<size_t>(64 * n + 65536, (size_t)16 << 20);   // pairs of hot components
 #define COL_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
@@ -105,6 +171,20 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
     cudaError_t e;
     unsigned *cnt = (unsigned *)counters;
+    if (cluster_ctas > 0) {                                  // small scene: one cluster kernel
+        ColArgs a = args(posm, vel, n);
+        const int key_bits = std::min(64, (((a.rooted ? 3 : 2) * a.idx_bits + 7) / 8) * 8);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)cluster_ctas); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClSmem); cfg.stream = st;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)cluster_ctas; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        if ((e = cudaLaunchKernelEx(&cfg, col_cluster_kernel, a, (unsigned long long *)keys, (unsigned *)vals, (unsigned long long *)pairs, key_bits)) != cudaSuccess) return e;
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     const unsigned gn = (unsigned)((n + 255) / 256), ge = (entry_cap + 255) / 256;
     ColArgs a = args(posm, vel, n);
     col_init_kernel<<<gn, 256, 0, st>>>(a);

@@ -112,6 +112,14 @@ cudaError_t launch_unpack_f64(double *pos3, double *vel3, double *acc3, size_t n
 cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, size_t shard_start,
                           size_t shard_count, double eps2, bool f64, double *out5, cudaStream_t st);
 
+// fused kick-drift epilogue of the Barnes-Hut walk (small scenes on one GPU): where the walk threads find velocities
+// and store the new state
+struct BhFuseArgs {
+    float *posm_next, *vel, *acc;
+    float G;
+    IntegParams ip;
+};
+
 // Barnes-Hut path (barnes_hut.cu): per-GPU workspace holding sorted keys and the pre-order node array
 struct BhWorkspace {
     size_t n_cap = 0;
@@ -119,6 +127,9 @@ struct BhWorkspace {
     void *root = nullptr, *box = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
     void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr, *node_slots = nullptr;   // node_data: one 32-byte record per node
+    void *node_owner = nullptr;  // single-cluster build: the sorted body that owns each cell
+    int cluster_ctas = 0;        // > 0: scenes of up to cluster_ctas x 49152 bodies are built by ONE cluster kernel of that many CTAs
+    static int cluster_ctas_available(int dims);
     int dims = 2;                // 2 = the reference's quadtree, 3 = octree
     unsigned *status = nullptr;  // host-visible sticky flags ([0] = more cells than reserved), owned by the context
     // cleared by one memset at the start of every build: box | sort scratch | scan scratch | arrival counters
@@ -126,14 +137,16 @@ struct BhWorkspace {
     size_t zero_bytes = 0;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
+    int walk_variant = 0;        // per-thread walk: record window 0 = 4, 1 = 8, 2 = 4 + prefetch of the next window
     unsigned walk_window = 256;  // warp-cooperative walk: how many records ahead of the slowest lane a lane may run
                                  // (sweep on B200, tools/bh_window_sweep.py: 256 is best or within 1 % of best everywhere)
-    cudaError_t alloc(size_t n, int dims, double node_factor);
+    cudaError_t alloc(size_t n, int dims, double node_factor, int cluster_mode, size_t cluster_max_n);
     cudaError_t node_count(size_t n, cudaStream_t st, unsigned *out);
     void release();
     cudaError_t build(const float *posm, size_t n, cudaStream_t st, int *launches);
     cudaError_t walk(const float *posm, size_t n, float theta, float eps, bool refcompat, bool fix_near_leaves,
-                     size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, cudaStream_t st);
+                     size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits,
+                     const BhFuseArgs *fuse, cudaStream_t st);
     cudaError_t download_nodes(float *f8, unsigned *u2, size_t cap, cudaStream_t st);
 };
 
@@ -146,7 +159,9 @@ struct CollideWorkspace {
     void *pairs_in = nullptr, *pairs = nullptr, *hot = nullptr, *parent = nullptr, *counters = nullptr, *temp = nullptr;
     size_t temp_bytes = 0;
     unsigned *status = nullptr;  // host-visible sticky flags ([1] = entry / pair buffers overflowed), owned by the context
-    cudaError_t alloc(size_t n);
+    int cluster_ctas = 0;        // > 0: the whole pass runs as ONE cluster kernel of that many CTAs (small scenes)
+    static int cluster_ctas_available();
+    cudaError_t alloc(size_t n, int cluster_mode, size_t cluster_max_n);
     void release();
     ColArgs args(float *posm, float *vel, size_t n) const;
     cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches);

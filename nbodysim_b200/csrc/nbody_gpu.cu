@@ -235,17 +235,32 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaHostAlloc((void **)&d.h_status, 64, cudaHostAllocMapped));
     memset(d.h_status, 0, 64);
     CU(cudaHostGetDevicePointer((void **)&d.d_status, d.h_status, 0));
+    size_t cl_max = 65536;                      // scenes up to this size run their build / collision pass as one cluster kernel (sort_impl = 0)
+    if (const char *cm = getenv("NBODY_CLUSTER_MAX_N")) cl_max = (size_t)std::max(0ll, atoll(cm));
     if (ctx->p.collide) {
-        CU(d.col.alloc(ctx->n));
+        const cudaError_t ce = d.col.alloc(ctx->n, ctx->p.sort_impl, cl_max);
+        if (ce == cudaErrorNotSupported) {
+            set_err(ctx, "sort_impl = 2 (single-cluster collision pass) needs a device that can host a cluster of >= 8 CTAs and n <= CTAs x 24576");
+            return NBODY_EINVAL;
+        }
+        CU(ce);
         d.col.status = d.d_status;
     }
     if (ctx->bh) {
         double factor = 4.0;
         if (const char *nf = getenv("NBODY_BH_NODE_FACTOR")) factor = atof(nf);
-        CU(d.bh.alloc(ctx->n, ctx->p.dims, factor));
+        {
+            const cudaError_t be = d.bh.alloc(ctx->n, ctx->p.dims, factor, ctx->p.sort_impl, cl_max);
+            if (be == cudaErrorNotSupported) {
+                set_err(ctx, "sort_impl = 2 (single-cluster build) needs a device that can host a cluster of >= 8 CTAs and n <= CTAs x 49152");
+                return NBODY_EINVAL;
+            }
+            CU(be);
+        }
         d.bh.status = d.d_status;
         d.bh.warp_walk = ctx->p.bh_walk == 2 || (ctx->p.bh_walk == 0 && (ctx->p.dims == 3 || ctx->p.theta < 0.7f));
         if (const char *ww = getenv("NBODY_BH_WALK_WINDOW")) d.bh.walk_window = (unsigned)std::max(1, atoi(ww));   // tuning override
+        if (const char *wv = getenv("NBODY_BH_WALK_VARIANT")) d.bh.walk_variant = std::min(2, std::max(0, atoi(wv)));
     }
     return NBODY_OK;
 }
@@ -368,7 +383,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         CU(cudaSetDevice(d.device));
         const bool prof = profile && (&d == &ctx->devs[0]);
         if (prof) CU(cudaEventRecord(d.ev_t[0], d.stream));
-        bool waited = false;
+        bool waited = false, bh_fused = false;
         if (ctx->bh) {
             if (d.gathered_pending) { CU(wait_remote(d)); waited = true; }
             int nl = 0;
@@ -377,8 +392,15 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
                 CU(cudaEventRecord(d.ev_t[3], d.stream));
                 CU(cudaMemsetAsync(d.walk_visits, 0, sizeof(unsigned long long), d.stream));
             }
+            // small scenes on one GPU: the walk threads integrate their own targets (no separate integrator launch)
+            bh_fused = ctx->world == 1 && !acc_only && !d.bh.warp_walk && ctx->n_padded <= 131072 && ctx->p.fuse_integrator != 0;
+            BhFuseArgs fa;
+            if (bh_fused) {
+                fa.posm_next = (float *)d.posm[d.cur ^ 1]; fa.vel = (float *)d.vel; fa.acc = (float *)d.acc;
+                fa.G = ctx->p.G; fa.ip = make_ip(ctx, dt);
+            }
             CU(d.bh.walk((const float *)d.posm[d.cur], ctx->n, ctx->p.theta, ctx->p.eps, refc, ctx->p.bh_fix_near_leaves != 0,
-                         d.shard_start, d.shard_count, (float *)d.accp, prof ? d.walk_visits : nullptr, d.stream));
+                         d.shard_start, d.shard_count, (float *)d.accp, prof ? d.walk_visits : nullptr, bh_fused ? &fa : nullptr, d.stream));
             ctx->launches += (unsigned long long)nl + 1;
         }
         for (const Range &r : d.plan) {
@@ -402,7 +424,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             CU(wait_remote(d));
         }
         if (prof) CU(cudaEventRecord(d.ev_t[1], d.stream));
-        const bool fused_now = d.fused && !acc_only && !ctx->f64 && !refc;
+        const bool fused_now = bh_fused || (d.fused && !acc_only && !ctx->f64 && !refc);
         if (!fused_now) {
             IntegLaunch I;
             memset(&I, 0, sizeof I);

@@ -65,7 +65,7 @@ def test_patched_reference_simulation_equals_unpatched_after_5_steps(tmp_path):
     assert np.array_equal(bits(got["acc"]), bits(want["acc"]))
     # bodies beyond the soft boundary go through expf (1-2 ulp between glibc and CUDA): bit-exact inside, tolerance outside
     inside = (start["pos"].astype(np.float64) ** 2).sum(1) < (0.79e5) ** 2
-    assert inside.sum() > 0.9 * N
+    assert inside.sum() > 0.8 * N
     for f in ("pos", "vel"):
         assert np.array_equal(bits(got[f][inside]), bits(want[f][inside])), f
     np.testing.assert_allclose(got["vel"], want["vel"], rtol=2e-6, atol=1e-6)
