@@ -182,6 +182,7 @@ struct BhNodes {
     float4 *rec;         // 2 x 16 bytes per node
     float4 *quad;        // cx, cy, size, cz (diagnostics / parity tests)
     float4 *slots;       // COM pass: (x, y, z, mass) of each completed child, [parent][quadrant]
+    unsigned *slot_cells; // COM pass: cells in that child's subtree (-> skip pointers), [parent][quadrant]
     __device__ __forceinline__ float4 *data(unsigned c) const { return rec + 2 * (size_t)c; }
     __device__ __forceinline__ uint4 *aux(unsigned c) const { return reinterpret_cast<uint4 *>(rec + 2 * (size_t)c + 1); }
 };
@@ -217,26 +218,9 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
                 const bool is_leaf = (d == leafd);
                 *nodes.data(c) = make_float4(is_leaf ? x : 0.f, is_leaf ? y : 0.f, is_leaf ? mass : 0.f, __fmul_rn(size, size));
                 nodes.quad[c] = make_float4(cx, cy, size, cz);
-                // skip pointer: first sorted body after s whose depth-d prefix differs
-                unsigned nx = 0;
-                if (d > 0) {
-                    const int sh = 64 - BITS * d;
-                    const unsigned long long p = k >> sh;
-                    // first j in (s, n) with (keys[j] >> sh) > p.  Most cells are deep and span a handful of
-                    // bodies, so gallop away from s (1, 2, 4, ... bodies) before bisecting the last stride.
-                    size_t lo = s + 1, hi = n, step = 1;
-                    while (lo < hi) {
-                        const size_t probe = (lo + step - 1 < hi) ? lo + step - 1 : hi - 1;
-                        if ((keys[probe] >> sh) > p) { hi = probe; break; }
-                        lo = probe + 1;
-                        step <<= 1;
-                    }
-                    while (lo < hi) {
-                        const size_t mid = (lo + hi) >> 1;
-                        if ((keys[mid] >> sh) > p) hi = mid; else lo = mid + 1;
-                    }
-                    nx = (lo < n) ? offs[lo] : 0u;
-                }
+                // the skip pointer (Node::next) = this cell's index + the number of cells in its subtree: filled in by the
+                // centre-of-mass pass, which accumulates subtree sizes on its way up -- no search over the sorted keys
+                const unsigned nx = 0;
                 // parent cell: the previous cell of this body's chain, or -- for the first owned cell -- the
                 // depth d-1 cell of the first sorted body that shares the (d-1)-prefix
                 unsigned par = 0xffffffffu;
@@ -278,14 +262,18 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
     }
 }
 
-// ---- 6. centres of mass (Quadtree::propagate, :236-258) -------------------------------------------------
+// ---- 6. centres of mass (Quadtree::propagate, :236-258) and skip pointers ------------------------------------------------
 // One launch, no level barriers: the thread of every leaf climbs towards the root.  A completed node deposits
-// (position, mass) into its parent's slot for its quadrant, then adds one arrival to the parent (bits 8..15 of
-// arrive[]; the low byte holds the number of children and bits 16.. the occupied quadrants, both counted by the
-// emit kernel) and stops unless it is the LAST child to arrive.  The last arriver reads the occupied slots --
-// independent loads of one contiguous line, no sibling chasing -- and sums them in quadrant order:
+// (position, mass) and the number of cells of its subtree into its parent's slot for its quadrant, then adds one
+// arrival to the parent (bits 8..15 of arrive[]; the low byte holds the number of children and bits 16.. the occupied
+// quadrants, both counted by the emit kernel) and stops unless it is the LAST child to arrive.  The last arriver reads
+// the occupied slots -- independent loads of one contiguous line, no sibling chasing -- and sums them in quadrant order:
 // `pos += child.pos * child.mass; mass += child.mass`, then `pos *= 1/mass` -- exactly the reference's arithmetic
 // and order (its empty leaves only ever add +0).  Slots written by other SMs are read with L1-bypassing loads.
+// Skip pointers (Node::next, Quadtree.hpp:71-75): in pre-order a subtree is a contiguous run of cells, so
+// next[c] = c + cells(subtree of c) (0 after the last cell) -- the subtree sizes ride up with the centres of mass,
+// which replaces a gallop-and-bisect search over the sorted keys per cell (the thread of the first body alone did
+// ~20 such searches, each up to 25 dependent loads: the emit kernel went 28 -> see profiles/ at n = 25,000).
 template <int DIMS>
 __global__ void __launch_bounds__(256)
 bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned char *__restrict__ first,
@@ -295,27 +283,37 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n || count[s] == 0) return;
-    const unsigned m = min(offs[n], cap);
+    const unsigned total = offs[n], m = min(total, cap);
     unsigned c = offs[s] + (unsigned)(leaf[s] - first[s]);           // this body's leaf cell (emitted by the previous launch)
     if (c >= m) return;
     uint4 a = __ldcg(nodes.aux(c));
     const float4 d0 = __ldcg(nodes.data(c));
     float x = d0.x, y = d0.y, z = (DIMS == 3) ? __uint_as_float(a.x) : 0.f, mass = d0.z;
+    unsigned cells = 1;                                               // cells in the subtree of c
+    reinterpret_cast<unsigned *>(nodes.aux(c))[1] = (c + 1u < total) ? c + 1u : 0u;
     for (;;) {
         const unsigned par = a.w;
         if (par == 0xffffffffu || par >= m) break;                     // reached the root
         const unsigned q = (a.z >> 9) & (NCHILD - 1u);
         __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, z, mass));
+        __stcg(&nodes.slot_cells[(size_t)par * NCHILD + q], cells);
         __threadfence();                                               // my deposit is visible before I announce it
         const unsigned old = atomicAdd(&arrive[par], 0x100u);
         if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;         // a sibling will arrive later and do the work
         __threadfence();
         const unsigned mask = (old >> 16) & 0xffu;
         float4 ch[NCHILD];
+        unsigned sub[NCHILD];
 #pragma unroll
-        for (unsigned k = 0; k < NCHILD; ++k)
-            ch[k] = ((mask >> k) & 1u) ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned k = 0; k < NCHILD; ++k) {
+            const bool occ = (mask >> k) & 1u;
+            ch[k] = occ ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sub[k] = occ ? __ldcg(&nodes.slot_cells[(size_t)par * NCHILD + k]) : 0u;
+        }
+        a = __ldcg(nodes.aux(par));                                    // independent of the sums below: issued with the slots
+        float4 dp = __ldcg(nodes.data(par));
         float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+        cells = 1;
 #pragma unroll
         for (unsigned k = 0; k < NCHILD; ++k) {
             if ((mask >> k) & 1u) {                                    // children in quadrant order
@@ -323,6 +321,7 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
                 py = __fadd_rn(py, __fmul_rn(ch[k].y, ch[k].w));
                 if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch[k].z, ch[k].w));
                 ms = __fadd_rn(ms, ch[k].w);
+                cells += sub[k];
             }
         }
         if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
@@ -331,11 +330,10 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
             py = __fmul_rn(py, inv);
             if (DIMS == 3) pz = __fmul_rn(pz, inv);
         }
-        a = __ldcg(nodes.aux(par));
-        float4 dp = __ldcg(nodes.data(par));
         dp.x = px; dp.y = py; dp.z = ms;
         __stcg(nodes.data(par), dp);
         if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(par)), pz);
+        reinterpret_cast<unsigned *>(nodes.aux(par))[1] = (par + cells < total) ? par + cells : 0u;
         x = px; y = py; z = pz; mass = ms;
         c = par;
     }
@@ -363,11 +361,14 @@ struct BhClusterArgs {
     unsigned *occ;                            // per cell: occupied quadrants (bit q)
     BhNodes nodes;
     unsigned *status;
+    long long *trace;                         // tuning (NBODY_CLUSTER_TRACE): SM clock of CTA 0 after every phase, else null
 };
 
 template <int DIMS>
 __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const BhClusterArgs a)
 {
+    int trace_k = 0;
+#define BH_TRACE() do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[trace_k] = clock64(); ++trace_k; } while (0)
     constexpr int BITS = BhT<DIMS>::BITS, LEVELS = BhT<DIMS>::LEVELS;
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
     extern __shared__ __align__(16) unsigned char cl_smem_raw[];
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
     const unsigned rank = cl_rank(), nc = cl_size(), tid = threadIdx.x, lane = tid & 31;
     const unsigned gtid = rank * CL_THREADS + tid, gthreads = nc * CL_THREADS;
     const unsigned n = a.n;
+    BH_TRACE();   // 0: start
 
     // ---- bounding box -> root quad (Quad::new_containing, Quad.hpp:40-44); same order-preserving keys as bh_bbox_kernel
     {
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
     }
     const BhRoot root = bh_root_from_box<DIMS>(&sm.misc[4]);
     if (gtid == 0) *a.root = root;
+    BH_TRACE();   // 1: box
 
     // ---- quadrant-path keys; clear the occupancy words
     for (unsigned i = gtid; i < n; i += gthreads) {
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
     }
     for (unsigned c = gtid; c < a.cap; c += gthreads) a.occ[c] = 0u;
     cl_sync();
+    BH_TRACE();   // 1: keys
 
     // ---- stable sort of (key, body); the result is brought back to the a-buffers
     unsigned long long *keys = a.keys_a;
@@ -426,6 +430,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
         cl_sync();
     }
 
+    BH_TRACE();   // 2: sort
     // ---- cells owned by each sorted body (see bh_count_kernel), deepest leaf, exclusive scan -> node offsets
     unsigned maxd = 0;
     for (unsigned s = gtid; s < n; s += gthreads) {
@@ -454,7 +459,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
         for (unsigned c = 0; c < nc; ++c) m = max(m, cl_ld_u32(&sm.xchg[1], c));
         maxd = m;
     }
+    BH_TRACE();   // 3: count
     const unsigned ncells = cl_excl_scan(sm, a.count, a.offs, n + 1);     // offs[n] = number of cells; ends with a barrier
+    BH_TRACE();   // 4: scan
     const unsigned m_cells = min(ncells, a.cap);
     if (gtid == 0 && ncells > a.cap && a.status) *reinterpret_cast<volatile unsigned *>(a.status) = 1u;
 
@@ -494,6 +501,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
         }
     }
     cl_sync();
+    BH_TRACE();   // 5: chains
 
     // ---- per cell: skip pointer (first sorted body after the cell's span), parent, quadrant (see bh_emit_kernel)
     for (unsigned c = gtid; c < m_cells; c += gthreads) {
@@ -546,6 +554,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
         if (DIMS != 3) reinterpret_cast<unsigned *>(ax)[0] = 0u;
     }
     cl_sync();
+    BH_TRACE();   // 6: cells
 
     // ---- centres of mass, deepest level first (Quadtree::propagate, :236-258)
     for (int lvl = (int)maxd; lvl >= 0; --lvl) {
@@ -593,7 +602,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
             if (par != 0xffffffffu && par < m_cells) __stcg(&a.nodes.slots[(size_t)par * NCHILD + ((ax.z >> 9) & (NCHILD - 1u))], make_float4(x, y, z, mass));
         }
         cl_sync();
+        BH_TRACE();   // 7 + k: level maxd - k
     }
+#undef BH_TRACE
 }
 
 // one node record = one 256-bit load (sm_100: LDG.E.256); the array is read-only while the walk runs
@@ -658,22 +669,11 @@ __device__ __forceinline__ bool bh_visit(const float4 nd, float ndz, bool is_lea
 // ---- the per-thread walk ----------------------------------------------------------------------------------------------
 // One thread per target, targets in Z-order.  A walk is a chain of DEPENDENT node-record loads -- which record comes
 // next is known only after the opening test on the current one -- and at the reference's size (25,000 targets = 782
-// warps on 148 SMs) nothing hides their latency: the kernel's time is (longest chain in a warp) x (one L2 round trip).
-// The pre-order layout makes the chain mostly sequential (i -> i+1 when a cell is opened or a leaf is passed; a
-// jump i -> next[i] only when a far branch is accepted), so each thread keeps a private WINDOW of WIN consecutive
-// records (WIN x 32 bytes, aligned) in shared memory, filled by cp.async (LDGSTS: global -> shared without staging
-// registers), and consumes records from it until the walk leaves the window: one round trip per window instead of
-// one per record.  With PREFETCH the next sequential window is requested into a second buffer while the current one
-// is consumed.  The order of visits and of the fp32 additions is exactly Quadtree::acc's -- bit-exact as before.
-// shared-memory layout: chunk-major float4 [chunk][thread] -- a quarter-warp's LDS.128 covers all 32 banks whatever
-// chunk each lane reads.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+// warps on 148 SMs) nothing hides their latency: the kernel's time is (longest chain in a warp) x (L2 round trip +
+// the opening test), ~107 visits per target on the shipped scene.  Tried in round 2 and rejected (profiles/
+// r2_walk_window_experiment.txt): a per-thread window of 4 or 8 consecutive records staged in shared memory by
+// cp.async, with and without prefetch of the next window -- 3.3x to 5.4x SLOWER (shared-memory bank conflicts on 78 %
+// of the wavefronts, 4 to 8 times the bytes per visit), so each visit stays one 256-bit load.
 // fused kick-drift epilogue (one GPU, small scenes): the walk thread integrates its own target -- scattered 4-byte
 // accesses, which at a few ten thousand bodies cost less than another launch
 struct BhFuse {
@@ -684,57 +684,17 @@ struct BhFuse {
 
 constexpr int WALK_THREADS = 128;
 
-template <int DIMS, bool REFCOMPAT, bool FUSE, int WIN, bool PREFETCH>
-__global__ void __launch_bounds__(WALK_THREADS)
-bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
-               float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-               float *__restrict__ accp, unsigned cap, unsigned long long *visits, const BhFuse fz)
+// end of a target's walk: store the acceleration, or -- fused -- integrate the target right away.
+// Simulation::iterate after attract(): the same integrate_body_f32 as the stand-alone integrator, same operand order.
+template <int DIMS, bool FUSE>
+__device__ __forceinline__ void bh_walk_finish(const float *__restrict__ posm, size_t g, unsigned body, size_t shard_start, float px,
+                                               float py, float pz, float ax, float ay, float az, float *__restrict__ accp, const BhFuse &fz)
 {
-    constexpr int CH = 2 * WIN;                              // 16-byte chunks per window
-    __shared__ float4 cache[PREFETCH ? 2 : 1][CH][WALK_THREADS];
-    const int t = threadIdx.x;
-    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const unsigned body = idx[s];                           // targets in Z-order: neighbouring threads walk alike
-    if (body < shard_start || body >= shard_start + shard_count) return;
-    const size_t g = blk_index(body, 0);
-    const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    unsigned i = 0, nvis = 0, base = 0;
-    int cur = 0;
-    auto fill = [&](int buf, unsigned b0) {
-        const float4 *src = nodes.rec + (size_t)b0 * 2;      // the array is padded by WIN records: a window never leaves it
-#pragma unroll
-        for (int c = 0; c < CH; ++c) cp_async16(&cache[buf][c][t], src + c);
-        cp_async_commit();
-    };
-    fill(0, 0);
-    for (;;) {
-        if (PREFETCH) { fill(cur ^ 1, base + WIN); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        do {                                                 // consume records while the walk stays inside the window
-            const unsigned c0 = (i - base) * 2;
-            const float4 nd = cache[cur][c0][t];
-            const uint4 na = *reinterpret_cast<const uint4 *>(&cache[cur][c0 + 1][t]);
-            ++nvis;
-            if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
-            else i = i + 1;
-        } while (i != 0 && i - base < (unsigned)WIN);       // pre-order: the walk only ever moves forward; 0 = end
-        if (i == 0 || i >= cap) break;                       // i >= cap only if the tree overflowed its reservation (status word)
-        const unsigned nb = i & ~(unsigned)(WIN - 1);
-        if (PREFETCH && nb == base + WIN) { cur ^= 1; base = nb; continue; }      // already on its way
-        if (PREFETCH) cp_async_wait<0>();                    // the discarded prefetch must land before its buffer is refilled
-        base = nb;
-        fill(cur, base);
-    }
-    if (PREFETCH) cp_async_wait<0>();
-    if (visits) atomicAdd(visits, (unsigned long long)nvis);   // profiled steps only: node records visited (roofline)
     if (!FUSE) {
         const size_t l = blk_index(body - shard_start, 0);
         accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = az;
         return;
     }
-    // Simulation::iterate after attract(): the same integrate_body_f32 as the stand-alone integrator, same operand order
     const float gx = ax * fz.G, gy = ay * fz.G, gz = az * fz.G;
     float qx = px, qy = py, qz = (DIMS == 3) ? pz : posm[g + 2 * BLK];
     float vx = fz.vel[g], vy = fz.vel[g + BLK], vz = fz.vel[g + 2 * BLK];
@@ -742,6 +702,32 @@ bh_walk_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx,
     fz.posm_next[g] = qx; fz.posm_next[g + BLK] = qy; fz.posm_next[g + 2 * BLK] = qz; fz.posm_next[g + 3 * BLK] = posm[g + 3 * BLK];
     fz.vel[g] = vx; fz.vel[g + BLK] = vy; fz.vel[g + 2 * BLK] = vz;
     fz.acc[g] = gx; fz.acc[g + BLK] = gy; fz.acc[g + 2 * BLK] = gz;
+}
+
+template <int DIMS, bool REFCOMPAT, bool FUSE>
+__global__ void __launch_bounds__(WALK_THREADS)
+bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
+                      float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
+                      float *__restrict__ accp, unsigned cap, unsigned long long *visits, const BhFuse fz)
+{
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const unsigned body = idx[s];                           // targets in Z-order: neighbouring threads walk alike
+    if (body < shard_start || body >= shard_start + shard_count) return;
+    const size_t g = blk_index(body, 0);
+    const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    unsigned i = 0, nvis = 0;
+    do {
+        float4 nd;
+        uint4 na;
+        bh_load_node(nodes, i, nd, na);
+        ++nvis;
+        if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
+        else i = i + 1;
+    } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (raises the status word)
+    if (visits) atomicAdd(visits, (unsigned long long)nvis);
+    bh_walk_finish<DIMS, FUSE>(posm, g, body, shard_start, px, py, pz, ax, ay, az, accp, fz);
 }
 
 // Warp-cooperative walk.  The 32 lanes of a warp hold 32 targets that are neighbours in Z-order; the
@@ -821,6 +807,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int clus
     BH_ALLOC(count, (n + 2) * 4) BH_ALLOC(offs, (n + 2) * 4) BH_ALLOC(first, n) BH_ALLOC(leaf, n)
     BH_ALLOC(node_data, ((size_t)node_cap + 16) * 32) BH_ALLOC(node_quad, (size_t)node_cap * 16)
     BH_ALLOC(node_slots, (size_t)node_cap * (dims == 3 ? 8 : 4) * 16)
+    BH_ALLOC(node_slot_cells, (size_t)node_cap * (dims == 3 ? 8 : 4) * 4)
     BH_ALLOC(node_owner, (size_t)node_cap * 4)
     // everything that must be zero at the start of a build lives in ONE region cleared by one memset per step:
     // bounding box | radix-sort scratch (histograms, tickets, status words) | scan scratch | arrival counters
@@ -838,7 +825,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int clus
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_owner, zero_region};
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_slot_cells, node_owner, zero_region, trace};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -846,7 +833,7 @@ void BhWorkspace::release()
 static BhNodes bh_nodes(const BhWorkspace &w)
 {
     BhNodes nd;
-    nd.rec = (float4 *)w.node_data; nd.quad = (float4 *)w.node_quad; nd.slots = (float4 *)w.node_slots;
+    nd.rec = (float4 *)w.node_data; nd.quad = (float4 *)w.node_quad; nd.slots = (float4 *)w.node_slots; nd.slot_cells = (unsigned *)w.node_slot_cells;
     return nd;
 }
 
@@ -932,9 +919,24 @@ cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int
         a.idx_a = (unsigned *)idx_in; a.idx_b = (unsigned *)idx;
         a.count = (unsigned *)count; a.offs = (unsigned *)offs; a.first = (unsigned char *)first; a.leaf = (unsigned char *)leaf;
         a.owner = (unsigned *)node_owner; a.occ = (unsigned *)node_arrive; a.nodes = bh_nodes(*this); a.status = status;
+        static const bool want_trace = getenv("NBODY_CLUSTER_TRACE") != nullptr;
+        a.trace = nullptr;
+        if (want_trace) {
+            if (!trace && cudaMalloc(&trace, 64 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+            cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st);
+            a.trace = (long long *)trace;
+        }
         const cudaError_t e = dims == 3 ? launch_cluster(bh_build_cluster_kernel<3>, cluster_ctas, sizeof(ClSmem), a, st)
                                         : launch_cluster(bh_build_cluster_kernel<2>, cluster_ctas, sizeof(ClSmem), a, st);
         if (e != cudaSuccess) return e;
+        if (want_trace) {                                                      // tuning aid: cycles per phase of this build, on stderr
+            long long h[64];
+            if (cudaMemcpyAsync(h, trace, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
+                fprintf(stderr, "[cluster build n=%zu ctas=%d] cycles: box..", n, cluster_ctas);
+                for (int k = 1; k < 64 && h[k]; ++k) fprintf(stderr, " %lld", h[k] - h[k - 1]);
+                fprintf(stderr, "\n");
+            }
+        }
         std::swap(keys_in, keys);                                              // the sorted pairs are in the a-buffers
         std::swap(idx_in, idx);
         count_valid = false;
@@ -971,17 +973,8 @@ static void bh_walk_t(const BhWorkspace &w, const float *posm, size_t n, float t
         else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
         return;
     }
-#define BH_WALK(RC, WIN, PF) bh_walk_kernel<DIMS, RC, FUSE, WIN, PF><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz)
-    // window variant: 0 = 4 records, 1 = 8 records, 2 = 4 records + prefetch (tuning: NBODY_BH_WALK_VARIANT)
-    switch (w.walk_variant * 2 + (refcompat ? 1 : 0)) {
-    case 0: BH_WALK(false, 4, false); break;
-    case 1: BH_WALK(true, 4, false); break;
-    case 2: BH_WALK(false, 8, false); break;
-    case 3: BH_WALK(true, 8, false); break;
-    case 4: BH_WALK(false, 4, true); break;
-    default: BH_WALK(true, 4, true); break;
-    }
-#undef BH_WALK
+    if (refcompat) bh_walk_direct_kernel<DIMS, true, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz);
+    else bh_walk_direct_kernel<DIMS, false, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz);
 }
 
 // `fuse` != nullptr: the walk threads also integrate their targets (kick-drift; one GPU, whole array = one shard)

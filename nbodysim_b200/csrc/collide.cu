@@ -73,7 +73,7 @@ col_cluster_kernel(ColArgs a, unsigned long long *keys_b, unsigned *vals_b, unsi
     const unsigned ne = min(__ldcg(a.counters + 0), a.entry_cap);
     if (ne > nc * CL_MAX_CHUNK && gtid == 0) col_overflow(a);            // more cell entries than the cluster sort holds
     if (__ldcg(a.counters + 2) || ne > nc * CL_MAX_CHUNK) return;         // uniform: every thread reads the same words
-    if (cl_radix_sort<true>(sm, a.keys_in, keys_b, a.vals_in, vals_b, ne, 0, 32)) { a.keys = keys_b; a.vals = vals_b; }
+    if (cl_radix_sort<true>(sm, a.keys_in, keys_b, a.vals_in, vals_b, ne, 0, COL_GROUP_BITS)) { a.keys = keys_b; a.vals = vals_b; }
     else { a.keys = a.keys_in; a.vals = a.vals_in; }
     col_phase_pairs<0>(a, gtid, gthreads);
     cl_sync();
@@ -189,10 +189,9 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     ColArgs a = args(posm, vel, n);
     col_init_kernel<<<gn, 256, 0, st>>>(a);
     col_entries_kernel<<<gn, 256, 0, st>>>(a);
-    // Only the GROUPING of equal cell hashes matters to the pair discovery (pairs are put in canonical order by the
-    // second sort), and the hashes are sign-extended 32-bit values: sorting their low 32 bits groups them.
+    // only the GROUPING of the entries matters to the pair discovery: sort on COL_GROUP_BITS bits of the hash (collide.cuh)
     if ((e = radix_sort_u64((unsigned long long *)keys_in, (unsigned long long *)keys, (unsigned *)vals_in, (unsigned *)vals,
-                            entry_cap, temp, st, 0, 32, launches, cnt + 0)) != cudaSuccess) return e;
+                            entry_cap, temp, st, 0, COL_GROUP_BITS, launches, cnt + 0)) != cudaSuccess) return e;
     std::swap(keys_in, keys);
     std::swap(vals_in, vals);
     a = args(posm, vel, n);

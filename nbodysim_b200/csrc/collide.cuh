@@ -8,6 +8,11 @@
 namespace nb {
 
 constexpr float COL_CELL = 600.0f;   // SpatialGrid::CELL_SIZE, Simulation.hpp:20
+// Pair discovery only needs the entries of one grid cell to be findable together, so the (hash, body) entries are
+// sorted on the low 16 bits of the hash -- two digit passes instead of four (or eight) -- and the pair loop skips the
+// few entries of other cells that share those bits.  Pairs are put in canonical order by their own sort afterwards.
+constexpr int COL_GROUP_BITS = 16;
+constexpr unsigned long long COL_GROUP_MASK = (1ull << COL_GROUP_BITS) - 1ull;
 
 // counters: [0] cell entries, [1] pairs kept (hot components), [2] overflow flag, [3] pairs resolved (narrow test
 // passed), [4] sweep pairs that overlap now
@@ -125,7 +130,11 @@ __device__ __forceinline__ void col_phase_pairs(const ColArgs &a, unsigned gtid,
         const unsigned long long key = a.keys[e];
         const unsigned ia = a.vals[e];
         const ColBody A = col_load(a.posm, a.vel, ia);
-        for (unsigned f = e + 1; f < ne && a.keys[f] == key; ++f) {
+        // the entries are sorted (grouped) by the low COL_GROUP_BITS bits of the hash only: walk the group, keep the same cell
+        for (unsigned f = e + 1; f < ne; ++f) {
+            const unsigned long long kf = a.keys[f];
+            if (((kf ^ key) & COL_GROUP_MASK) != 0ull) break;
+            if (kf != key) continue;
             const unsigned ib = a.vals[f];
             if (ib == ia) continue;
             const ColBody B = col_load(a.posm, a.vel, ib);

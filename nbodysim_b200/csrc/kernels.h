@@ -127,6 +127,8 @@ struct BhWorkspace {
     void *root = nullptr, *box = nullptr, *keys_in = nullptr, *keys = nullptr, *idx_in = nullptr, *idx = nullptr;
     void *count = nullptr, *offs = nullptr, *first = nullptr, *leaf = nullptr;
     void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr, *node_slots = nullptr;   // node_data: one 32-byte record per node
+    void *trace = nullptr;       // tuning aid (NBODY_CLUSTER_TRACE): per-phase clock stamps of the cluster build
+    void *node_slot_cells = nullptr; // centre-of-mass pass: subtree sizes riding up with the centres of mass (-> skip pointers)
     void *node_owner = nullptr;  // single-cluster build: the sorted body that owns each cell
     int cluster_ctas = 0;        // > 0: scenes of up to cluster_ctas x 49152 bodies are built by ONE cluster kernel of that many CTAs
     static int cluster_ctas_available(int dims);
@@ -137,7 +139,6 @@ struct BhWorkspace {
     size_t zero_bytes = 0;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
-    int walk_variant = 0;        // per-thread walk: record window 0 = 4, 1 = 8, 2 = 4 + prefetch of the next window
     unsigned walk_window = 256;  // warp-cooperative walk: how many records ahead of the slowest lane a lane may run
                                  // (sweep on B200, tools/bh_window_sweep.py: 256 is best or within 1 % of best everywhere)
     cudaError_t alloc(size_t n, int dims, double node_factor, int cluster_mode, size_t cluster_max_n);

@@ -250,7 +250,10 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
         double factor = 4.0;
         if (const char *nf = getenv("NBODY_BH_NODE_FACTOR")) factor = atof(nf);
         {
-            const cudaError_t be = d.bh.alloc(ctx->n, ctx->p.dims, factor, ctx->p.sort_impl, cl_max);
+            // measured (profiles/r2_cluster_build_trace.txt): the single-cluster BUILD is slower than one kernel per phase on
+            // the whole GPU (267 vs 157 us at n = 25,000), so it runs only on request; the single-cluster COLLISION PASS is
+            // faster (60 vs ~300 us cold) and is the default for small scenes
+            const cudaError_t be = d.bh.alloc(ctx->n, ctx->p.dims, factor, ctx->p.sort_impl == 2 ? 2 : 1, cl_max);
             if (be == cudaErrorNotSupported) {
                 set_err(ctx, "sort_impl = 2 (single-cluster build) needs a device that can host a cluster of >= 8 CTAs and n <= CTAs x 49152");
                 return NBODY_EINVAL;
@@ -260,7 +263,6 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
         d.bh.status = d.d_status;
         d.bh.warp_walk = ctx->p.bh_walk == 2 || (ctx->p.bh_walk == 0 && (ctx->p.dims == 3 || ctx->p.theta < 0.7f));
         if (const char *ww = getenv("NBODY_BH_WALK_WINDOW")) d.bh.walk_window = (unsigned)std::max(1, atoi(ww));   // tuning override
-        if (const char *wv = getenv("NBODY_BH_WALK_VARIANT")) d.bh.walk_variant = std::min(2, std::max(0, atoi(wv)));
     }
     return NBODY_OK;
 }

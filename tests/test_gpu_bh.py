@@ -265,12 +265,10 @@ def test_bh_cell_overflow_is_reported_and_capacity_can_be_raised(monkeypatch):
     assert np.array_equal(bits(out), bits(O.orc_bh_acc(b, 1.0, 1.0)))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("sort_impl", [1, 2])
-def test_walk_window_variants_and_build_paths_bitexact(variant, sort_impl, monkeypatch):
-    """the per-thread walk's record window (4 / 8 records, 4 + prefetch) and the two build paths (one kernel per
-    phase, single cluster kernel) change the execution, never a bit of the result; 5 fused walk-and-integrate steps"""
-    monkeypatch.setenv("NBODY_BH_WALK_VARIANT", str(variant))
+def test_build_paths_and_fused_walk_bitexact(sort_impl):
+    """the two build paths (one kernel per phase, single cluster kernel) and the two integrators (walk threads integrate
+    their own targets -- small scenes -- / stand-alone kernel) change the execution, never a bit of the result"""
     b = ic.spinning_disc(25000, seed=5, scale=100.0 * np.sqrt(25000 / 1024.0))
     b["mass"] = np.random.default_rng(5).uniform(0.1, 3.0, 25000).astype(np.float32)
     with bh_sim(b, theta=1.0, eps=1.0, sort_impl=sort_impl) as s:
@@ -282,7 +280,7 @@ def test_walk_window_variants_and_build_paths_bitexact(variant, sort_impl, monke
         want["acc"] = O.orc_bh_acc(want, 1.0, 1.0)
         O.oracle().orc_iterate_after_attract(want.ctypes.data, want.shape[0], 0.01, 3, 2)
     outs = []
-    for fuse in (-1, 0):           # walk threads integrate their targets (small scenes) / stand-alone integrator
+    for fuse in (-1, 0):
         with bh_sim(b, dt=0.01, theta=1.0, eps=1.0, sort_impl=sort_impl, fuse_integrator=fuse,
                     integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY) as s:
             s.step(3)

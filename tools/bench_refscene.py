@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """The reference's shipped scene (uniform_disc(25000), Simulation::step = BH theta=1 + clamp + boundary + collide,
-refcompat) under the execution variants of the library: launch-per-phase vs single-cluster build / collision pass
-(sort_impl 1 / 0) x the per-thread walk's record window (NBODY_BH_WALK_VARIANT 0 / 1 / 2).  One JSON line each:
+refcompat) under the execution variants of the library (sort_impl 1 = one kernel per phase, 0 = default: collision pass
+as one cluster kernel, 2 = build as one cluster kernel too), with / without collide and fused integrator.  One JSON line each:
 CUDA-graph replay rate, cold single-step phase times.  Sizes other than 25,000 via argv."""
 import json
 import os
@@ -15,11 +15,10 @@ sys.path.insert(0, ROOT)
 from nbodysim_b200 import Simulation, capi, ic  # noqa: E402
 
 
-def run(n, sort_impl, variant, collide=1, fuse=-1):
-    os.environ["NBODY_BH_WALK_VARIANT"] = str(variant)
+def run(n, sort_impl, collide=1, fuse=-1):
     b = ic.reference_disc(n)
     st = torch.cuda.Stream()
-    row = {"n": n, "sort_impl": sort_impl, "walk_variant": variant, "collide": collide, "fuse": fuse}
+    row = {"n": n, "sort_impl": sort_impl, "collide": collide, "fuse": fuse}
     with Simulation(b, dt=0.01, force_algo=capi.FORCE_BARNES_HUT, dims=2, theta=1.0, eps=1.0, collide=collide, sort_impl=sort_impl,
                     fuse_integrator=fuse, rsqrt_mode=capi.RSQRT_REFCOMPAT, integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY,
                     stream=st.cuda_stream) as s:
@@ -44,8 +43,7 @@ def run(n, sort_impl, variant, collide=1, fuse=-1):
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [25000]
     for n in sizes:
-        for sort_impl in (1, 0):
-            for variant in (0, 1, 2):
-                run(n, sort_impl, variant)
-        run(n, 0, 0, collide=0)
-        run(n, 0, 0, collide=0, fuse=0)
+        for sort_impl in (1, 0, 2):
+            run(n, sort_impl)
+        run(n, 0, collide=0)
+        run(n, 0, collide=0, fuse=0)
