@@ -95,13 +95,14 @@ typedef struct nbody_params {
     int32_t  bh_fix_near_leaves; /* Barnes-Hut only.  0 = the reference's behaviour: a NEAR leaf contributes
                                  nothing (insert() leaves every body Range empty, Quadtree.hpp:133-147);
                                  1 = add the leaf's body for near leaves (self excluded) */
-    int32_t  sort_impl;       /* execution of the Barnes-Hut build and the collision pass.  0 = auto: the build runs one kernel per
-                                 phase with the single-pass ("onesweep") radix sort and chained scan of csrc/radix_sort.cuh; the
-                                 collision pass of scenes of up to 65,536 bodies (NBODY_CLUSTER_MAX_N) runs as ONE thread-block-
-                                 cluster kernel (sort passes, union-find, resolve separated by hardware cluster barriers, a step
-                                 without overlapping bodies ends after the detection phase).  1 = always one kernel per phase.
-                                 2 = also run the BUILD as one cluster kernel (measured slower than 0 on B200, kept selectable;
-                                 init fails if the device cannot host the cluster or n is too large).  Identical results. */
+    int32_t  sort_impl;       /* execution of the Barnes-Hut build and of the (rare) full collision pass.  0 = auto: the build runs
+                                 one kernel per phase with the single-pass ("onesweep") radix sort and chained scan of
+                                 csrc/radix_sort.cuh; the full collision pass of scenes of up to 65,536 bodies
+                                 (NBODY_CLUSTER_MAX_N) runs as ONE CTA whose phases are separated by barriers, launched after the
+                                 screening of every pass and returning at once when no two bodies sharing a grid cell overlap.
+                                 1 = always one kernel per phase.  2 = also run the BUILD as one thread-block-cluster kernel
+                                 (measured slower than 0 on B200, kept selectable; init fails if the device cannot host the
+                                 cluster or n is too large).  Identical results. */
     int32_t  bh_walk;         /* Barnes-Hut only.  0 = auto, 1 = one independent walk per thread (targets in Z-order),
                                  2 = warp-cooperative walk (the warp walks the union of its 32 targets' traversals, every
                                  node record loaded once per warp).  Identical results bit for bit.  Measured: short

@@ -349,6 +349,8 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
 //   deposits (position, mass) in its parent's slot for its quadrant, the next level sums its occupied slots in
 //   quadrant order -- Quadtree::propagate's arithmetic and order, with a cluster barrier per level instead of
 //   atomics-and-fences per cell.
+constexpr size_t BH_CL_RANKS_OFFSET = (sizeof(ClSmem) + 15) & ~(size_t)15;
+constexpr size_t BH_CL_SMEM = BH_CL_RANKS_OFFSET + (size_t)CL_MAX_CHUNK * sizeof(unsigned short);   // ~115 KB: one CTA per SM
 struct BhClusterArgs {
     const float *posm;
     unsigned n, cap;
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
     extern __shared__ __align__(16) unsigned char cl_smem_raw[];
     ClSmem &sm = *reinterpret_cast<ClSmem *>(cl_smem_raw);
+    unsigned short *ranks = reinterpret_cast<unsigned short *>(cl_smem_raw + BH_CL_RANKS_OFFSET);
     const unsigned rank = cl_rank(), nc = cl_size(), tid = threadIdx.x, lane = tid & 31;
     const unsigned gtid = rank * CL_THREADS + tid, gthreads = nc * CL_THREADS;
     const unsigned n = a.n;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) bh_build_cluster_kernel(const B
     // ---- stable sort of (key, body); the result is brought back to the a-buffers
     unsigned long long *keys = a.keys_a;
     unsigned *idx = a.idx_a;
-    if (cl_radix_sort<true>(sm, a.keys_a, a.keys_b, a.idx_a, a.idx_b, n, 0, 64)) {
+    if (cl_radix_sort<true>(sm, ranks, a.keys_a, a.keys_b, a.idx_a, a.idx_b, n, 0, 64)) {
         for (unsigned i = gtid; i < n; i += gthreads) { __stcg(a.keys_a + i, __ldcg(a.keys_b + i)); __stcg(a.idx_a + i, __ldcg(a.idx_b + i)); }
         cl_sync();
     }
@@ -904,7 +907,7 @@ static cudaError_t launch_cluster(K kernel, int nc, size_t smem, const A &args, 
 
 int BhWorkspace::cluster_ctas_available(int dims_)
 {
-    return dims_ == 3 ? cluster_ctas_for(bh_build_cluster_kernel<3>, sizeof(ClSmem)) : cluster_ctas_for(bh_build_cluster_kernel<2>, sizeof(ClSmem));
+    return dims_ == 3 ? cluster_ctas_for(bh_build_cluster_kernel<3>, BH_CL_SMEM) : cluster_ctas_for(bh_build_cluster_kernel<2>, BH_CL_SMEM);
 }
 
 // Build the tree of the first n bodies of `posm`.  Fully asynchronous (no host read-back): the node count
@@ -926,8 +929,8 @@ cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int
             cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st);
             a.trace = (long long *)trace;
         }
-        const cudaError_t e = dims == 3 ? launch_cluster(bh_build_cluster_kernel<3>, cluster_ctas, sizeof(ClSmem), a, st)
-                                        : launch_cluster(bh_build_cluster_kernel<2>, cluster_ctas, sizeof(ClSmem), a, st);
+        const cudaError_t e = dims == 3 ? launch_cluster(bh_build_cluster_kernel<3>, cluster_ctas, BH_CL_SMEM, a, st)
+                                        : launch_cluster(bh_build_cluster_kernel<2>, cluster_ctas, BH_CL_SMEM, a, st);
         if (e != cudaSuccess) return e;
         if (want_trace) {                                                      // tuning aid: cycles per phase of this build, on stderr
             long long h[64];

@@ -13,7 +13,7 @@
 namespace nb {
 
 constexpr int CL_THREADS = 512, CL_WARPS = CL_THREADS / 32;
-constexpr unsigned CL_MAX_CHUNK = 49152;          // sort items per CTA (their ranks are kept as 16-bit words in shared memory: 96 KB)
+constexpr unsigned CL_MAX_CHUNK = 49152;          // sort items per CTA when their ranks are kept in shared memory (16-bit words: 96 KB)
 
 __device__ __forceinline__ unsigned cl_rank()
 {
@@ -42,9 +42,8 @@ __device__ __forceinline__ unsigned cl_ld_u32(const unsigned *local, unsigned ct
     return v;
 }
 
-struct ClSmem {                                   // dynamic shared memory of a cluster kernel (~115 KB; one CTA per SM)
+struct ClSmem {                                   // shared memory of a cluster kernel (~19 KB, + the ranks when they live on chip)
     unsigned counts[CL_WARPS][256];               // per-warp digit counts of a sort pass, then the warps' bases inside the digit
-    unsigned short ranks[CL_MAX_CHUNK];           // rank of every item of this CTA's chunk among its warp's items of the same digit
     unsigned hist[256];                           // this CTA's digit counts (read by the other CTAs)
     unsigned dest[256];                           // first output index for (this CTA, digit)
     unsigned xchg[64];                            // small per-CTA results exposed to the cluster (scan totals, box, maxima)
@@ -103,9 +102,11 @@ __device__ __forceinline__ void cl_exchange_sum(ClSmem &sm, unsigned *slot, unsi
 // Per digit: every CTA ranks its contiguous chunk -- warps take contiguous sub-chunks row by row, __match_any_sync
 // groups, one shared-memory atomic per group, so ranks follow input order (stable) -- publishes its 256 digit
 // counts, reads the other CTAs' counts through distributed shared memory, and scatters.  Two cluster barriers per digit.
-// n <= cl_size() * CL_MAX_CHUNK.  Every thread of the cluster must call it with the same arguments.
-template <bool HAS_VALS>
-__device__ int cl_radix_sort(ClSmem &sm, unsigned long long *ka, unsigned long long *kb, unsigned *va, unsigned *vb,
+// `ranks` holds one RankT per item of this CTA's chunk (the item's rank among its warp's items of the same digit): shared
+// memory (16-bit, chunks of up to CL_MAX_CHUNK items) or a global scratch array.  Every thread of the cluster must call it
+// with the same arguments.
+template <bool HAS_VALS, typename RankT>
+__device__ int cl_radix_sort(ClSmem &sm, RankT *ranks, unsigned long long *ka, unsigned long long *kb, unsigned *va, unsigned *vb,
                              unsigned n, int begin_bit, int end_bit)
 {
     const unsigned rank = cl_rank(), nc = cl_size();
@@ -129,7 +130,7 @@ __device__ int cl_radix_sort(ClSmem &sm, unsigned long long *ka, unsigned long l
             unsigned base = 0;
             if (valid && lane == leader) base = atomicAdd(&sm.counts[w][d], (unsigned)__popc(peers));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (valid) sm.ranks[i - c0] = (unsigned short)(base + __popc(peers & ((1u << lane) - 1u)));
+            if (valid) ranks[i - c0] = (RankT)(base + __popc(peers & ((1u << lane) - 1u)));
         }
         __syncthreads();
         if (tid < 256) {                           // digit tid: bases of the warps inside the digit, CTA total
@@ -156,7 +157,7 @@ __device__ int cl_radix_sort(ClSmem &sm, unsigned long long *ka, unsigned long l
                 if (i < c1) {
                     const unsigned long long k = __ldcg(ka + i);
                     const unsigned d = (unsigned)(k >> shift) & 255u;
-                    const unsigned dst = sm.dest[d] + sm.counts[w][d] + sm.ranks[i - c0];
+                    const unsigned dst = sm.dest[d] + sm.counts[w][d] + (unsigned)ranks[i - c0];
                     __stcg(kb + dst, k);
                     if (HAS_VALS) __stcg(vb + dst, __ldcg(va + i));
                 }

@@ -57,27 +57,41 @@ __global__ void __launch_bounds__(128) col_resolve_kernel(ColArgs a, const unsig
     col_phase_resolve(a, pairs_sorted, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-// ---- the whole pass as ONE cluster kernel (small scenes): the same phases, separated by cluster barriers; a step
-// without overlapping pairs -- the common case -- ends after the detect phase.
-__global__ void __launch_bounds__(CL_THREADS, 1)
-col_cluster_kernel(ColArgs a, unsigned long long *keys_b, unsigned *vals_b, unsigned long long *pairs_b, int key_bits)
+// ---- screening kernels (every pass) -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_grid_insert_kernel(ColArgs a, ColGrid g)
 {
-    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
-    ClSmem &sm = *reinterpret_cast<ClSmem *>(cl_smem_raw);
-    const unsigned nc = cl_size();
-    const unsigned gtid = cl_rank() * CL_THREADS + threadIdx.x, gthreads = nc * CL_THREADS;
+    col_grid_insert(a, g, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(256) col_grid_detect_kernel(ColArgs a, ColGrid g)
+{
+    col_grid_detect(a, g, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// ---- the full pass as ONE CTA (small scenes) ----------------------------------------------------------------------------------
+// Launched after the screening of every pass, it returns at once unless the screening saw an overlap: a step without
+// collisions costs a memset, two short kernels and this empty launch.  When it does run, the phases of the full pass
+// follow one another separated by CTA-wide barriers (the cluster primitives with a cluster of one CTA; sort ranks in a
+// global scratch array).  Collisions are rare events in the scenes this path serves, so its own speed matters little.
+__global__ void __launch_bounds__(CL_THREADS, 1)
+col_single_cta_kernel(ColArgs a, unsigned long long *keys_b, unsigned *vals_b, unsigned long long *pairs_b, unsigned *ranks, int key_bits)
+{
+    __shared__ ClSmem sm;
+    const unsigned gtid = threadIdx.x, gthreads = CL_THREADS;
+    if (gtid < 8) a.counters[gtid] = 0;                                   // the statistics of a pass that found nothing
+    if (col_gate_closed(a)) return;
+    a.gate = nullptr;
+    cl_sync();
     col_phase_init(a, gtid, gthreads);
     cl_sync();
     col_phase_entries(a, gtid, gthreads);
     cl_sync();
     const unsigned ne = min(__ldcg(a.counters + 0), a.entry_cap);
-    if (ne > nc * CL_MAX_CHUNK && gtid == 0) col_overflow(a);            // more cell entries than the cluster sort holds
-    if (__ldcg(a.counters + 2) || ne > nc * CL_MAX_CHUNK) return;         // uniform: every thread reads the same words
-    if (cl_radix_sort<true>(sm, a.keys_in, keys_b, a.vals_in, vals_b, ne, 0, COL_GROUP_BITS)) { a.keys = keys_b; a.vals = vals_b; }
+    if (__ldcg(a.counters + 2)) return;                                   // uniform: every thread reads the same word
+    if (cl_radix_sort<true>(sm, ranks, a.keys_in, keys_b, a.vals_in, vals_b, ne, 0, COL_GROUP_BITS)) { a.keys = keys_b; a.vals = vals_b; }
     else { a.keys = a.keys_in; a.vals = a.vals_in; }
     col_phase_pairs<0>(a, gtid, gthreads);
     cl_sync();
-    if (__ldcg(a.counters + 4) == 0) return;                              // nothing overlaps: no resolve could pass its test
+    if (__ldcg(a.counters + 4) == 0) return;                              // no SWEEP pair overlaps: no resolve could pass its test
     col_phase_pairs<1>(a, gtid, gthreads);
     cl_sync();
     col_phase_mark(a, gtid, gthreads);
@@ -85,52 +99,32 @@ col_cluster_kernel(ColArgs a, unsigned long long *keys_b, unsigned *vals_b, unsi
     col_phase_pairs<2>(a, gtid, gthreads);
     cl_sync();
     const unsigned np = __ldcg(a.counters + 1);
-    if ((np > a.pair_cap || np > nc * CL_MAX_CHUNK) && gtid == 0) col_overflow(a);
-    if (__ldcg(a.counters + 2) || np > a.pair_cap || np > nc * CL_MAX_CHUNK) return;
-    const unsigned long long *sorted = cl_radix_sort<false>(sm, a.pairs, pairs_b, nullptr, nullptr, np, 0, key_bits) ? pairs_b : a.pairs;
+    if (__ldcg(a.counters + 2) || np > a.pair_cap) return;
+    const unsigned long long *sorted = cl_radix_sort<false>(sm, ranks, a.pairs, pairs_b, nullptr, nullptr, np, 0, key_bits) ? pairs_b : a.pairs;
     col_phase_resolve(a, sorted, gtid, gthreads);
 }
 
-int CollideWorkspace::cluster_ctas_available()
-{
-    auto kernel = col_cluster_kernel;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClSmem)) != cudaSuccess) { cudaGetLastError(); return 0; }
-    const bool np_ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    if (!np_ok) cudaGetLastError();
-    for (int nc = np_ok ? 16 : 8; nc >= 8; nc -= 8) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3((unsigned)nc); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClSmem);
-        cudaLaunchAttribute at;
-        at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = (unsigned)nc; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-        cfg.attrs = &at; cfg.numAttrs = 1;
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) == cudaSuccess && nclusters >= 1) return nc;
-        cudaGetLastError();
-    }
-    return 0;
-}
-
-// cluster_mode as BhWorkspace::alloc
-cudaError_t CollideWorkspace::alloc(size_t n, int cluster_mode, size_t cluster_max_n)
+// single_cta_mode: 0 = scenes of up to single_cta_max_n bodies run their (rare) full pass as one CTA, 1 = never (one
+// kernel per phase), 2 = always
+cudaError_t CollideWorkspace::alloc(size_t n, int single_cta_mode, size_t single_cta_max_n)
 {
     cudaError_t e;
-    cluster_ctas = 0;
-    if (cluster_mode != 1) {
-        const int avail = cluster_ctas_available();
-        // the cell entries (about one per body, more for bodies that straddle cells) must fit the cluster sort
-        const size_t lim = std::min<size_t>((size_t)avail * CL_MAX_CHUNK / 2, cluster_mode == 2 ? (size_t)-1 : cluster_max_n);
-        if (avail > 0 && n <= lim) cluster_ctas = avail;
-        else if (cluster_mode == 2) return cudaErrorNotSupported;
-    }
+    single_cta = single_cta_mode == 2 || (single_cta_mode == 0 && n <= single_cta_max_n);
     entry_cap = (unsigned)std::min<size_t>(4 * n + 4096, 0x7fffffffu);
     pair_cap = (unsigned)std::min<size_t>(64 * n + 65536, (size_t)16 << 20);   // pairs of hot components
+    unsigned tsize = 1024;
+    while (tsize < 2 * (size_t)entry_cap && tsize < (1u << 30)) tsize <<= 1;   // open addressing at load <= 1/2
+    table_slots = tsize;
 #define COL_ALLOC(p, bytes) if ((e = cudaMalloc((void **)&(p), (bytes))) != cudaSuccess) return e;
     COL_ALLOC(keys_in, (size_t)entry_cap * 8) COL_ALLOC(keys, (size_t)entry_cap * 8)
     COL_ALLOC(vals_in, (size_t)entry_cap * 4) COL_ALLOC(vals, (size_t)entry_cap * 4)
     COL_ALLOC(pairs_in, (size_t)pair_cap * 8) COL_ALLOC(pairs, (size_t)pair_cap * 8)
     COL_ALLOC(hot, 2 * n) COL_ALLOC(parent, n * 4) COL_ALLOC(counters, 32)
+    // screening: flags (64 B) | table keys | list heads -- one region, one memset per pass; then the list links
+    grid_bytes = 64 + (size_t)tsize * 12;
+    COL_ALLOC(grid, grid_bytes)
+    COL_ALLOC(grid_links, (size_t)entry_cap * 8)
+    if (single_cta) { COL_ALLOC(ranks, (size_t)std::max(entry_cap, pair_cap) * 4) }
     temp_bytes = radix_sort_temp_bytes(std::max<size_t>(entry_cap, pair_cap));
     COL_ALLOC(temp, temp_bytes)
 #undef COL_ALLOC
@@ -140,7 +134,7 @@ cudaError_t CollideWorkspace::alloc(size_t n, int cluster_mode, size_t cluster_m
 
 void CollideWorkspace::release()
 {
-    void *ptrs[] = {keys_in, keys, vals_in, vals, pairs_in, pairs, hot, parent, counters, temp};
+    void *ptrs[] = {keys_in, keys, vals_in, vals, pairs_in, pairs, hot, parent, counters, temp, grid, grid_links, ranks};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = CollideWorkspace();
 }
@@ -155,6 +149,7 @@ ColArgs CollideWorkspace::args(float *posm, float *vel, size_t n) const
     a.pairs = (unsigned long long *)pairs_in; a.pair_cap = pair_cap;
     a.hot = (unsigned char *)hot; a.parent = (unsigned *)parent; a.counters = (unsigned *)counters;
     a.status = status;
+    a.gate = (const unsigned *)grid;       // flags[0] of the screening
     int idx_bits = 1;
     while (((size_t)1 << idx_bits) < n) ++idx_bits;
     a.idx_bits = idx_bits;
@@ -171,22 +166,36 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
     cudaError_t e;
     unsigned *cnt = (unsigned *)counters;
-    if (cluster_ctas > 0) {                                  // small scene: one cluster kernel
-        ColArgs a = args(posm, vel, n);
-        const int key_bits = std::min(64, (((a.rooted ? 3 : 2) * a.idx_bits + 7) / 8) * 8);
+    ColArgs a = args(posm, vel, n);
+    const int key_bits = std::min(64, (((a.rooted ? 3 : 2) * a.idx_bits + 7) / 8) * 8);
+    {   // screening: hash-grid insert + overlap test; everything after it is gated on its flag
+        ColGrid g;
+        g.flags = (unsigned *)grid;
+        g.tkeys = (unsigned long long *)((char *)grid + 64);
+        g.heads = (unsigned *)((char *)grid + 64 + (size_t)table_slots * 8);
+        g.enext = (unsigned *)grid_links; g.ebody = (unsigned *)grid_links + entry_cap;
+        g.tmask = table_slots - 1; g.ecap = entry_cap;
+        if ((e = cudaMemsetAsync(grid, 0, grid_bytes, st)) != cudaSuccess) return e;
+        const unsigned gb = (unsigned)((n + 255) / 256);
+        col_grid_insert_kernel<<<gb, 256, 0, st>>>(a, g);
+        col_grid_detect_kernel<<<gb, 256, 0, st>>>(a, g);
+        if (launches) *launches += 2;
+    }
+    if (single_cta) {
+        // an explicit cluster of ONE CTA: the phase barriers are the cluster primitives of cluster_prims.cuh
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3((unsigned)cluster_ctas); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClSmem); cfg.stream = st;
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(CL_THREADS); cfg.stream = st;
         cudaLaunchAttribute at;
         at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = (unsigned)cluster_ctas; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        at.val.clusterDim.x = 1; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, col_cluster_kernel, a, (unsigned long long *)keys, (unsigned *)vals, (unsigned long long *)pairs, key_bits)) != cudaSuccess) return e;
+        if ((e = cudaLaunchKernelEx(&cfg, col_single_cta_kernel, a, (unsigned long long *)keys, (unsigned *)vals, (unsigned long long *)pairs,
+                                    (unsigned *)ranks, key_bits)) != cudaSuccess) return e;
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
     const unsigned gn = (unsigned)((n + 255) / 256), ge = (entry_cap + 255) / 256;
-    ColArgs a = args(posm, vel, n);
     col_init_kernel<<<gn, 256, 0, st>>>(a);
     col_entries_kernel<<<gn, 256, 0, st>>>(a);
     // only the GROUPING of the entries matters to the pair discovery: sort on COL_GROUP_BITS bits of the hash (collide.cuh)
@@ -200,7 +209,6 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     col_mark_kernel<<<gn, 256, 0, st>>>(a);
     col_emit_kernel<<<ge, 256, 0, st>>>(a);
     // a pair key packs (component, first, second) into 3 x idx_bits bits: 6 digit passes at n = 25,000
-    const int key_bits = std::min(64, (((a.rooted ? 3 : 2) * a.idx_bits + 7) / 8) * 8);
     if ((e = radix_sort_u64((unsigned long long *)pairs_in, (unsigned long long *)pairs, nullptr, nullptr, pair_cap, temp, st,
                             0, key_bits, launches, cnt + 1)) != cudaSuccess) return e;
     std::swap(pairs_in, pairs);

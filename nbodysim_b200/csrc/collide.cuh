@@ -30,6 +30,7 @@ struct ColArgs {
     unsigned *parent;                      // union-find forest over the bodies
     unsigned *counters;
     unsigned *status;                      // host-visible sticky flags ([1] = collision buffers overflowed), may be null
+    const unsigned *gate;                  // screening result ([0] = pairs sharing a cell that overlap now); 0 there: nothing to do
     int idx_bits, rooted;
 };
 
@@ -53,6 +54,86 @@ __device__ __forceinline__ void col_overflow(const ColArgs &a)
     atomicExch(&a.counters[2], 1u);
     if (a.status) *reinterpret_cast<volatile unsigned *>(a.status + 1) = 1u;
 }
+
+// ---- screening: does ANY pair of bodies sharing a grid cell overlap now? --------------------------------------------------
+// resolve() moves nothing unless a pair passes `d.mag_sq() <= r*r` (Simulation.hpp:301), and the first pair to pass it
+// in a pass does so on unmoved positions.  So when no two bodies that share a grid cell overlap at the start of the pass,
+// the whole pass is the identity -- the common case by far (no collision in the first steps of the shipped scene) -- and
+// it is decided without sorting anything: the bodies are inserted into a hash table keyed by their cells (open
+// addressing, one linked list of bodies per cell), then every body tests the later-numbered bodies of its cells.  The
+// test is resolve()'s own, on every pair sharing a cell: a superset of the sweep pairs, so a miss is impossible and a
+// false alarm merely runs the full pass, which applies the reference's rules exactly.
+struct ColGrid {
+    unsigned long long *tkeys;             // [tmask + 1]  0 = empty, else 1 << 32 | cell hash
+    unsigned *heads;                       // [tmask + 1]  entry index + 1 of the cell's list head, 0 = none
+    unsigned *enext, *ebody;               // [ecap]       list links (entry index + 1) and bodies
+    unsigned *flags;                       // [0] overlapping pairs seen, [1] entries used       (zeroed with the table)
+    unsigned tmask, ecap;
+};
+
+__device__ __forceinline__ bool col_cell_range(const ColBody &b, int &minX, int &maxX, int &minY, int &maxY)
+{
+    // Simulation.hpp:228-233: AABB = pos -+ radius ; cell = static_cast<int>(coordinate / CELL_SIZE)
+    minX = __float2int_rz(__fdiv_rn(__fsub_rn(b.x, b.r), COL_CELL)); maxX = __float2int_rz(__fdiv_rn(__fadd_rn(b.x, b.r), COL_CELL));
+    minY = __float2int_rz(__fdiv_rn(__fsub_rn(b.y, b.r), COL_CELL)); maxY = __float2int_rz(__fdiv_rn(__fadd_rn(b.y, b.r), COL_CELL));
+    const long long cells = (long long)(maxX - minX + 1) * (long long)(maxY - minY + 1);
+    return cells > 0 && cells <= 4096;
+}
+
+__device__ __forceinline__ void col_grid_insert(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads)
+{
+    for (unsigned i = gtid; i < a.n; i += gthreads) {
+        const ColBody b = col_load(a.posm, a.vel, i);
+        int minX, maxX, minY, maxY;
+        if (!col_cell_range(b, minX, maxX, minY, maxY)) { col_overflow(a); atomicAdd(&g.flags[0], 1u); continue; }   // let the full pass report it
+        for (int y = minY; y <= maxY; ++y)
+            for (int x = minX; x <= maxX; ++x) {
+                const unsigned long long key = (1ull << 32) | (unsigned)col_hash(x, y);
+                unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
+                unsigned probes = 0;
+                for (;;) {                                              // find or claim the cell's slot
+                    const unsigned long long old = atomicCAS(&g.tkeys[slot], 0ull, key);
+                    if (old == 0ull || old == key) break;
+                    slot = (slot + 1) & g.tmask;
+                    if (++probes > g.tmask) break;
+                }
+                const unsigned e = atomicAdd(&g.flags[1], 1u);
+                if (e >= g.ecap || probes > g.tmask) { col_overflow(a); atomicAdd(&g.flags[0], 1u); continue; }
+                g.ebody[e] = i;
+                g.enext[e] = atomicExch(&g.heads[slot], e + 1u);
+            }
+    }
+}
+
+__device__ __forceinline__ void col_grid_detect(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads)
+{
+    unsigned overlaps = 0;
+    for (unsigned i = gtid; i < a.n; i += gthreads) {
+        const ColBody A = col_load(a.posm, a.vel, i);
+        int minX, maxX, minY, maxY;
+        if (!col_cell_range(A, minX, maxX, minY, maxY)) continue;
+        for (int y = minY; y <= maxY; ++y)
+            for (int x = minX; x <= maxX; ++x) {
+                const unsigned long long key = (1ull << 32) | (unsigned)col_hash(x, y);
+                unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
+                for (unsigned probes = 0; probes <= g.tmask; ++probes) {
+                    const unsigned long long k = g.tkeys[slot];
+                    if (k == key || k == 0ull) break;
+                    slot = (slot + 1) & g.tmask;
+                }
+                if (g.tkeys[slot] != key) continue;
+                for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
+                    const unsigned j = g.ebody[e - 1u];
+                    if (j <= i) continue;                                // every pair once (per shared cell)
+                    const ColBody B = col_load(a.posm, a.vel, j);
+                    const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
+                    if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r))) ++overlaps;
+                }
+            }
+    }
+    if (overlaps) atomicAdd(&g.flags[0], overlaps);
+}
+
 
 // ---- union-find (lock-free; a root is always the smallest index of its tree) ------------------------------------
 __device__ __forceinline__ unsigned uf_find(unsigned *parent, unsigned x)
@@ -84,15 +165,16 @@ __device__ __forceinline__ void col_phase_init(const ColArgs &a, unsigned gtid, 
     for (unsigned i = gtid; i < a.n; i += gthreads) { a.parent[i] = i; a.hot[i] = 0; a.hot[a.n + i] = 0; }
 }
 
+__device__ __forceinline__ bool col_gate_closed(const ColArgs &a) { return a.gate != nullptr && __ldcg(a.gate) == 0u; }
+
 __device__ __forceinline__ void col_phase_entries(const ColArgs &a, unsigned gtid, unsigned gthreads)
 {
+    if (col_gate_closed(a)) return;
     for (unsigned i = gtid; i < a.n; i += gthreads) {
         const ColBody b = col_load(a.posm, a.vel, i);
-        // Simulation.hpp:228-233: AABB = pos -+ radius ; cell = static_cast<int>(coordinate / CELL_SIZE)
-        const int minX = __float2int_rz(__fdiv_rn(__fsub_rn(b.x, b.r), COL_CELL)), maxX = __float2int_rz(__fdiv_rn(__fadd_rn(b.x, b.r), COL_CELL));
-        const int minY = __float2int_rz(__fdiv_rn(__fsub_rn(b.y, b.r), COL_CELL)), maxY = __float2int_rz(__fdiv_rn(__fadd_rn(b.y, b.r), COL_CELL));
+        int minX, maxX, minY, maxY;
+        if (!col_cell_range(b, minX, maxX, minY, maxY)) { col_overflow(a); continue; }
         const long long cells = (long long)(maxX - minX + 1) * (long long)(maxY - minY + 1);
-        if (cells <= 0 || cells > 4096) { col_overflow(a); continue; }
         const unsigned base = atomicAdd(&a.counters[0], (unsigned)cells);
         if ((unsigned long long)base + (unsigned long long)cells > a.entry_cap) { col_overflow(a); continue; }
         unsigned k = base;
@@ -122,6 +204,7 @@ __device__ __forceinline__ bool col_sweep_pair(const ColBody &a, unsigned ia, co
 template <int MODE>
 __device__ __forceinline__ void col_phase_pairs(const ColArgs &a, unsigned gtid, unsigned gthreads)
 {
+    if (col_gate_closed(a)) return;
     if (__ldcg(a.counters + 2)) return;                   // overflow: the pass is abandoned (reported through status / sync)
     if (MODE > 0 && __ldcg(a.counters + 4) == 0) return;  // nothing overlaps: no resolve can pass its test
     const unsigned ne = __ldcg(a.counters + 0);
@@ -164,7 +247,7 @@ __device__ __forceinline__ void col_phase_pairs(const ColArgs &a, unsigned gtid,
 // a component is hot when one of its bodies is in a pair that overlaps now
 __device__ __forceinline__ void col_phase_mark(const ColArgs &a, unsigned gtid, unsigned gthreads)
 {
-    if (__ldcg(a.counters + 2) || __ldcg(a.counters + 4) == 0) return;
+    if (col_gate_closed(a) || __ldcg(a.counters + 2) || __ldcg(a.counters + 4) == 0) return;
     for (unsigned i = gtid; i < a.n; i += gthreads)
         if (a.hot[i]) a.hot[a.n + uf_find(a.parent, i)] = 1;
 }
@@ -217,7 +300,7 @@ __device__ __forceinline__ bool col_resolve(float *posm, float *vel, unsigned i,
 __device__ __forceinline__ void col_phase_resolve(const ColArgs &a, const unsigned long long *__restrict__ pairs_sorted,
                                                   unsigned gtid, unsigned gthreads)
 {
-    if (__ldcg(a.counters + 2)) return;
+    if (col_gate_closed(a) || __ldcg(a.counters + 2)) return;
     const unsigned np = min(__ldcg(a.counters + 1), a.pair_cap);
     const int b = a.idx_bits, rs = a.rooted ? 2 * b : 63;
     const unsigned long long imask = (1ull << b) - 1ull;

@@ -160,9 +160,11 @@ struct CollideWorkspace {
     void *pairs_in = nullptr, *pairs = nullptr, *hot = nullptr, *parent = nullptr, *counters = nullptr, *temp = nullptr;
     size_t temp_bytes = 0;
     unsigned *status = nullptr;  // host-visible sticky flags ([1] = entry / pair buffers overflowed), owned by the context
-    int cluster_ctas = 0;        // > 0: the whole pass runs as ONE cluster kernel of that many CTAs (small scenes)
-    static int cluster_ctas_available();
-    cudaError_t alloc(size_t n, int cluster_mode, size_t cluster_max_n);
+    void *grid = nullptr, *grid_links = nullptr, *ranks = nullptr;   // screening hash grid (flags | keys | heads), its list links; sort ranks
+    size_t grid_bytes = 0;
+    unsigned table_slots = 0;
+    bool single_cta = false;     // small scenes: the (rare) full pass runs as ONE CTA, phases separated by barriers
+    cudaError_t alloc(size_t n, int single_cta_mode, size_t single_cta_max_n);
     void release();
     ColArgs args(float *posm, float *vel, size_t n) const;
     cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches);

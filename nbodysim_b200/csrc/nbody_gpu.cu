@@ -238,12 +238,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     size_t cl_max = 65536;                      // scenes up to this size run their build / collision pass as one cluster kernel (sort_impl = 0)
     if (const char *cm = getenv("NBODY_CLUSTER_MAX_N")) cl_max = (size_t)std::max(0ll, atoll(cm));
     if (ctx->p.collide) {
-        const cudaError_t ce = d.col.alloc(ctx->n, ctx->p.sort_impl, cl_max);
-        if (ce == cudaErrorNotSupported) {
-            set_err(ctx, "sort_impl = 2 (single-cluster collision pass) needs a device that can host a cluster of >= 8 CTAs and n <= CTAs x 24576");
-            return NBODY_EINVAL;
-        }
-        CU(ce);
+        CU(d.col.alloc(ctx->n, ctx->p.sort_impl, cl_max));
         d.col.status = d.d_status;
     }
     if (ctx->bh) {
