@@ -67,41 +67,58 @@ __global__ void __launch_bounds__(256) col_grid_detect_kernel(ColArgs a, ColGrid
     col_grid_detect(a, g, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-// ---- the full pass as ONE CTA (small scenes) ----------------------------------------------------------------------------------
-// Launched after the screening of every pass, it returns at once unless the screening saw an overlap: a step without
-// collisions costs a memset, two short kernels and this empty launch.  When it does run, the phases of the full pass
-// follow one another separated by CTA-wide barriers (the cluster primitives with a cluster of one CTA; sort ranks in a
-// global scratch array).  Collisions are rare events in the scenes this path serves, so its own speed matters little.
+__global__ void __launch_bounds__(256) col_grid_pairs_kernel(ColArgs a, ColGrid g)
+{
+    col_grid_pairs(a, g, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// ---- small scenes: the rest of the pass as ONE CTA ------------------------------------------------------------------------------
+// The shipped scene has a few hundred sweep pairs among its 25,000 bodies and, once bodies start falling into the
+// central mass, a few dozen collisions per step: too little work to spread over launches.  One CTA takes the pair list
+// of col_grid_pairs and, unless nothing overlaps, runs the remaining phases separated by CTA barriers: union-find over
+// the pairs, hot components, the kept pairs keyed (component, first, second), their sort (cluster_prims.cuh with a
+// cluster of one CTA), and the resolve -- one thread per component, pairs in canonical order.
 __global__ void __launch_bounds__(CL_THREADS, 1)
-col_single_cta_kernel(ColArgs a, unsigned long long *keys_b, unsigned *vals_b, unsigned long long *pairs_b, unsigned *ranks, int key_bits)
+col_finish_kernel(ColArgs a, ColGrid g, unsigned long long *pairs_b, unsigned *ranks, int key_bits)
 {
     __shared__ ClSmem sm;
-    const unsigned gtid = threadIdx.x, gthreads = CL_THREADS;
-    if (gtid < 8) a.counters[gtid] = 0;                                   // the statistics of a pass that found nothing
-    if (col_gate_closed(a)) return;
-    a.gate = nullptr;
-    cl_sync();
-    col_phase_init(a, gtid, gthreads);
-    cl_sync();
-    col_phase_entries(a, gtid, gthreads);
-    cl_sync();
-    const unsigned ne = min(__ldcg(a.counters + 0), a.entry_cap);
-    if (__ldcg(a.counters + 2)) return;                                   // uniform: every thread reads the same word
-    if (cl_radix_sort<true>(sm, ranks, a.keys_in, keys_b, a.vals_in, vals_b, ne, 0, COL_GROUP_BITS)) { a.keys = keys_b; a.vals = vals_b; }
-    else { a.keys = a.keys_in; a.vals = a.vals_in; }
-    col_phase_pairs<0>(a, gtid, gthreads);
-    cl_sync();
-    if (__ldcg(a.counters + 4) == 0) return;                              // no SWEEP pair overlaps: no resolve could pass its test
-    col_phase_pairs<1>(a, gtid, gthreads);
-    cl_sync();
-    col_phase_mark(a, gtid, gthreads);
-    cl_sync();
-    col_phase_pairs<2>(a, gtid, gthreads);
-    cl_sync();
+    const unsigned tid = threadIdx.x;
+    if (tid < 8) a.counters[tid] = 0;                                     // the statistics of a pass that found nothing
+    const unsigned P = min(__ldcg(g.flags + 2), a.pair_cap);
+    if (__ldcg(g.flags + 0) == 0u || P == 0u || __ldcg(g.flags + 2) > a.pair_cap) return;   // uniform
+    __syncthreads();
+    const int b = a.idx_bits;
+    const unsigned long long imask = (1ull << b) - 1ull;
+    for (unsigned p = tid; p < P; p += CL_THREADS) {                      // the bodies that occur in pairs: singleton sets, cold
+        const unsigned long long k = a.pairs[p];
+        const unsigned f = (unsigned)((k >> b) & imask), s2 = (unsigned)(k & imask);
+        a.parent[f] = f; a.parent[s2] = s2;
+        a.hot[a.n + f] = 0; a.hot[a.n + s2] = 0;
+    }
+    __syncthreads();
+    for (unsigned p = tid; p < P; p += CL_THREADS) {
+        const unsigned long long k = a.pairs[p];
+        uf_union(a.parent, (unsigned)((k >> b) & imask), (unsigned)(k & imask));
+    }
+    __syncthreads();
+    for (unsigned p = tid; p < P; p += CL_THREADS) {
+        const unsigned long long k = a.pairs[p];
+        if (k & COL_OVERLAP_BIT) a.hot[a.n + uf_find(a.parent, (unsigned)((k >> b) & imask))] = 1;
+    }
+    __syncthreads();
+    for (unsigned p = tid; p < P; p += CL_THREADS) {
+        const unsigned long long k = a.pairs[p] & ~COL_OVERLAP_BIT;
+        const unsigned root = uf_find(a.parent, (unsigned)((k >> b) & imask));
+        if (a.hot[a.n + root]) {
+            const unsigned q = atomicAdd(&a.counters[1], 1u);
+            pairs_b[q] = a.rooted ? (k | ((unsigned long long)root << (2 * b))) : k;
+        }
+    }
+    if (tid == 0) { a.counters[4] = __ldcg(g.flags + 0); a.counters[0] = __ldcg(g.flags + 1); }
+    __syncthreads();
     const unsigned np = __ldcg(a.counters + 1);
-    if (__ldcg(a.counters + 2) || np > a.pair_cap) return;
-    const unsigned long long *sorted = cl_radix_sort<false>(sm, ranks, a.pairs, pairs_b, nullptr, nullptr, np, 0, key_bits) ? pairs_b : a.pairs;
-    col_phase_resolve(a, sorted, gtid, gthreads);
+    const unsigned long long *sorted = cl_radix_sort<false>(sm, ranks, pairs_b, a.pairs, nullptr, nullptr, np, 0, key_bits) ? a.pairs : pairs_b;
+    col_phase_resolve(a, sorted, tid, CL_THREADS);
 }
 
 // single_cta_mode: 0 = scenes of up to single_cta_max_n bodies run their (rare) full pass as one CTA, 1 = never (one
@@ -168,21 +185,19 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     unsigned *cnt = (unsigned *)counters;
     ColArgs a = args(posm, vel, n);
     const int key_bits = std::min(64, (((a.rooted ? 3 : 2) * a.idx_bits + 7) / 8) * 8);
-    {   // screening: hash-grid insert + overlap test; everything after it is gated on its flag
-        ColGrid g;
-        g.flags = (unsigned *)grid;
-        g.tkeys = (unsigned long long *)((char *)grid + 64);
-        g.heads = (unsigned *)((char *)grid + 64 + (size_t)table_slots * 8);
-        g.enext = (unsigned *)grid_links; g.ebody = (unsigned *)grid_links + entry_cap;
-        g.tmask = table_slots - 1; g.ecap = entry_cap;
-        if ((e = cudaMemsetAsync(grid, 0, grid_bytes, st)) != cudaSuccess) return e;
-        const unsigned gb = (unsigned)((n + 255) / 256);
-        col_grid_insert_kernel<<<gb, 256, 0, st>>>(a, g);
-        col_grid_detect_kernel<<<gb, 256, 0, st>>>(a, g);
-        if (launches) *launches += 2;
-    }
-    if (single_cta) {
-        // an explicit cluster of ONE CTA: the phase barriers are the cluster primitives of cluster_prims.cuh
+    // the hash grid over the bodies' cells; what follows it is gated on whether anything overlaps
+    ColGrid g;
+    g.flags = (unsigned *)grid;
+    g.tkeys = (unsigned long long *)((char *)grid + 64);
+    g.heads = (unsigned *)((char *)grid + 64 + (size_t)table_slots * 8);
+    g.enext = (unsigned *)grid_links; g.ebody = (unsigned *)grid_links + entry_cap;
+    g.tmask = table_slots - 1; g.ecap = entry_cap;
+    if ((e = cudaMemsetAsync(grid, 0, grid_bytes, st)) != cudaSuccess) return e;
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    col_grid_insert_kernel<<<gb, 256, 0, st>>>(a, g);
+    if (single_cta) {   // small scene: sweep pairs straight from the grid, everything else in one CTA
+        col_grid_pairs_kernel<<<gb, 256, 0, st>>>(a, g);
+        // an explicit cluster of ONE CTA: its sort uses the cluster primitives of cluster_prims.cuh
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(1); cfg.blockDim = dim3(CL_THREADS); cfg.stream = st;
@@ -190,11 +205,12 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
         at.id = cudaLaunchAttributeClusterDimension;
         at.val.clusterDim.x = 1; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, col_single_cta_kernel, a, (unsigned long long *)keys, (unsigned *)vals, (unsigned long long *)pairs,
-                                    (unsigned *)ranks, key_bits)) != cudaSuccess) return e;
-        if (launches) *launches += 1;
+        if ((e = cudaLaunchKernelEx(&cfg, col_finish_kernel, a, g, (unsigned long long *)pairs, (unsigned *)ranks, key_bits)) != cudaSuccess) return e;
+        if (launches) *launches += 3;
         return cudaGetLastError();
     }
+    col_grid_detect_kernel<<<gb, 256, 0, st>>>(a, g);
+    if (launches) *launches += 2;
     const unsigned gn = (unsigned)((n + 255) / 256), ge = (entry_cap + 255) / 256;
     col_init_kernel<<<gn, 256, 0, st>>>(a);
     col_entries_kernel<<<gn, 256, 0, st>>>(a);

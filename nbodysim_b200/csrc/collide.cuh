@@ -197,6 +197,46 @@ __device__ __forceinline__ bool col_sweep_pair(const ColBody &a, unsigned ia, co
     return true;
 }
 
+// Small scenes: the sweep pairs themselves come straight from the hash grid -- body i lists, for every cell it covers,
+// the bodies of that cell whose x interval overlaps its own and for which i is the pair's `first` (so every (pair, shared
+// cell) is produced exactly once, as by the reference's sweep) -- key (first, second), bit 63 = the pair overlaps now.
+// flags[2] counts the pairs, flags[0] the overlapping ones.
+constexpr unsigned long long COL_OVERLAP_BIT = 1ull << 63;
+__device__ __forceinline__ void col_grid_pairs(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads)
+{
+    unsigned overlaps = 0;
+    for (unsigned i = gtid; i < a.n; i += gthreads) {
+        const ColBody A = col_load(a.posm, a.vel, i);
+        int minX, maxX, minY, maxY;
+        if (!col_cell_range(A, minX, maxX, minY, maxY)) continue;
+        for (int y = minY; y <= maxY; ++y)
+            for (int x = minX; x <= maxX; ++x) {
+                const unsigned long long key = (1ull << 32) | (unsigned)col_hash(x, y);
+                unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
+                for (unsigned probes = 0; probes <= g.tmask; ++probes) {
+                    const unsigned long long k = g.tkeys[slot];
+                    if (k == key || k == 0ull) break;
+                    slot = (slot + 1) & g.tmask;
+                }
+                if (g.tkeys[slot] != key) continue;
+                for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
+                    const unsigned j = g.ebody[e - 1u];
+                    if (j == i) continue;
+                    const ColBody B = col_load(a.posm, a.vel, j);
+                    unsigned first, second;
+                    if (!col_sweep_pair(A, i, B, j, first, second) || first != i) continue;
+                    const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
+                    const bool overlap = !(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r));
+                    const unsigned p = atomicAdd(&g.flags[2], 1u);
+                    if (p < a.pair_cap) a.pairs[p] = ((unsigned long long)first << a.idx_bits) | second | (overlap ? COL_OVERLAP_BIT : 0ull);
+                    else col_overflow(a);
+                    overlaps += overlap ? 1u : 0u;
+                }
+            }
+    }
+    if (overlaps) atomicAdd(&g.flags[0], overlaps);
+}
+
 // Enumerate the sweep pairs (one thread per cell entry: the pairs it forms with the later entries of its cell).
 //   MODE 0  detect: mark the bodies of pairs that overlap now (Simulation.hpp:301: d.mag_sq() <= r*r) and count them
 //   MODE 1  connect: union the two bodies of every sweep pair            (only when something overlaps)
