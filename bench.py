@@ -118,16 +118,19 @@ def pinned_bodies(n):
 
 
 def ncu_traffic_bytes():
-    """DRAM bytes per force launch from the committed ncu capture (None if absent)."""
-    try:
-        tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r1_force_uniform_ncu.txt")):
-            f = line.split()
-            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
-        return tot or None
-    except Exception:
-        return None
+    """DRAM bytes per force launch from the newest committed ncu capture of the headline kernel (None if absent)."""
+    for name in ("r2_force_streamk_ncu.txt", "r1_force_uniform_ncu.txt"):
+        try:
+            tot = 0.0
+            for line in open(os.path.join(ROOT, "profiles", name)):
+                f = line.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+            if tot:
+                return {"bytes": tot, "file": "profiles/" + name}
+        except Exception:
+            continue
+    return None
 
 
 def fp32_peak_tflops(info, sm_max_mhz):
@@ -693,11 +696,15 @@ def native_arm(args):
     }
     tr = ncu_traffic_bytes()
     if tr is not None and n == 1048576 and world == 1:
-        roof["traffic"] = tr
+        roof["traffic"] = tr["bytes"]
         roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this N from the committed "
-                                  "ncu --set full capture profiles/r1_force_uniform_ncu.txt")
-    # bytes the kernel must move per launch: every source once (16 B) + one 12-byte partial per target and split
-    roof["algorithmic_bytes"] = n * 16 + (n / world) * 12 * max(1, i1["j_splits"])
+                                  f"ncu --set full capture {tr['file']}")
+    # algorithmic bytes per launch: every source read once (16 B) + one 12-byte sum per target; what the kernel
+    # really writes on top of that are its partial-sum slots (stream-K: the CTAs that share a target tile, two at N = 1M)
+    roof["algorithmic_bytes"] = n * 16 + (n / world) * 12
+    roof["partial_slots_max"] = max(1, i1["j_splits"])
+    roof["partial_slot_bytes_upper_bound"] = (n / world) * 12 * max(1, i1["j_splits"])
+    roof["form"] = f"stream-K, {i1['streamk_ctas']} persistent CTAs" if i1["streamk_ctas"] else f"split, {i1['j_splits']} source splits"
     if clocks and clocks.get("sm_mhz"):
         roof["frac_at_observed_clock"] = achieved_tf / (peak_tf * clocks["sm_mhz"] / peak_mhz)
     try:
@@ -731,7 +738,7 @@ def native_arm(args):
                                     "flags in peer memory; no collective call)" if i1["p2p_exchange"] == 2 else
                                     "ncclAllGather on a communication stream") if world > 1 else "one GPU"),
                    "exchange": {0: "nccl_allgather", 1: "peer_stores_one_process", 2: "peer_stores_ipc"}[i1["p2p_exchange"]] if world > 1 else None,
-                   "l2": "flushed (256 MiB write) before every timed step", "j_splits": i1["j_splits"],
+                   "l2": "flushed (256 MiB write) before every timed step", "j_splits": i1["j_splits"], "streamk_ctas": i1["streamk_ctas"],
                    "force_ctas": i1["force_ctas"], "ctas_per_sm": i1["ctas_per_sm"], "fused_integrator": bool(i1["fused"]),
                    "mass_form": ("uniform-mass (equal masses detected: 11 fp32 lane-ops per interaction)" if i1["uniform_mass"]
                                  else "general masses (12 fp32 lane-ops per interaction)")},

@@ -77,7 +77,9 @@ typedef struct nbody_params {
     float    soft_boundary;   /* 0.8      Simulation.hpp:121 (fraction of boundary_radius) */
     float    boundary_force;  /* 0.9      Simulation.hpp:122 */
     float    damping;         /* 0.9995   Simulation.hpp:123 */
-    int32_t  j_splits;        /* 0 = auto; >0 forces the number of source-range splits */
+    int32_t  j_splits;        /* 0 = auto: the fast fp32 kernel runs in stream-K form (one persistent CTA per SM slot, equal runs of
+                                 (target tile, source stage) units; at most a few partial slots per target); > 0 forces the split
+                                 form with that many source-range splits (one partial slot per split) */
     int32_t  fuse_integrator; /* -1 = auto; 0 = separate integrator kernel; 1 (with j_splits = 1) = kick-drift fused
                                  into the force kernel's epilogue (2048-target tiles) */
     int32_t  use_graph;       /* -1 = auto (launch-bound sizes: n <= 32768, Barnes-Hut n <= 262144), 0 = never, 1 = always:
@@ -135,14 +137,15 @@ typedef struct nbody_info {
                                  2 = across processes (CUDA IPC mappings + completion flags in peer memory); 0 = NCCL */
     int32_t  sm_count;        /* of the first local device */
     int32_t  sm_clock_khz;    /* cudaDevAttrClockRate */
-    int32_t  j_splits;        /* source-range splits chosen for the force kernel */
+    int32_t  j_splits;        /* partial-sum slots per target of the (first) force launch: the source-range splits of the split form,
+                                 or the most CTAs that share a target tile in the stream-K form (see streamk_ctas) */
     int32_t  force_ctas;      /* CTAs per force launch (per GPU) */
     int32_t  ctas_per_sm;     /* resident force CTAs per SM (occupancy query) */
     int32_t  fused;           /* 1 if the kick-drift runs in the force kernel's epilogue */
     int32_t  uniform_mass;    /* 1 if the fast kernel runs the uniform-mass (11-op) form */
     int32_t  graph;           /* 1 if multi-step calls replay a CUDA graph */
     uint32_t bh_nodes;        /* Barnes-Hut: non-empty cells of the last tree built */
-    uint32_t reserved0;
+    uint32_t streamk_ctas;    /* > 0: the fast fp32 kernel runs its stream-K form on that many persistent CTAs */
     uint64_t kernel_launches; /* kernels of this library launched so far (all local GPUs) */
     uint64_t interactions;    /* pair interactions evaluated so far by this process */
     float    last_force_ms;   /* device time of the force kernel(s) of the last profiled step (Barnes-Hut: tree build + walk) */

@@ -76,7 +76,7 @@ class NbodyInfo(C.Structure):
         ("uniform_mass", C.c_int32),
         ("graph", C.c_int32),
         ("bh_nodes", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("streamk_ctas", C.c_uint32),
         ("kernel_launches", C.c_uint64),
         ("interactions", C.c_uint64),
         ("last_force_ms", C.c_float),

@@ -295,33 +295,45 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
         const unsigned par = a.w;
         if (par == 0xffffffffu || par >= m) break;                     // reached the root
         const unsigned q = (a.z >> 9) & (NCHILD - 1u);
-        __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, z, mass));
-        __stcg(&nodes.slot_cells[(size_t)par * NCHILD + q], cells);
-        __threadfence();                                               // my deposit is visible before I announce it
-        const unsigned old = atomicAdd(&arrive[par], 0x100u);
-        if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;         // a sibling will arrive later and do the work
-        __threadfence();
-        const unsigned mask = (old >> 16) & 0xffu;
-        float4 ch[NCHILD];
-        unsigned sub[NCHILD];
-#pragma unroll
-        for (unsigned k = 0; k < NCHILD; ++k) {
-            const bool occ = (mask >> k) & 1u;
-            ch[k] = occ ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            sub[k] = occ ? __ldcg(&nodes.slot_cells[(size_t)par * NCHILD + k]) : 0u;
-        }
-        a = __ldcg(nodes.aux(par));                                    // independent of the sums below: issued with the slots
+        // everything about the parent that does not depend on its other children, requested at once
+        const unsigned pinfo = __ldcg(&arrive[par]);                   // low byte: number of children (counted by the emit kernel)
+        const uint4 pa = __ldcg(nodes.aux(par));
         float4 dp = __ldcg(nodes.data(par));
         float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
-        cells = 1;
+        if ((pinfo & 0xffu) == 1u) {
+            // an only child (the chains of single-child cells above two close bodies): nobody to wait for, nothing to
+            // publish -- the same sum over "the children in quadrant order", with one term
+            px = __fadd_rn(px, __fmul_rn(x, mass));
+            py = __fadd_rn(py, __fmul_rn(y, mass));
+            if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(z, mass));
+            ms = __fadd_rn(ms, mass);
+            cells += 1;
+        } else {
+            __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, z, mass));
+            __stcg(&nodes.slot_cells[(size_t)par * NCHILD + q], cells);
+            __threadfence();                                           // my deposit is visible before I announce it
+            const unsigned old = atomicAdd(&arrive[par], 0x100u);
+            if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;     // a sibling will arrive later and do the work
+            __threadfence();
+            const unsigned mask = (old >> 16) & 0xffu;
+            float4 ch[NCHILD];
+            unsigned sub[NCHILD];
 #pragma unroll
-        for (unsigned k = 0; k < NCHILD; ++k) {
-            if ((mask >> k) & 1u) {                                    // children in quadrant order
-                px = __fadd_rn(px, __fmul_rn(ch[k].x, ch[k].w));
-                py = __fadd_rn(py, __fmul_rn(ch[k].y, ch[k].w));
-                if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch[k].z, ch[k].w));
-                ms = __fadd_rn(ms, ch[k].w);
-                cells += sub[k];
+            for (unsigned k = 0; k < NCHILD; ++k) {
+                const bool occ = (mask >> k) & 1u;
+                ch[k] = occ ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                sub[k] = occ ? __ldcg(&nodes.slot_cells[(size_t)par * NCHILD + k]) : 0u;
+            }
+            cells = 1;
+#pragma unroll
+            for (unsigned k = 0; k < NCHILD; ++k) {
+                if ((mask >> k) & 1u) {                                // children in quadrant order
+                    px = __fadd_rn(px, __fmul_rn(ch[k].x, ch[k].w));
+                    py = __fadd_rn(py, __fmul_rn(ch[k].y, ch[k].w));
+                    if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch[k].z, ch[k].w));
+                    ms = __fadd_rn(ms, ch[k].w);
+                    cells += sub[k];
+                }
             }
         }
         if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
@@ -335,6 +347,7 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
         if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(par)), pz);
         reinterpret_cast<unsigned *>(nodes.aux(par))[1] = (par + cells < total) ? par + cells : 0u;
         x = px; y = py; z = pz; mass = ms;
+        a = pa;
         c = par;
     }
 }

@@ -117,7 +117,25 @@ col_finish_kernel(ColArgs a, ColGrid g, unsigned long long *pairs_b, unsigned *r
     if (tid == 0) { a.counters[4] = __ldcg(g.flags + 0); a.counters[0] = __ldcg(g.flags + 1); }
     __syncthreads();
     const unsigned np = __ldcg(a.counters + 1);
-    const unsigned long long *sorted = cl_radix_sort<false>(sm, ranks, pairs_b, a.pairs, nullptr, nullptr, np, 0, key_bits) ? a.pairs : pairs_b;
+    const unsigned long long *sorted;
+    constexpr unsigned RANK_SORT_MAX = sizeof(sm.counts) / sizeof(unsigned long long);   // 2048 keys fit the counter array
+    if (np <= RANK_SORT_MAX) {
+        // a handful of pairs: rank sort in shared memory (every key counts the keys before it; ties -- the same pair met in
+        // several shared cells -- keep their order), one barrier instead of 6 radix digits
+        unsigned long long *sk = reinterpret_cast<unsigned long long *>(&sm.counts[0][0]);
+        for (unsigned p = tid; p < np; p += CL_THREADS) sk[p] = pairs_b[p];
+        __syncthreads();
+        for (unsigned p = tid; p < np; p += CL_THREADS) {
+            const unsigned long long k = sk[p];
+            unsigned r = 0;
+            for (unsigned q = 0; q < np; ++q) { const unsigned long long o = sk[q]; r += (o < k || (o == k && q < p)) ? 1u : 0u; }
+            a.pairs[r] = k;
+        }
+        __syncthreads();
+        sorted = a.pairs;
+    } else {
+        sorted = cl_radix_sort<false>(sm, ranks, pairs_b, a.pairs, nullptr, nullptr, np, 0, key_bits) ? a.pairs : pairs_b;
+    }
     col_phase_resolve(a, sorted, tid, CL_THREADS);
 }
 

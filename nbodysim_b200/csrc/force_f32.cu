@@ -21,6 +21,7 @@
 //    guard, and accumulation over sources in index order 0..n-1 by a single thread per target,
 //    so accelerations equal the reference's (strict build) bit for bit.
 #include "force_f32_fast.cuh"
+#include <cstring>
 
 namespace nb {
 
@@ -136,6 +137,54 @@ static cudaError_t launch_fast_d(const ForceLaunch &L, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <typename C, int FORM, bool GUARD, int DIMS>
+static cudaError_t launch_streamk_d(const ForceLaunch &L, cudaStream_t st)
+{
+    using RingT = Ring<BLK_ELEMS, C::STAGE>;
+    auto kern = force_f32_streamk_kernel<C::I, C::THREADS, C::MINB, C::UNROLL, C::STAGE, FORM, GUARD, DIMS>;
+    FastArgs a;
+    memset(&a, 0, sizeof a);
+    a.posm = (const float *)L.posm;
+    a.accp = (float *)L.accp;
+    a.i_blk0 = L.i_blk0; a.i_blk_local0 = L.i_blk_local0; a.n_iblk_shard = L.n_iblk_shard;
+    a.j_blk0 = L.j_blk0; a.j_nblk = L.j_nblk; a.splits = 1; a.slot0 = L.slot0;
+    a.n_tiles = L.n_iblk / C::TILE_BLKS;
+    a.eps2 = L.eps2; a.acc_scale = L.acc_scale; a.n_real = L.j_body_limit;
+    kern<<<L.streamk_ctas, C::THREADS, RingT::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+template <int FORM, bool GUARD>
+static cudaError_t launch_streamk_t(const ForceLaunch &L, cudaStream_t st)
+{
+    if (L.small_tile) return L.dims == 2 ? launch_streamk_d<SmallCfg, FORM, GUARD, 2>(L, st) : launch_streamk_d<SmallCfg, FORM, GUARD, 3>(L, st);
+    return L.dims == 2 ? launch_streamk_d<LargeCfg, FORM, GUARD, 2>(L, st) : launch_streamk_d<LargeCfg, FORM, GUARD, 3>(L, st);
+}
+
+int force_f32_streamk_slots(int tiles, int stages, int ctas)
+{
+    const long long U = (long long)tiles * stages;
+    int worst = 1;
+    for (int t = 0; t < tiles; ++t)
+        worst = std::max(worst, sk_owner((long long)t * stages + stages - 1, U, ctas) - sk_owner((long long)t * stages, U, ctas) + 1);
+    return worst;
+}
+
+int force_f32_streamk_ctas_per_sm(bool uniform_mass, bool small_tile)
+{
+    int n = 0;
+    cudaError_t e;
+    if (small_tile) {
+        using RingT = Ring<BLK_ELEMS, SMALL_STAGE_BLKS>;
+        e = uniform_mass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_UNIFORM, false, 3>, SMALL_THREADS, RingT::SMEM)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_PLAIN, false, 3>, SMALL_THREADS, RingT::SMEM);
+    } else {
+        using RingT = Ring<BLK_ELEMS, FAST_STAGE_BLKS>;
+        e = uniform_mass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_UNIFORM, false, 3>, FAST_THREADS, RingT::SMEM)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_PLAIN, false, 3>, FAST_THREADS, RingT::SMEM);
+    }
+    return e == cudaSuccess ? n : 0;
+}
+
 template <int FORM, bool GUARD, bool FUSE>
 static cudaError_t launch_fast_t(const ForceLaunch &L, cudaStream_t st)
 {
@@ -155,6 +204,15 @@ int force_f32_fast_grid(const ForceLaunch &L)
 cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStream_t st)
 {
     const int tile = L.small_tile ? SMALL_TILE_BLKS : FAST_TILE_BLKS;
+    if (L.streamk_ctas > 0) {
+        if (L.n_iblk % tile != 0 || L.j_nblk < 1 || L.fuse) return cudaErrorInvalidValue;
+        switch ((L.uniform_mass ? 2 : 0) | (guard_zero ? 1 : 0)) {
+        case 0: return launch_streamk_t<FORM_PLAIN, false>(L, st);
+        case 1: return launch_streamk_t<FORM_PLAIN, true>(L, st);
+        case 2: return launch_streamk_t<FORM_UNIFORM, false>(L, st);
+        default: return launch_streamk_t<FORM_UNIFORM, true>(L, st);
+        }
+    }
     if (L.n_iblk % tile != 0 || L.splits < 1 || L.j_nblk < L.splits) return cudaErrorInvalidValue;
     if (L.fuse && (L.splits != 1 || L.small_tile)) return cudaErrorInvalidValue;
     const int v = (L.uniform_mass ? 4 : 0) | (guard_zero ? 2 : 0) | (L.fuse ? 1 : 0);
@@ -215,7 +273,7 @@ cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st)
 __device__ __forceinline__ void
 integrate_f32_group(const float *__restrict__ posm_cur, const PeerDests &dests,
                     float *__restrict__ vel, float *__restrict__ acc,
-                    const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                    const float *__restrict__ accp, float acc_scale, const SlotPlan &slots, int i_blk0,
                     int n_iblk_shard, int acc_only, long long n_real, const IntegParams &ip)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // one per 4 bodies
@@ -226,12 +284,20 @@ integrate_f32_group(const float *__restrict__ posm_cur, const PeerDests &dests,
     const size_t goff = (size_t)(i_blk0 + lb) * BLK_ELEMS + q;
 
     float4 A[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
-    for (int s = 0; s < nslots; ++s) {
-        const float *p = accp + (size_t)s * n_iblk_shard * BLK_ELEMS + loff;
+    for (int r = 0; r < slots.n; ++r) {                      // the launches of the step in order, each launch's slots in order
+        const SlotRange &R = slots.r[r];
+        int ns = R.nslots;
+        if (R.sk_S > 0) {                                    // stream-K launch: the CTAs that shared this block's tile
+            const long long u0 = (long long)(lb / R.tile_blks) * R.sk_S;
+            ns = sk_owner(u0 + R.sk_S - 1, R.sk_U, R.sk_G) - sk_owner(u0, R.sk_U, R.sk_G) + 1;
+        }
+        for (int s = 0; s < ns; ++s) {
+            const float *p = accp + (size_t)(R.slot0 + s) * n_iblk_shard * BLK_ELEMS + loff;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float4 v = *reinterpret_cast<const float4 *>(p + c * BLK);
-            A[c].x += v.x; A[c].y += v.y; A[c].z += v.z; A[c].w += v.w;
+            for (int c = 0; c < 3; ++c) {
+                const float4 v = *reinterpret_cast<const float4 *>(p + c * BLK);
+                A[c].x += v.x; A[c].y += v.y; A[c].z += v.z; A[c].w += v.w;
+            }
         }
     }
 #pragma unroll
@@ -269,10 +335,10 @@ integrate_f32_group(const float *__restrict__ posm_cur, const PeerDests &dests,
 __global__ void __launch_bounds__(256)
 integrate_f32_kernel(const float *__restrict__ posm_cur, PeerDests dests, PeerSignal sig,
                      float *__restrict__ vel, float *__restrict__ acc,
-                     const float *__restrict__ accp, float acc_scale, int nslots, int i_blk0,
+                     const float *__restrict__ accp, float acc_scale, SlotPlan slots, int i_blk0,
                      int n_iblk_shard, int acc_only, long long n_real, IntegParams ip)
 {
-    integrate_f32_group(posm_cur, dests, vel, acc, accp, acc_scale, nslots, i_blk0, n_iblk_shard, acc_only, n_real, ip);
+    integrate_f32_group(posm_cur, dests, vel, acc, accp, acc_scale, slots, i_blk0, n_iblk_shard, acc_only, n_real, ip);
     signal_peers_when_grid_done(sig);
 }
 
@@ -282,7 +348,7 @@ cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st)
     const int grid = (threads + 255) / 256;
     integrate_f32_kernel<<<grid, 256, 0, st>>>((const float *)L.posm_cur, L.dests, L.signal,
                                                (float *)L.vel, (float *)L.acc,
-                                               (const float *)L.accp, L.acc_scale, L.nslots, L.i_blk0,
+                                               (const float *)L.accp, L.acc_scale, L.slots, L.i_blk0,
                                                L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
     return cudaGetLastError();
 }

@@ -83,6 +83,12 @@ struct Ring {
         tma_bulk_g2s(stage + (size_t)s * STAGE_FLOATS,
                      src_blocks + (size_t)t * STAGE_BLKS * SRC_BLK_ELEMS, bytes, &full[s]);
     }
+    // stage buffer s <- `bytes` bytes at gsrc (whole source blocks)
+    __device__ __forceinline__ void issue_raw(int s, const float *gsrc, uint32_t bytes) const
+    {
+        mbar_expect_tx(&full[s], bytes);
+        tma_bulk_g2s(stage + (size_t)s * STAGE_FLOATS, gsrc, bytes, &full[s]);
+    }
     // consumer side of stage t is done; thread 0 refills the buffer of the PREVIOUS stage
     __device__ __forceinline__ void release_and_refill(const float *src_blocks, int t, int nst,
                                                        int chunk_blks) const
@@ -171,6 +177,7 @@ struct FastArgs {
     const float *posm;       // blocked (x,y,z,m): sources and targets
     float *accp;
     int i_blk0, i_blk_local0, n_iblk_shard, j_blk0, j_nblk, splits, slot0;
+    int n_tiles;             // stream-K kernel: target tiles of the launch
     float eps2;
     float acc_scale;         // fused epilogue factor: G (plain) or G*m (uniform)
     long long n_real;
@@ -275,6 +282,110 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_fast_kernel(const Fas
             float *o = a.accp + (size_t)(a.slot0 + split) * a.n_iblk_shard * BLK_ELEMS + loff;
             o[0] = fx; o[BLK] = fy; o[2 * BLK] = fz;
         }
+    }
+}
+
+// ---- stream-K form of the same kernel ---------------------------------------------------------------------------------------
+// The work of a launch is (target tiles) x (source stages).  The split form above cuts it into tiles x splits CTAs and
+// every CTA writes one partial sum per target -- 13 partial slots at N = 1M, 116 MB written by the force kernel and
+// read back by the integrator.  Here the launch is ONE persistent CTA per SM slot, and the tile-major sequence of
+// (tile, stage) units is dealt out in equal contiguous runs: CTA k takes units [k U / G, (k+1) U / G).  Inside a run the
+// TMA ring never drains -- the source stage of a unit does not depend on the tile, so crossing a tile boundary only
+// means storing the finished partial sum and loading the next tile's targets while the ring keeps prefetching.  A tile
+// is shared by at most (stages per tile) / (units per CTA) + 2 CTAs -- two at N = 1M -- each writing its own slot, in
+// unit order; the integrator derives the number of slots of a tile from the same arithmetic and sums them in that
+// order (deterministic).  Balance: every CTA gets the same number of units to within one stage (512 sources).
+__host__ __device__ __forceinline__ long long sk_start(long long k, long long U, int G) { return (k * U) / G; }
+__host__ __device__ __forceinline__ int sk_owner(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
+
+template <int I, int THREADS, int MINB, int UNROLL, int STAGE_BLKS, int FORM, bool GUARD, int DIMS = 3>
+__global__ void __launch_bounds__(THREADS, MINB) force_f32_streamk_kernel(const FastArgs a)
+{
+    constexpr int SRC_ELEMS = BLK_ELEMS;
+    using RingT = Ring<SRC_ELEMS, STAGE_BLKS>;
+    constexpr int LANES_PER_BLK = BLK / THREADS;
+    static_assert(BLK % THREADS == 0 && I % LANES_PER_BLK == 0, "tile shape");
+    constexpr int TILE_BLKS = I / LANES_PER_BLK;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int S = (a.j_nblk + STAGE_BLKS - 1) / STAGE_BLKS;              // source stages per tile
+    const long long U = (long long)a.n_tiles * S;
+    const int G = (int)gridDim.x;
+    const long long g0 = sk_start(blockIdx.x, U, G), g1 = sk_start((long long)blockIdx.x + 1, U, G);
+    const int nst = (int)(g1 - g0);
+    if (nst <= 0) return;                                                // more CTAs than units
+    RingT ring;
+    ring.setup(smem_raw, THREADS / 32);
+    const int tid = threadIdx.x;
+    const float *src = a.posm + (size_t)a.j_blk0 * SRC_ELEMS;
+    const int jst0 = (int)(g0 % S);
+    auto issue = [&](int t) {                                            // stage t of this CTA's run
+        const int jst = (jst0 + t) % S;
+        const int nb = min(STAGE_BLKS, a.j_nblk - jst * STAGE_BLKS);
+        ring.issue_raw(t % NSTAGE, src + (size_t)jst * STAGE_BLKS * SRC_ELEMS, (uint32_t)nb * SRC_ELEMS * 4u);
+    };
+    if (tid == 0) {
+        const int pre = min(NSTAGE, nst);
+        for (int t = 0; t < pre; ++t) issue(t);
+    }
+
+    float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
+    size_t tgt_off[I];
+    const float2 e2 = make_float2(a.eps2, a.eps2);
+    int tile = (int)(g0 / S), jst = jst0;
+    for (int t = 0; t < nst; ++t) {
+        if (t == 0 || jst == 0) {                                        // first unit of a tile (or of this CTA's share of it)
+#pragma unroll
+            for (int k = 0; k < I; ++k) {
+                const int blk = tile * TILE_BLKS + k / LANES_PER_BLK;
+                const int lane = (k % LANES_PER_BLK) * THREADS + tid;
+                tgt_off[k] = (size_t)blk * BLK_ELEMS + lane;
+                const float *b = a.posm + (size_t)a.i_blk0 * BLK_ELEMS + tgt_off[k];
+                const float x = b[0], y = b[BLK], z = b[2 * BLK];
+                nxi[k] = make_float2(-x, -x);
+                nyi[k] = make_float2(-y, -y);
+                nzi[k] = make_float2(-z, -z);
+                ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+            }
+        }
+        const int s = t % NSTAGE;
+        mbar_wait(&ring.full[s], (uint32_t)(t / NSTAGE) & 1u);
+        const float *st = ring.stage + (size_t)s * RingT::STAGE_FLOATS;
+        const int nb = min(STAGE_BLKS, a.j_nblk - jst * STAGE_BLKS);
+        for (int b = 0; b < nb; ++b) {
+            const float *sx = st + b * SRC_ELEMS;
+#pragma unroll UNROLL
+            for (int j = 0; j < BLK; j += 4) {
+                const float4 X = *reinterpret_cast<const float4 *>(sx + j);
+                const float4 Y = *reinterpret_cast<const float4 *>(sx + BLK + j);
+                const float4 Z = (DIMS == 3) ? *reinterpret_cast<const float4 *>(sx + 2 * BLK + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FORM == FORM_UNIFORM) {
+                    interact_pair_uniform<I, GUARD, DIMS>(lo2(X), lo2(Y), lo2(Z), nxi, nyi, nzi, ax, ay, az, e2);
+                    interact_pair_uniform<I, GUARD, DIMS>(hi2(X), hi2(Y), hi2(Z), nxi, nyi, nzi, ax, ay, az, e2);
+                    continue;
+                }
+                const float4 M = *reinterpret_cast<const float4 *>(sx + 3 * BLK + j);
+                interact_pair_plain<I, GUARD, DIMS>(lo2(X), lo2(Y), lo2(Z), lo2(M), nxi, nyi, nzi, ax, ay, az, e2);
+                interact_pair_plain<I, GUARD, DIMS>(hi2(X), hi2(Y), hi2(Z), hi2(M), nxi, nyi, nzi, ax, ay, az, e2);
+            }
+        }
+        // this stage's buffer is free; thread 0 refills the buffer of the PREVIOUS stage (see Ring::release_and_refill)
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&ring.empty[s]);
+        if (tid == 0 && t >= 1 && (t - 1 + NSTAGE) < nst) {
+            const int tp = t - 1;
+            mbar_wait(&ring.empty[tp % NSTAGE], (uint32_t)(tp / NSTAGE) & 1u);
+            issue(tp + NSTAGE);
+        }
+        if (jst == S - 1 || t == nst - 1) {                              // the tile (or this CTA's share of it) is done
+            const int slot = a.slot0 + (int)blockIdx.x - sk_owner((long long)tile * S, U, G);
+#pragma unroll
+            for (int k = 0; k < I; ++k) {
+                const float fx = ax[k].x + ax[k].y, fy = ay[k].x + ay[k].y, fz = az[k].x + az[k].y;
+                float *o = a.accp + (size_t)slot * a.n_iblk_shard * BLK_ELEMS + (size_t)a.i_blk_local0 * BLK_ELEMS + tgt_off[k];
+                o[0] = fx; o[BLK] = fy; o[2 * BLK] = fz;
+            }
+        }
+        if (++jst == S) { jst = 0; ++tile; }
     }
 }
 

@@ -180,10 +180,12 @@ integrate_f64_kernel(const double *__restrict__ posm_cur, PeerDests dests, PeerS
 
 cudaError_t launch_integrate_f64(const IntegLaunch &L, cudaStream_t st)
 {
+    int nslots = 0;                                       // fp64 launches are split launches: every slot of every range is filled
+    for (int r = 0; r < L.slots.n; ++r) nslots += L.slots.r[r].nslots;
     const int threads = L.n_iblk_shard * BLK;
     integrate_f64_kernel<<<(threads + 255) / 256, 256, 0, st>>>(
         (const double *)L.posm_cur, L.dests, L.signal, (double *)L.vel, (double *)L.acc,
-        (const double *)L.accp, L.acc_scale, L.nslots, L.i_blk0, L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
+        (const double *)L.accp, L.acc_scale, nslots, L.i_blk0, L.n_iblk_shard, L.acc_only, L.n_real, L.ip);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@ struct ForceLaunch {
     int j_blk0, j_nblk;      // source block range
     long long j_body_limit;  // sources >= this global body index are padding (refcompat skips them)
     int splits, slot0;
+    int streamk_ctas;        // fast kernel: > 0 = stream-K form with that many persistent CTAs (splits ignored); 0 = split form
     float eps2;
     double eps2_f64;
     // fused kick-drift epilogue (fast fp32 kernel, splits == 1, single launch per step)
@@ -55,6 +56,20 @@ struct PeerDests {
     int n;
 };
 
+// Which partial slots hold the sum of a target block.  A step's force launches each own a run of slots:
+//   split launch      `nslots` slots, all filled for every target
+//   stream-K launch   the slots of target tile T are slot0 .. slot0 + owner(T S + S - 1) - owner(T S), with
+//                     owner(u) = ((u + 1) G - 1) / U  (force_f32_fast.cuh)
+struct SlotRange {
+    int slot0, nslots;
+    int sk_S, sk_G, tile_blks;   // stream-K: source stages per tile (0 = split launch), CTAs, target blocks per tile
+    long long sk_U;              // stream-K: units of the launch (tiles x stages)
+};
+struct SlotPlan {
+    int n;
+    SlotRange r[4];
+};
+
 struct IntegLaunch {
     const void *posm_cur;    // blocked, full array
     void *posm_next;         // blocked, full array
@@ -63,7 +78,7 @@ struct IntegLaunch {
     void *vel, *acc;         // blocked, shard-local
     const void *accp;        // partial slots
     float acc_scale;         // G, or G*m when the uniform-mass force kernel summed unit masses
-    int nslots;
+    SlotPlan slots;
     int i_blk0;              // first global block of the shard
     int n_iblk_shard;
     int acc_only;            // 1: acc := G * sum(partials), no kick-drift (nbody_gpu_accel_only)
@@ -87,6 +102,9 @@ cudaError_t launch_force_f32_fast(const ForceLaunch &L, bool guard_zero, cudaStr
 cudaError_t launch_force_f32_refcompat(const ForceLaunch &L, cudaStream_t st);
 cudaError_t launch_force_f64(const ForceLaunch &L, cudaStream_t st);
 int force_f32_fast_ctas_per_sm(bool uniform_mass, bool small_tile = false);
+int force_f32_streamk_ctas_per_sm(bool uniform_mass, bool small_tile);
+// slots a stream-K launch of `tiles` target tiles x `stages` source stages on `ctas` CTAs needs (the most any tile uses)
+int force_f32_streamk_slots(int tiles, int stages, int ctas);
 int force_f32_fast_grid(const ForceLaunch &L);
 
 cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st);

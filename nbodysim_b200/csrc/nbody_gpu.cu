@@ -28,6 +28,7 @@ struct Range {          // one force launch of the per-step plan
     int j_blk0, j_nblk; // source blocks
     int splits, slot0;
     bool remote;        // needs the allgather of the previous step to have landed
+    int sk_ctas = 0;    // > 0: stream-K launch on that many persistent CTAs (fast fp32 kernel); `splits` then holds the slots it needs
 };
 
 struct Dev {
@@ -83,7 +84,7 @@ struct nbody_ctx {
     size_t esz = 4;
     std::vector<Dev> devs;
     nbody_body_t *h_stage = nullptr; // pinned, n records (download merges / uploads)
-    int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0, ctas_per_sm_small = 0;
+    int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0, ctas_per_sm_small = 0, sk_ctas_per_sm = 0, sk_ctas_per_sm_small = 0;
     unsigned long long launches = 0, interactions = 0;
     int profile_next = 0;
     float last_force_ms = 0.f, last_integ_ms = 0.f, last_build_ms = 0.f, last_collide_ms = 0.f;
@@ -176,7 +177,7 @@ int plan_device(nbody_ctx *c, Dev &d)
     struct Seg { int b0, nb; bool remote; };
     std::vector<Seg> segs;
     if (c->bh) { // one tree over all sources, one walk launch, one partial slot
-        d.plan.push_back({0, nblk, 1, 0, c->world > 1});
+        d.plan.push_back(Range{0, nblk, 1, 0, c->world > 1});
         d.nslots = 1;
         d.force_ctas = (int)((c->n + 127) / 128);
         return NBODY_OK;
@@ -189,17 +190,28 @@ int plan_device(nbody_ctx *c, Dev &d)
         if (ib0 + ibn < nblk) segs.push_back({ib0 + ibn, nblk - ib0 - ibn, true});
     }
     int slot = 0;
+    const bool fastk = !c->f64 && !refc;
     for (const Seg &s : segs) {
-        int S = 1;
-        if (!refc) {
+        int S = 1, sk = 0;
+        if (fastk && c->p.j_splits == 0 && c->p.fuse_integrator != 1) {
+            // stream-K: one persistent CTA per SM slot, equal runs of (tile, source stage) units; a tile's partial sums land
+            // in as many slots as CTAs share it (two at N = 1M) instead of one per source split (13 there)
+            const int per_sm = d.small_tile ? c->sk_ctas_per_sm_small : c->sk_ctas_per_sm;
+            const int stage_blks = d.small_tile ? SMALL_STAGE_BLKS : FAST_STAGE_BLKS;
+            const int stages = (s.nb + stage_blks - 1) / stage_blks;
+            sk = std::max(1, c->sm_count * std::max(1, per_sm));
+            S = force_f32_streamk_slots(tiles, stages, sk);
+        } else if (!refc) {
             if (c->p.j_splits > 0) S = std::min(c->p.j_splits, s.nb);
             else S = choose_splits(tiles, s.nb, slots, min_chunk, 64);
         }
-        d.plan.push_back({s.b0, s.nb, S, slot, s.remote});
+        Range r{s.b0, s.nb, S, slot, s.remote};
+        r.sk_ctas = sk;
+        d.plan.push_back(r);
         slot += S;
     }
     d.nslots = slot;
-    if (!c->f64 && !refc && !d.small_tile && c->world == 1 && d.plan.size() == 1 && d.plan[0].splits == 1) {
+    if (!c->f64 && !refc && !d.small_tile && c->world == 1 && d.plan.size() == 1 && d.plan[0].splits == 1 && d.plan[0].sk_ctas == 0) {
         d.fused = (c->p.fuse_integrator != 0);
     }
     if (c->p.fuse_integrator == 1 && !(d.plan.size() == 1 && d.plan[0].splits == 1 && !c->f64 && !refc && !d.small_tile)) {
@@ -207,7 +219,7 @@ int plan_device(nbody_ctx *c, Dev &d)
         d.fused = false;
     }
     d.force_ctas = 0;
-    for (const Range &r : d.plan) d.force_ctas += tiles * r.splits;
+    for (const Range &r : d.plan) d.force_ctas += r.sk_ctas > 0 ? r.sk_ctas : tiles * r.splits;
     return NBODY_OK;
 }
 
@@ -343,6 +355,7 @@ ForceLaunch make_force(const nbody_ctx *c, const Dev &d, const Range &r, float d
     L.j_nblk = r.j_nblk;
     L.j_body_limit = (long long)c->n;
     L.splits = r.splits;
+    L.streamk_ctas = r.sk_ctas;
     L.slot0 = r.slot0;
     L.eps2 = c->p.eps * c->p.eps;                       // Quadtree ctor: e_sq = eps*eps in fp32
     L.eps2_f64 = (double)c->p.eps * (double)c->p.eps;
@@ -447,7 +460,18 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             I.vel = d.vel;
             I.acc = d.acc;
             I.accp = d.accp;
-            I.nslots = d.nslots;
+            I.slots.n = 0;
+            for (const Range &r : d.plan) {
+                SlotRange &R = I.slots.r[I.slots.n++];
+                R.slot0 = r.slot0; R.nslots = r.splits; R.sk_S = 0; R.sk_G = 0; R.sk_U = 0; R.tile_blks = 1;
+                if (r.sk_ctas > 0) {
+                    const int stage_blks = d.small_tile ? SMALL_STAGE_BLKS : FAST_STAGE_BLKS;
+                    R.tile_blks = d.small_tile ? SMALL_TILE_BLKS : FAST_TILE_BLKS;
+                    R.sk_S = (r.j_nblk + stage_blks - 1) / stage_blks;
+                    R.sk_G = r.sk_ctas;
+                    R.sk_U = (long long)((int)(d.shard_count / BLK) / R.tile_blks) * R.sk_S;
+                }
+            }
             I.i_blk0 = (int)(d.shard_start / BLK);
             I.n_iblk_shard = (int)(d.shard_count / BLK);
             I.acc_only = acc_only ? 1 : 0;
@@ -458,7 +482,8 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             if (d.fused && acc_only) {
                 // fused plans own no partial slot buffer semantics beyond slot 0: the non-fused
                 // force launch above wrote slot 0.
-                I.nslots = 1;
+                I.slots.n = 1;
+                I.slots.r[0].nslots = 1;
             }
             CU(ctx->f64 ? launch_integrate_f64(I, d.stream) : launch_integrate_f32(I, d.stream));
             ctx->launches++;
@@ -828,6 +853,8 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
         cudaSetDevice(ctx->devs[0].device);
         ctx->ctas_per_sm = force_f32_fast_ctas_per_sm(ctx->uniform, false);
         ctx->ctas_per_sm_small = force_f32_fast_ctas_per_sm(ctx->uniform, true);
+        ctx->sk_ctas_per_sm = force_f32_streamk_ctas_per_sm(ctx->uniform, false);
+        ctx->sk_ctas_per_sm_small = force_f32_streamk_ctas_per_sm(ctx->uniform, true);
     }
     if (!multiproc && nlocal > 1 && p->exchange != 1) {
         // peer-to-peer exchange needs every local GPU to reach every other one (NVLink / NVSwitch)
@@ -1119,6 +1146,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->sm_count = ctx->sm_count;
     info->sm_clock_khz = ctx->sm_clock_khz;
     info->j_splits = d0.plan.empty() ? 0 : d0.plan[0].splits;
+    info->streamk_ctas = d0.plan.empty() ? 0u : (uint32_t)d0.plan[0].sk_ctas;
     info->force_ctas = d0.force_ctas;
     info->ctas_per_sm = ctx->ctas_per_sm;
     info->fused = d0.fused ? 1 : 0;
