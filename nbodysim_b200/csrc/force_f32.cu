@@ -150,7 +150,12 @@ static cudaError_t launch_streamk_d(const ForceLaunch &L, cudaStream_t st)
     a.j_blk0 = L.j_blk0; a.j_nblk = L.j_nblk; a.splits = 1; a.slot0 = L.slot0;
     a.n_tiles = L.n_iblk / C::TILE_BLKS;
     a.eps2 = L.eps2; a.acc_scale = L.acc_scale; a.n_real = L.j_body_limit;
-    kern<<<L.streamk_ctas, C::THREADS, RingT::SMEM, st>>>(a);
+    constexpr size_t smem = SK_SMEM(RingT::SMEM, C::I, C::THREADS);
+    if (smem > 48 * 1024) {                       // the ring plus the second-level accumulators: opt in once per kernel
+        static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr != cudaSuccess) return attr;
+    }
+    kern<<<L.streamk_ctas, C::THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <int FORM, bool GUARD>
@@ -175,12 +180,12 @@ int force_f32_streamk_ctas_per_sm(bool uniform_mass, bool small_tile)
     cudaError_t e;
     if (small_tile) {
         using RingT = Ring<BLK_ELEMS, SMALL_STAGE_BLKS>;
-        e = uniform_mass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_UNIFORM, false, 3>, SMALL_THREADS, RingT::SMEM)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_PLAIN, false, 3>, SMALL_THREADS, RingT::SMEM);
+        e = uniform_mass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_UNIFORM, false, 3>, SMALL_THREADS, SK_SMEM(RingT::SMEM, SMALL_I, SMALL_THREADS))
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<SMALL_I, SMALL_THREADS, SMALL_MINB, SMALL_UNROLL, SMALL_STAGE_BLKS, FORM_PLAIN, false, 3>, SMALL_THREADS, SK_SMEM(RingT::SMEM, SMALL_I, SMALL_THREADS));
     } else {
         using RingT = Ring<BLK_ELEMS, FAST_STAGE_BLKS>;
-        e = uniform_mass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_UNIFORM, false, 3>, FAST_THREADS, RingT::SMEM)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_PLAIN, false, 3>, FAST_THREADS, RingT::SMEM);
+        e = uniform_mass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_UNIFORM, false, 3>, FAST_THREADS, SK_SMEM(RingT::SMEM, FAST_I, FAST_THREADS))
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, force_f32_streamk_kernel<FAST_I, FAST_THREADS, FAST_MINB, FAST_UNROLL, FAST_STAGE_BLKS, FORM_PLAIN, false, 3>, FAST_THREADS, SK_SMEM(RingT::SMEM, FAST_I, FAST_THREADS));
     }
     return e == cudaSuccess ? n : 0;
 }

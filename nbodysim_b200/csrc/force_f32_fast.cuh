@@ -295,6 +295,12 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_fast_kernel(const Fas
 // is shared by at most (stages per tile) / (units per CTA) + 2 CTAs -- two at N = 1M -- each writing its own slot, in
 // unit order; the integrator derives the number of slots of a tile from the same arithmetic and sums them in that
 // order (deterministic).  Balance: every CTA gets the same number of units to within one stage (512 sources).
+constexpr int SK_FLUSH = 8;                        // stages (4,096 sources with 2-block stages) between folds of the register sums
+__host__ __device__ constexpr size_t SK_SACC_OFFSET(size_t ring_bytes) { return (ring_bytes + 15) & ~(size_t)15; }
+__host__ __device__ constexpr size_t SK_SMEM(size_t ring_bytes, int targets_per_thread, int threads)
+{
+    return SK_SACC_OFFSET(ring_bytes) + (size_t)3 * targets_per_thread * threads * sizeof(float);
+}
 __host__ __device__ __forceinline__ long long sk_start(long long k, long long U, int G) { return (k * U) / G; }
 __host__ __device__ __forceinline__ int sk_owner(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
 
@@ -328,64 +334,83 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_streamk_kernel(const 
         for (int t = 0; t < pre; ++t) issue(t);
     }
 
-    float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
-    size_t tgt_off[I];
+    // second-level accumulators (blocked summation): every SK_FLUSH stages the register sums are folded into per-thread
+    // shared-memory cells and restarted, so no fp32 accumulator ever adds more than SK_FLUSH x 256 terms per packed lane
+    // before it is added to a sum of its own size class -- the error of a long sequential fp32 sum grows with its length
+    // (at N = 1M one accumulator per target and lane would see 524,288 terms; the split form had 13 x 2 accumulators)
+    float *sacc = reinterpret_cast<float *>(smem_raw + SK_SACC_OFFSET(RingT::SMEM));     // [3][I][THREADS]
     const float2 e2 = make_float2(a.eps2, a.eps2);
-    int tile = (int)(g0 / S), jst = jst0;
-    for (int t = 0; t < nst; ++t) {
-        if (t == 0 || jst == 0) {                                        // first unit of a tile (or of this CTA's share of it)
+    int tile = (int)(g0 / S), jst = jst0, t = 0;
+    while (t < nst) {
+        // ---- one segment: this CTA's share of `tile`, source stages [jst, jst + seg_n)
+        const int seg_n = min(nst - t, S - jst);
+        float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
 #pragma unroll
-            for (int k = 0; k < I; ++k) {
-                const int blk = tile * TILE_BLKS + k / LANES_PER_BLK;
-                const int lane = (k % LANES_PER_BLK) * THREADS + tid;
-                tgt_off[k] = (size_t)blk * BLK_ELEMS + lane;
-                const float *b = a.posm + (size_t)a.i_blk0 * BLK_ELEMS + tgt_off[k];
-                const float x = b[0], y = b[BLK], z = b[2 * BLK];
-                nxi[k] = make_float2(-x, -x);
-                nyi[k] = make_float2(-y, -y);
-                nzi[k] = make_float2(-z, -z);
-                ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
-            }
+        for (int k = 0; k < I; ++k) {
+            const int blk = tile * TILE_BLKS + k / LANES_PER_BLK;
+            const int lane = (k % LANES_PER_BLK) * THREADS + tid;
+            const float *b = a.posm + (size_t)a.i_blk0 * BLK_ELEMS + (size_t)blk * BLK_ELEMS + lane;
+            const float x = b[0], y = b[BLK], z = b[2 * BLK];
+            nxi[k] = make_float2(-x, -x);
+            nyi[k] = make_float2(-y, -y);
+            nzi[k] = make_float2(-z, -z);
+            ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+            sacc[(0 * I + k) * THREADS + tid] = 0.f; sacc[(1 * I + k) * THREADS + tid] = 0.f; sacc[(2 * I + k) * THREADS + tid] = 0.f;
         }
-        const int s = t % NSTAGE;
-        mbar_wait(&ring.full[s], (uint32_t)(t / NSTAGE) & 1u);
-        const float *st = ring.stage + (size_t)s * RingT::STAGE_FLOATS;
-        const int nb = min(STAGE_BLKS, a.j_nblk - jst * STAGE_BLKS);
-        for (int b = 0; b < nb; ++b) {
-            const float *sx = st + b * SRC_ELEMS;
+        for (int u = 0; u < seg_n; ++u, ++t) {
+            const int s = t % NSTAGE;
+            mbar_wait(&ring.full[s], (uint32_t)(t / NSTAGE) & 1u);
+            const float *st = ring.stage + (size_t)s * RingT::STAGE_FLOATS;
+            const int nb = min(STAGE_BLKS, a.j_nblk - (jst + u) * STAGE_BLKS);
+            for (int b = 0; b < nb; ++b) {
+                const float *sx = st + b * SRC_ELEMS;
 #pragma unroll UNROLL
-            for (int j = 0; j < BLK; j += 4) {
-                const float4 X = *reinterpret_cast<const float4 *>(sx + j);
-                const float4 Y = *reinterpret_cast<const float4 *>(sx + BLK + j);
-                const float4 Z = (DIMS == 3) ? *reinterpret_cast<const float4 *>(sx + 2 * BLK + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (FORM == FORM_UNIFORM) {
-                    interact_pair_uniform<I, GUARD, DIMS>(lo2(X), lo2(Y), lo2(Z), nxi, nyi, nzi, ax, ay, az, e2);
-                    interact_pair_uniform<I, GUARD, DIMS>(hi2(X), hi2(Y), hi2(Z), nxi, nyi, nzi, ax, ay, az, e2);
-                    continue;
+                for (int j = 0; j < BLK; j += 4) {
+                    const float4 X = *reinterpret_cast<const float4 *>(sx + j);
+                    const float4 Y = *reinterpret_cast<const float4 *>(sx + BLK + j);
+                    const float4 Z = (DIMS == 3) ? *reinterpret_cast<const float4 *>(sx + 2 * BLK + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (FORM == FORM_UNIFORM) {
+                        interact_pair_uniform<I, GUARD, DIMS>(lo2(X), lo2(Y), lo2(Z), nxi, nyi, nzi, ax, ay, az, e2);
+                        interact_pair_uniform<I, GUARD, DIMS>(hi2(X), hi2(Y), hi2(Z), nxi, nyi, nzi, ax, ay, az, e2);
+                        continue;
+                    }
+                    const float4 M = *reinterpret_cast<const float4 *>(sx + 3 * BLK + j);
+                    interact_pair_plain<I, GUARD, DIMS>(lo2(X), lo2(Y), lo2(Z), lo2(M), nxi, nyi, nzi, ax, ay, az, e2);
+                    interact_pair_plain<I, GUARD, DIMS>(hi2(X), hi2(Y), hi2(Z), hi2(M), nxi, nyi, nzi, ax, ay, az, e2);
                 }
-                const float4 M = *reinterpret_cast<const float4 *>(sx + 3 * BLK + j);
-                interact_pair_plain<I, GUARD, DIMS>(lo2(X), lo2(Y), lo2(Z), lo2(M), nxi, nyi, nzi, ax, ay, az, e2);
-                interact_pair_plain<I, GUARD, DIMS>(hi2(X), hi2(Y), hi2(Z), hi2(M), nxi, nyi, nzi, ax, ay, az, e2);
             }
-        }
-        // this stage's buffer is free; thread 0 refills the buffer of the PREVIOUS stage (see Ring::release_and_refill)
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&ring.empty[s]);
-        if (tid == 0 && t >= 1 && (t - 1 + NSTAGE) < nst) {
-            const int tp = t - 1;
-            mbar_wait(&ring.empty[tp % NSTAGE], (uint32_t)(tp / NSTAGE) & 1u);
-            issue(tp + NSTAGE);
-        }
-        if (jst == S - 1 || t == nst - 1) {                              // the tile (or this CTA's share of it) is done
-            const int slot = a.slot0 + (int)blockIdx.x - sk_owner((long long)tile * S, U, G);
+            // this stage's buffer is free; thread 0 refills the buffer of the PREVIOUS stage (see Ring::release_and_refill)
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&ring.empty[s]);
+            if (tid == 0 && t >= 1 && (t - 1 + NSTAGE) < nst) {
+                const int tp = t - 1;
+                mbar_wait(&ring.empty[tp % NSTAGE], (uint32_t)(tp / NSTAGE) & 1u);
+                issue(tp + NSTAGE);
+            }
+            if (((u + 1) % SK_FLUSH) == 0 && u + 1 < seg_n) {
 #pragma unroll
-            for (int k = 0; k < I; ++k) {
-                const float fx = ax[k].x + ax[k].y, fy = ay[k].x + ay[k].y, fz = az[k].x + az[k].y;
-                float *o = a.accp + (size_t)slot * a.n_iblk_shard * BLK_ELEMS + (size_t)a.i_blk_local0 * BLK_ELEMS + tgt_off[k];
-                o[0] = fx; o[BLK] = fy; o[2 * BLK] = fz;
+                for (int k = 0; k < I; ++k) {
+                    sacc[(0 * I + k) * THREADS + tid] += ax[k].x + ax[k].y;
+                    sacc[(1 * I + k) * THREADS + tid] += ay[k].x + ay[k].y;
+                    sacc[(2 * I + k) * THREADS + tid] += az[k].x + az[k].y;
+                    ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+                }
             }
         }
-        if (++jst == S) { jst = 0; ++tile; }
+        // ---- the segment's partial sums -> the slot of this CTA among those that share the tile
+        const int slot = a.slot0 + (int)blockIdx.x - sk_owner((long long)tile * S, U, G);
+#pragma unroll
+        for (int k = 0; k < I; ++k) {
+            const float fx = sacc[(0 * I + k) * THREADS + tid] + (ax[k].x + ax[k].y);
+            const float fy = sacc[(1 * I + k) * THREADS + tid] + (ay[k].x + ay[k].y);
+            const float fz = sacc[(2 * I + k) * THREADS + tid] + (az[k].x + az[k].y);
+            const int blk = tile * TILE_BLKS + k / LANES_PER_BLK;
+            const int lane = (k % LANES_PER_BLK) * THREADS + tid;
+            float *o = a.accp + (size_t)slot * a.n_iblk_shard * BLK_ELEMS + (size_t)(a.i_blk_local0 + blk) * BLK_ELEMS + lane;
+            o[0] = fx; o[BLK] = fy; o[2 * BLK] = fz;
+        }
+        jst += seg_n;
+        if (jst == S) { jst = 0; ++tile; }
     }
 }
 

@@ -79,6 +79,7 @@ struct nbody_ctx {
     unsigned long long peer_timeout_ns = 120ull * 1000000000ull;
     unsigned long long step_index = 0;
     bool bh = false;             // force_algo == NBODY_FORCE_BARNES_HUT
+    bool streamk = true;         // fast fp32 kernel in stream-K form unless j_splits > 0 (tuning: NBODY_FORCE_FORM=split)
     bool uniform = false;        // every massive body has the same mass: 11-op force kernel
     float uniform_mass = 0.f;
     size_t esz = 4;
@@ -193,13 +194,15 @@ int plan_device(nbody_ctx *c, Dev &d)
     const bool fastk = !c->f64 && !refc;
     for (const Seg &s : segs) {
         int S = 1, sk = 0;
-        if (fastk && c->p.j_splits == 0 && c->p.fuse_integrator != 1) {
+        if (fastk && c->p.j_splits == 0 && c->p.fuse_integrator != 1 && c->streamk) {
             // stream-K: one persistent CTA per SM slot, equal runs of (tile, source stage) units; a tile's partial sums land
             // in as many slots as CTAs share it (two at N = 1M) instead of one per source split (13 there)
             const int per_sm = d.small_tile ? c->sk_ctas_per_sm_small : c->sk_ctas_per_sm;
             const int stage_blks = d.small_tile ? SMALL_STAGE_BLKS : FAST_STAGE_BLKS;
             const int stages = (s.nb + stage_blks - 1) / stage_blks;
-            sk = std::max(1, c->sm_count * std::max(1, per_sm));
+            // never more CTAs than units: every CTA then owns a non-empty run, so the CTAs that share a tile are consecutive
+            // and every slot the integrator reads has been written
+            sk = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * std::max(1, per_sm), (long long)tiles * stages));
             S = force_f32_streamk_slots(tiles, stages, sk);
         } else if (!refc) {
             if (c->p.j_splits > 0) S = std::min(c->p.j_splits, s.nb);
@@ -791,6 +794,7 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     ctx->f64 = (p->precision == NBODY_PRECISION_F64);
     ctx->bh = (p->force_algo == NBODY_FORCE_BARNES_HUT);
     ctx->esz = ctx->f64 ? 8 : 4;
+    if (const char *ff = getenv("NBODY_FORCE_FORM")) ctx->streamk = strcmp(ff, "split") != 0;
     {
         // Geometry and padding.  The fast kernel's 2048-target tiles need n padded to 2048 per rank; a small
         // shard, for which those tiles could not give every SM two CTAs, runs 512-target tiles and pads to 512

@@ -13,4 +13,4 @@ for n in [int(a) for a in sys.argv[1:]] or [1024, 4096, 16384, 25000, 32768, 655
         inf = s.info()
         print(json.dumps({"n": n, "us_per_step": round(1e6 * dt, 2), "G_inter_per_s": round(n * n / dt / 1e9, 1),
                           "pct_fp32_peak_20flop": round(100 * n * n / dt * 20 / 74.45e12, 1), "splits": inf["j_splits"],
-                          "ctas": inf["force_ctas"], "graph": inf["graph"], "fused": inf["fused"]}), flush=True)
+                          "ctas": inf["force_ctas"], "streamk": inf["streamk_ctas"], "graph": inf["graph"], "fused": inf["fused"]}), flush=True)
