@@ -642,43 +642,57 @@ __device__ __forceinline__ float bh_quake(float number)
 // ---- 7. walk (Quadtree::acc, :113-155) ------------------------------------------------------------------
 // one node's contribution to one target; the reference's per-node arithmetic (Quadtree.hpp:119-127) with the z
 // terms appended for the octree.  Returns true when the walk should skip the node's subtree (far node or leaf).
+// The opening test: displacement to the node's datum, its square, and whether the node is FAR (size^2 < d^2 theta^2,
+// Quadtree.hpp:122).  Same expressions as the reference in refcompat mode; fused multiply-adds otherwise.
 template <int DIMS, bool REFCOMPAT>
-__device__ __forceinline__ bool bh_visit(const float4 nd, float ndz, bool is_leaf, float px, float py, float pz, float t_sq,
-                                         float e_sq, int fix_near_leaves, float &ax, float &ay, float &az)
+__device__ __forceinline__ bool bh_open_test(const float4 nd, float ndz, float px, float py, float pz, float t_sq,
+                                             float &dx, float &dy, float &dz, float &d_sq)
+{
+    if (!REFCOMPAT) {
+        dx = nd.x - px; dy = nd.y - py; dz = (DIMS == 3) ? ndz - pz : 0.f;
+        d_sq = fmaf(dx, dx, dy * dy);
+        if (DIMS == 3) d_sq = fmaf(dz, dz, d_sq);
+        return nd.w < d_sq * t_sq;
+    }
+    dx = __fsub_rn(nd.x, px); dy = __fsub_rn(nd.y, py); dz = (DIMS == 3) ? __fsub_rn(ndz, pz) : 0.f;
+    d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (DIMS == 3) d_sq = __fadd_rn(d_sq, __fmul_rn(dz, dz));
+    return nd.w < __fmul_rn(d_sq, t_sq);
+}
+
+// The contribution of an accepted node (far, or a near leaf when those are included): Quadtree.hpp:123-127.
+template <int DIMS, bool REFCOMPAT>
+__device__ __forceinline__ void bh_accumulate(float mass, float dx, float dy, float dz, float d_sq, bool contributes, float e_sq,
+                                              float &ax, float &ay, float &az)
 {
     if (!REFCOMPAT) {
         // accurate-rsqrt mode has no bit-for-bit counterpart in the reference: fused multiply-adds, and a select
-        // instead of a branch around the interaction (the walk is instruction-issue-bound, profiles/)
-        const float fx = nd.x - px, fy = nd.y - py, fz = (DIMS == 3) ? ndz - pz : 0.f;
-        float r_sq = fmaf(fx, fx, fy * fy);
-        if (DIMS == 3) r_sq = fmaf(fz, fz, r_sq);
-        const bool far_ = nd.w < r_sq * t_sq;
-        if (!(far_ || is_leaf)) return false;
-        const float inv = rsqrt_approx(r_sq + e_sq);
-        const float s3 = ((far_ || fix_near_leaves) && r_sq > 0.f) ? nd.z * inv * inv * inv : 0.f;
-        ax = fmaf(fx, s3, ax);
-        ay = fmaf(fy, s3, ay);
-        if (DIMS == 3) az = fmaf(fz, s3, az);
-        return true;
+        // instead of a branch around the interaction (the large-N walk is instruction-issue-bound, profiles/)
+        const float inv = rsqrt_approx(d_sq + e_sq);
+        const float s3 = (contributes && d_sq > 0.f) ? mass * inv * inv * inv : 0.f;
+        ax = fmaf(dx, s3, ax);
+        ay = fmaf(dy, s3, ay);
+        if (DIMS == 3) az = fmaf(dz, s3, az);
+        return;
     }
-    const float dx = __fsub_rn(nd.x, px), dy = __fsub_rn(nd.y, py), dz = (DIMS == 3) ? __fsub_rn(ndz, pz) : 0.f;
-    float d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    if (DIMS == 3) d_sq = __fadd_rn(d_sq, __fmul_rn(dz, dz));
-    const bool far = nd.w < __fmul_rn(d_sq, t_sq);
-    if (!(far || is_leaf)) return false;
-    if ((far || fix_near_leaves) && d_sq > 0.f) {
-        float s3;
-        if (REFCOMPAT) {
-            const float inv = bh_quake(__fadd_rn(d_sq, e_sq));
-            s3 = __fmul_rn(nd.z, __fmul_rn(__fmul_rn(inv, inv), inv));
-        } else {
-            const float inv = rsqrt_approx(d_sq + e_sq);
-            s3 = nd.z * inv * inv * inv;
-        }
+    if (contributes && d_sq > 0.f) {
+        const float inv = bh_quake(__fadd_rn(d_sq, e_sq));
+        const float s3 = __fmul_rn(mass, __fmul_rn(__fmul_rn(inv, inv), inv));
         ax = __fadd_rn(ax, __fmul_rn(dx, s3));
         ay = __fadd_rn(ay, __fmul_rn(dy, s3));
         if (DIMS == 3) az = __fadd_rn(az, __fmul_rn(dz, s3));
     }
+}
+
+// one node's contribution to one target; returns true when the walk should skip the node's subtree (far node or leaf)
+template <int DIMS, bool REFCOMPAT>
+__device__ __forceinline__ bool bh_visit(const float4 nd, float ndz, bool is_leaf, float px, float py, float pz, float t_sq,
+                                         float e_sq, int fix_near_leaves, float &ax, float &ay, float &az)
+{
+    float dx, dy, dz, d_sq;
+    const bool far = bh_open_test<DIMS, REFCOMPAT>(nd, ndz, px, py, pz, t_sq, dx, dy, dz, d_sq);
+    if (!(far || is_leaf)) return false;
+    bh_accumulate<DIMS, REFCOMPAT>(nd.z, dx, dy, dz, d_sq, far || fix_near_leaves, e_sq, ax, ay, az);
     return true;
 }
 
@@ -733,15 +747,31 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
     const size_t g = blk_index(body, 0);
     const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
     float ax = 0.f, ay = 0.f, az = 0.f;
+    // With one or two warps per scheduler (the reference's 25,000 targets) nothing hides a load: a warp's time is its
+    // longest walk x (load round trip + the arithmetic of a visit).  The loop is software-pipelined: the record of the
+    // NEXT node is requested as soon as the opening test has chosen it, and the force arithmetic of the current node
+    // (the Quake rsqrt chain) runs while that load is in flight.  Same visits, same operations, same order of additions
+    // as Quadtree::acc.  (Measured and dropped, profiles/r2_walk_experiments.txt: prefetching the following records
+    // into L1, and requesting BOTH possible successors before the test -- neither shortens the chain.)
     unsigned i = 0, nvis = 0;
-    do {
-        float4 nd;
-        uint4 na;
-        bh_load_node(nodes, i, nd, na);
+    float4 nd;
+    uint4 na;
+    bh_load_node(nodes, 0u, nd, na);
+    for (;;) {
         ++nvis;
-        if (bh_visit<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), (na.z & 256u) != 0u, px, py, pz, t_sq, e_sq, fix_near_leaves, ax, ay, az)) i = na.y;
-        else i = i + 1;
-    } while (i != 0 && i < cap);   // i >= cap only if the tree overflowed its reservation (raises the status word)
+        float dx, dy, dz, d_sq;
+        const bool far = bh_open_test<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), px, py, pz, t_sq, dx, dy, dz, d_sq);
+        const bool skip = far || (na.z & 256u) != 0u;                    // far node or leaf: its subtree is not entered
+        const unsigned nxt = skip ? na.y : i + 1u;
+        const bool more = nxt != 0u && nxt < cap;                        // nxt >= cap only if the tree overflowed (status word)
+        const float mass = nd.z;
+        float4 nd2 = nd;
+        uint4 na2 = na;
+        if (more) bh_load_node(nodes, nxt, nd2, na2);
+        if (skip) bh_accumulate<DIMS, REFCOMPAT>(mass, dx, dy, dz, d_sq, far || fix_near_leaves, e_sq, ax, ay, az);
+        if (!more) break;
+        nd = nd2; na = na2; i = nxt;
+    }
     if (visits) atomicAdd(visits, (unsigned long long)nvis);
     bh_walk_finish<DIMS, FUSE>(posm, g, body, shard_start, px, py, pz, ax, ay, az, accp, fz);
 }

@@ -158,7 +158,7 @@ cudaError_t CollideWorkspace::alloc(size_t n, int single_cta_mode, size_t single
     // screening: flags (64 B) | table keys | list heads -- one region, one memset per pass; then the list links
     grid_bytes = 64 + (size_t)tsize * 12;
     COL_ALLOC(grid, grid_bytes)
-    COL_ALLOC(grid_links, (size_t)entry_cap * 8)
+    COL_ALLOC(grid_links, (size_t)entry_cap * 20)
     if (single_cta) { COL_ALLOC(ranks, (size_t)std::max(entry_cap, pair_cap) * 4) }
     temp_bytes = radix_sort_temp_bytes(std::max<size_t>(entry_cap, pair_cap));
     COL_ALLOC(temp, temp_bytes)
@@ -208,7 +208,7 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     g.flags = (unsigned *)grid;
     g.tkeys = (unsigned long long *)((char *)grid + 64);
     g.heads = (unsigned *)((char *)grid + 64 + (size_t)table_slots * 8);
-    g.enext = (unsigned *)grid_links; g.ebody = (unsigned *)grid_links + entry_cap;
+    g.edata = (float4 *)grid_links; g.enext = (unsigned *)((char *)grid_links + (size_t)entry_cap * 16);
     g.tmask = table_slots - 1; g.ecap = entry_cap;
     if ((e = cudaMemsetAsync(grid, 0, grid_bytes, st)) != cudaSuccess) return e;
     const unsigned gb = (unsigned)((n + 255) / 256);

@@ -66,7 +66,8 @@ __device__ __forceinline__ void col_overflow(const ColArgs &a)
 struct ColGrid {
     unsigned long long *tkeys;             // [tmask + 1]  0 = empty, else 1 << 32 | cell hash
     unsigned *heads;                       // [tmask + 1]  entry index + 1 of the cell's list head, 0 = none
-    unsigned *enext, *ebody;               // [ecap]       list links (entry index + 1) and bodies
+    unsigned *enext;                       // [ecap]       list links (entry index + 1)
+    float4 *edata;                         // [ecap]       (x, y, radius, body index bits) of the entry's body: one load per list element
     unsigned *flags;                       // [0] overlapping pairs seen, [1] entries used       (zeroed with the table)
     unsigned tmask, ecap;
 };
@@ -99,7 +100,7 @@ __device__ __forceinline__ void col_grid_insert(const ColArgs &a, const ColGrid 
                 }
                 const unsigned e = atomicAdd(&g.flags[1], 1u);
                 if (e >= g.ecap || probes > g.tmask) { col_overflow(a); atomicAdd(&g.flags[0], 1u); continue; }
-                g.ebody[e] = i;
+                g.edata[e] = make_float4(b.x, b.y, b.r, __uint_as_float(i));
                 g.enext[e] = atomicExch(&g.heads[slot], e + 1u);
             }
     }
@@ -123,9 +124,10 @@ __device__ __forceinline__ void col_grid_detect(const ColArgs &a, const ColGrid 
                 }
                 if (g.tkeys[slot] != key) continue;
                 for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
-                    const unsigned j = g.ebody[e - 1u];
+                    const float4 E = g.edata[e - 1u];
+                    const unsigned j = __float_as_uint(E.w);
                     if (j <= i) continue;                                // every pair once (per shared cell)
-                    const ColBody B = col_load(a.posm, a.vel, j);
+                    ColBody B; B.x = E.x; B.y = E.y; B.r = E.z;
                     const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
                     if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r))) ++overlaps;
                 }
@@ -220,9 +222,10 @@ __device__ __forceinline__ void col_grid_pairs(const ColArgs &a, const ColGrid &
                 }
                 if (g.tkeys[slot] != key) continue;
                 for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
-                    const unsigned j = g.ebody[e - 1u];
+                    const float4 E = g.edata[e - 1u];
+                    const unsigned j = __float_as_uint(E.w);
                     if (j == i) continue;
-                    const ColBody B = col_load(a.posm, a.vel, j);
+                    ColBody B; B.x = E.x; B.y = E.y; B.r = E.z;
                     unsigned first, second;
                     if (!col_sweep_pair(A, i, B, j, first, second) || first != i) continue;
                     const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
