@@ -738,8 +738,10 @@ template <int DIMS, bool REFCOMPAT, bool FUSE>
 __global__ void __launch_bounds__(WALK_THREADS)
 bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                       float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-                      float *__restrict__ accp, unsigned cap, unsigned long long *visits, const BhFuse fz)
+                      float *__restrict__ accp, unsigned cap, unsigned long long *visits, const BhFuse fz,
+                      const unsigned *__restrict__ n_dev)
 {
+    if (n_dev) n = min(n, (size_t)*n_dev);                  // sharded: `idx` is the compacted list of this GPU's targets
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const unsigned body = idx[s];                           // targets in Z-order: neighbouring threads walk alike
@@ -788,8 +790,10 @@ template <int DIMS, bool REFCOMPAT>
 __global__ void __launch_bounds__(128)
 bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__ idx, size_t n, BhNodes nodes,
                     float t_sq, float e_sq, int fix_near_leaves, size_t shard_start, size_t shard_count,
-                    float *__restrict__ accp, unsigned cap, unsigned window, unsigned long long *visits)
+                    float *__restrict__ accp, unsigned cap, unsigned window, unsigned long long *visits,
+                    const unsigned *__restrict__ n_dev)
 {
+    if (n_dev) n = min(n, (size_t)*n_dev);                  // sharded: `idx` is the compacted list of this GPU's targets
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = s < n;
     const unsigned body = valid ? idx[s] : 0u;
@@ -826,6 +830,26 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
     if (visits && nvis) atomicAdd(visits, (unsigned long long)nvis);
 }
 
+// Several GPUs: every GPU builds the whole tree but walks only the targets of its shard (a range of BODY indices,
+// scattered all over the Z-order).  Compact them -- order kept inside a block of 256 sorted bodies, blocks in arrival
+// order -- so that the walk's warps are full of this GPU's targets, still neighbours in Z-order, instead of holding
+// one target in world_size lanes (the warp-cooperative walk then pays a whole union walk for 32 / world targets).
+__global__ void __launch_bounds__(256)
+bh_shard_targets_kernel(const unsigned *__restrict__ idx, size_t n, size_t shard_start, size_t shard_count,
+                        unsigned *__restrict__ out, unsigned *__restrict__ counter)
+{
+    __shared__ unsigned warp_sums[RS_WARPS];
+    __shared__ unsigned s_base;
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned body = s < n ? idx[s] : 0u;
+    const unsigned mine = (s < n && body >= shard_start && body < shard_start + shard_count) ? 1u : 0u;
+    unsigned total = 0;
+    const unsigned before = rs_block_excl_scan(mine, warp_sums, &total);
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(counter, total) : 0u;
+    __syncthreads();
+    if (mine) out[s_base + before] = body;
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 // Cells: a body owns the cells of its path that first appear with it -- about 2.8 n for well-separated bodies (the
 // reference's shipped scene: 69,681 cells for 25,000 bodies), up to 32 n when many bodies are much closer to a
@@ -855,6 +879,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int clus
     BH_ALLOC(node_slots, (size_t)node_cap * (dims == 3 ? 8 : 4) * 16)
     BH_ALLOC(node_slot_cells, (size_t)node_cap * (dims == 3 ? 8 : 4) * 4)
     BH_ALLOC(node_owner, (size_t)node_cap * 4)
+    BH_ALLOC(shard_targets, (n + 1) * 4)
     // everything that must be zero at the start of a build lives in ONE region cleared by one memset per step:
     // bounding box | radix-sort scratch (histograms, tickets, status words) | scan scratch | arrival counters
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -871,7 +896,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int clus
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_slot_cells, node_owner, zero_region, trace};
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_slot_cells, node_owner, shard_targets, zero_region, trace};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -1011,16 +1036,25 @@ template <int DIMS, bool FUSE>
 static void bh_walk_t(const BhWorkspace &w, const float *posm, size_t n, float t_sq, float e_sq, bool refcompat, int fix,
                       size_t shard_start, size_t shard_count, float *accp, unsigned long long *visits, const BhFuse &fz, cudaStream_t st)
 {
-    const unsigned g = (unsigned)((n + 127) / 128);
     const unsigned *idx = (const unsigned *)w.idx;
+    const unsigned *n_dev = nullptr;
     const BhNodes nd = bh_nodes(w);
+    if (!(shard_start == 0 && shard_count >= n)) {           // this GPU owns a shard: walk the compacted list of its targets
+        unsigned *counter = (unsigned *)w.shard_targets + w.n_cap;
+        cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+        bh_shard_targets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, n, shard_start, shard_count, (unsigned *)w.shard_targets, counter);
+        idx = (const unsigned *)w.shard_targets;
+        n_dev = counter;
+        n = std::min(n, shard_count);
+    }
+    const unsigned g = (unsigned)((n + 127) / 128);
     if (w.warp_walk && !FUSE) {
-        if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
-        else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits);
+        if (refcompat) bh_walk_warp_kernel<DIMS, true><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits, n_dev);
+        else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits, n_dev);
         return;
     }
-    if (refcompat) bh_walk_direct_kernel<DIMS, true, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz);
-    else bh_walk_direct_kernel<DIMS, false, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz);
+    if (refcompat) bh_walk_direct_kernel<DIMS, true, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz, n_dev);
+    else bh_walk_direct_kernel<DIMS, false, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz, n_dev);
 }
 
 // `fuse` != nullptr: the walk threads also integrate their targets (kick-drift; one GPU, whole array = one shard)

@@ -147,6 +147,7 @@ struct BhWorkspace {
     void *node_data = nullptr, *node_quad = nullptr, *node_arrive = nullptr, *node_slots = nullptr;   // node_data: one 32-byte record per node
     void *trace = nullptr;       // tuning aid (NBODY_CLUSTER_TRACE): per-phase clock stamps of the cluster build
     void *node_slot_cells = nullptr; // centre-of-mass pass: subtree sizes riding up with the centres of mass (-> skip pointers)
+    void *shard_targets = nullptr; // several GPUs: this GPU's targets compacted out of the Z-order (+ their count)
     void *node_owner = nullptr;  // single-cluster build: the sorted body that owns each cell
     int cluster_ctas = 0;        // > 0: scenes of up to cluster_ctas x 49152 bodies are built by ONE cluster kernel of that many CTAs
     static int cluster_ctas_available(int dims);

@@ -101,3 +101,19 @@ def test_two_gpu_exchanges_agree_bitwise_over_many_steps():
             outs.append(s.bodies.copy())
     for f in ("pos", "pos_z", "vel", "vel_z", "acc", "acc_z"):
         assert np.array_equal(bits(outs[0][f]), bits(outs[1][f])), f
+
+
+@needs2
+@pytest.mark.parametrize("bh_walk", [1, 2])
+def test_two_gpu_octree_walks_equal_one_gpu(bh_walk):
+    """each GPU walks the compacted list of its own targets (per-thread and warp-cooperative walk): the accelerations
+    of the 3-D octree path equal the one-GPU run bit for bit, and so does the state after a few steps"""
+    b = ic.plummer(20000, seed=21, dims=3)
+    outs = []
+    for ng in (1, 2):
+        with Simulation(b, dt=1e-3, eps=0.01, dims=3, theta=0.5, force_algo=capi.FORCE_BARNES_HUT, bh_fix_near_leaves=1,
+                        rsqrt_mode=capi.RSQRT_REFCOMPAT, bh_walk=bh_walk, ngpus=ng, device_ids=[0, 1][:ng]) as s:
+            s.step(4)
+            outs.append(s.bodies.copy())
+    for f in ("pos", "pos_z", "vel", "vel_z", "acc", "acc_z"):
+        assert np.array_equal(bits(outs[0][f]), bits(outs[1][f])), f
