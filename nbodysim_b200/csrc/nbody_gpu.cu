@@ -64,6 +64,10 @@ struct Dev {
     float graph_dt = 0.f;
     int graph_cur = -1;
     unsigned long long graph_launches = 0, graph_interactions = 0;
+    // ... and of ONE step per buffer parity, for callers that step once per call (a viewer, the e2e loop)
+    cudaGraphExec_t graph1[2] = {nullptr, nullptr};
+    float graph1_dt[2] = {0.f, 0.f};
+    unsigned long long graph1_launches = 0, graph1_interactions = 0;
 };
 
 } // namespace
@@ -88,6 +92,7 @@ struct nbody_ctx {
     int sm_count = 0, sm_clock_khz = 0, ctas_per_sm = 0, ctas_per_sm_small = 0, sk_ctas_per_sm = 0, sk_ctas_per_sm_small = 0;
     unsigned long long launches = 0, interactions = 0;
     int profile_next = 0;
+    unsigned long long short_calls = 0;  // nbody_gpu_step calls of fewer than 8 steps so far
     float last_force_ms = 0.f, last_integ_ms = 0.f, last_build_ms = 0.f, last_collide_ms = 0.f;
     unsigned long long last_visits = 0;
     char err[512];
@@ -689,6 +694,7 @@ void free_all(nbody_ctx *c)
         d.bh.release();
         d.col.release();
         if (d.graph) cudaGraphExecDestroy(d.graph);
+        for (int k = 0; k < 2; ++k) if (d.graph1[k]) cudaGraphExecDestroy(d.graph1[k]);
         if (d.ev_integrated) cudaEventDestroy(d.ev_integrated);
         if (d.ev_gathered) cudaEventDestroy(d.ev_gathered);
         for (int k = 0; k < 2; ++k) if (d.ev_pushed[k]) cudaEventDestroy(d.ev_pushed[k]);
@@ -952,17 +958,61 @@ static int step_with_graph(nbody_ctx *ctx, float dt, int &remaining)
     return NBODY_OK;
 }
 
+// One step per call (nbody_gpu_step(ctx, dt, 1) from a viewer loop or an upload / step / download cycle): one graph per
+// buffer parity, so such a caller pays one graph launch instead of ~18 kernel launches per step.
+static int step_with_single_graph(nbody_ctx *ctx, float dt)
+{
+    Dev &d = ctx->devs[0];
+    CU(cudaSetDevice(d.device));
+    const int par = d.cur;
+    if (!d.graph1[par] || d.graph1_dt[par] != dt) {
+        if (d.graph1[par]) { cudaGraphExecDestroy(d.graph1[par]); d.graph1[par] = nullptr; }
+        const unsigned long long l0 = ctx->launches, i0 = ctx->interactions, s0 = ctx->step_index;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step(ctx, dt, false, false);
+        cudaError_t e = cudaStreamEndCapture(d.stream, &g);
+        d.graph1_launches = ctx->launches - l0;           // nothing ran yet: undo the bookkeeping of the capture
+        d.graph1_interactions = ctx->interactions - i0;
+        ctx->launches = l0;
+        ctx->interactions = i0;
+        ctx->step_index = s0;
+        d.cur = par;
+        if (rc != NBODY_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        CU(e);
+        e = cudaGraphInstantiate(&d.graph1[par], g, 0);
+        cudaGraphDestroy(g);
+        CU(e);
+        d.graph1_dt[par] = dt;
+    }
+    CU(cudaGraphLaunch(d.graph1[par], d.stream));
+    ctx->launches += d.graph1_launches;
+    ctx->interactions += d.graph1_interactions;
+    d.cur ^= 1;
+    ctx->step_index++;
+    return NBODY_OK;
+}
+
 int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
 {
     if (!ctx || nsteps < 0 || !(dt == dt)) return NBODY_EINVAL;
     // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
     // (the Barnes-Hut build and the collision pass are fully asynchronous -- sorts, scan, COM pass, pair
     //  discovery and resolve keep their counters on the device -- so they capture too)
-    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->profile_next && nsteps >= 8;
+    const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->profile_next;
     const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && (ctx->n_padded <= 32768 || (ctx->bh && ctx->n_padded <= 262144)));
-    if (graph_ok && want) {
+    if (graph_ok && want && nsteps >= 8) {
         int rc = step_with_graph(ctx, dt, nsteps);
         if (rc != NBODY_OK) return rc;
+    }
+    // short calls: once a context has been stepped a few times in calls of fewer than 8 steps (a per-frame caller), its
+    // steps replay from the one-step graphs as well
+    if (nsteps > 0 && nsteps < 8) ctx->short_calls++;
+    if (graph_ok && want && nsteps > 0 && nsteps < 8 && (ctx->short_calls > 3 || ctx->p.use_graph == 1)) {
+        for (; nsteps > 0; --nsteps) {
+            int rc = step_with_single_graph(ctx, dt);
+            if (rc != NBODY_OK) return rc;
+        }
     }
     for (int s = 0; s < nsteps; ++s) {
         const bool prof = ctx->profile_next && s == 0;
@@ -1155,7 +1205,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->ctas_per_sm = ctx->ctas_per_sm;
     info->fused = d0.fused ? 1 : 0;
     info->uniform_mass = ctx->uniform ? 1 : 0;
-    info->graph = (d0.graph != nullptr) ? 1 : 0;
+    info->graph = (d0.graph != nullptr || d0.graph1[0] != nullptr || d0.graph1[1] != nullptr) ? 1 : 0;
     info->kernel_launches = ctx->launches;
     info->interactions = ctx->interactions;
     info->last_force_ms = ctx->last_force_ms;

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 namespace nb {
 
@@ -116,12 +117,14 @@ __device__ __forceinline__ void rs_st_status(unsigned long long *p, unsigned lon
 }
 constexpr int RS_LOOKBACK_WINDOW = 4;                     // predecessors' status words fetched at once
 
-template <bool HAS_VALS, int RS_ROWS>
-static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
-os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, const unsigned *__restrict__ n_dev,
-               int shift, unsigned pass,
-               const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, unsigned long long *status,
-               unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
+// One tile of one digit pass (the body of both kernels below).  `tile` < 0: take the next tile by ticket.  IDENTITY_COPY:
+// a digit on which all keys agree makes the pass a plain copy (the launch-per-pass form keeps its ping-pong fixed);
+// the all-passes kernel tests that itself and skips such a pass altogether.
+template <bool HAS_VALS, int RS_ROWS, bool IDENTITY_COPY>
+__device__ __forceinline__ void
+os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, int shift, unsigned pass,
+             const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, int fixed_tile, unsigned long long *status,
+             unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
 {
     constexpr int RS_ITEMS = RS_ROWS, RS_CHUNK = 32 * RS_ROWS, RS_TILE = RS_THREADS * RS_ROWS;
     __shared__ unsigned long long skeys[RS_TILE];        // the tile in digit order; reused for the values afterwards
@@ -133,8 +136,8 @@ os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__re
     __shared__ unsigned s_tile;
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    if (n_dev) n = (*n_dev < n) ? *n_dev : n;             // live item count kept on the device (n is its bound)
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();                                      // a previous tile / pass of this CTA may still read the shared arrays
+    if (tid == 0) s_tile = fixed_tile >= 0 ? (unsigned)fixed_tile : atomicAdd(ticket, 1u);
 #pragma unroll
     for (int q = 0; q < RS_WARPS; ++q) counts[q][tid] = 0;
     __syncthreads();
@@ -144,7 +147,7 @@ os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__re
     const unsigned cnt = (unsigned)((n - tile0 < (size_t)RS_TILE) ? (n - tile0) : (size_t)RS_TILE);
 
     // ---- every key has the same digit (e.g. the unused high bytes of small keys): the pass is the identity
-    if (__syncthreads_or(hist_p[tid] == (unsigned)n)) {
+    if (IDENTITY_COPY && __syncthreads_or(hist_p[tid] == (unsigned)n)) {
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; ++j) {
             const unsigned i = (unsigned)j * RS_THREADS + tid;
@@ -272,10 +275,89 @@ os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__re
     }
 }
 
+template <bool HAS_VALS, int RS_ROWS>
+static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
+os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, const unsigned *__restrict__ n_dev,
+               int shift, unsigned pass,
+               const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, unsigned long long *status,
+               unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
+{
+    if (n_dev) n = (*n_dev < n) ? *n_dev : n;             // live item count kept on the device (n is its bound)
+    os_pass_tile<HAS_VALS, RS_ROWS, true>(keys, vals, n, shift, pass, hist_p, ticket, -1, status, keys_out, vals_out);
+}
+
+// ---- all digit passes in ONE kernel (small inputs: every tile co-resident) -------------------------------------------------
+// At the reference's size a digit pass is 13 tiles of work and ~9 us of launch, ramp and drain: launched cooperatively
+// with one CTA per tile, the passes follow one another inside the kernel, separated by a grid-wide barrier (the scattered
+// keys of pass p must be complete before pass p + 1 reads them).  Same tile code, same decoupled look-back (the status
+// words carry the pass in their tag).  A digit on which all keys agree is skipped without moving anything; the result
+// is brought back to the first buffer pair at the end if an odd number of passes moved data.
+__device__ __forceinline__ void rs_grid_barrier(unsigned *counter, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // this CTA's scattered keys are visible before it arrives
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned *>(counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool HAS_VALS, int RS_ROWS>
+static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
+os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b, size_t n,
+                   const unsigned *__restrict__ n_dev, int pass0, int npasses, const unsigned *__restrict__ hist,
+                   unsigned *__restrict__ barrier_word, unsigned long long *status)
+{
+    if (n_dev) n = (*n_dev < n) ? *n_dev : n;
+    unsigned long long *kin = keys_a, *kout = keys_b;
+    unsigned *vin = vals_a, *vout = vals_b;
+    unsigned syncs = 0;
+    bool flipped = false;
+    for (int p = 0; p < npasses; ++p) {
+        const unsigned *hist_p = hist + p * 256;
+        if (__syncthreads_or(hist_p[threadIdx.x] == (unsigned)n)) continue;        // uniform over the grid: identity pass
+        os_pass_tile<HAS_VALS, RS_ROWS, false>(kin, vin, n, 8 * (pass0 + p), (unsigned)p, hist_p, nullptr, (int)blockIdx.x, status, kout, vout);
+        rs_grid_barrier(barrier_word, ++syncs * gridDim.x);
+        unsigned long long *tk = kin; kin = kout; kout = tk;
+        unsigned *tv = vin; vin = vout; vout = tv;
+        flipped = !flipped;
+    }
+    if (flipped) {                                         // bring the result back to the first buffer pair
+        for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_THREADS) {
+            keys_a[i] = keys_b[i];
+            if (HAS_VALS) vals_a[i] = vals_b[i];
+        }
+    }
+}
+
 inline size_t radix_sort_temp_bytes(size_t n)
 {
     const size_t ntiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
     return (size_t)RS_MAX_PASSES * 256 * sizeof(unsigned) + 64 + ntiles * 256 * sizeof(unsigned long long);
+}
+
+// tiles the all-passes kernel may be launched with (one CTA per tile, all co-resident); 0 disables it
+// (NBODY_SORT_COOP=0, or a device without cooperative launch)
+static inline int rs_coop_tile_limit(bool has_vals)
+{
+    static int limit[2] = {-1, -1};
+    int &l = limit[has_vals ? 1 : 0];
+    if (l < 0) {
+        l = 0;
+        const char *env = getenv("NBODY_SORT_COOP");
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        if (!(env && atoi(env) == 0) && cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+            const cudaError_t e = has_vals ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, os_sort_all_kernel<true, RS_ROWS_SMALL>, RS_THREADS, 0)
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, os_sort_all_kernel<false, RS_ROWS_SMALL>, RS_THREADS, 0);
+            if (e == cudaSuccess) l = sms * per_sm;
+            else cudaGetLastError();
+        }
+    }
+    return l;
 }
 
 // Stable sort of n (key, value) pairs by key.  Result ends in keys_a / vals_a.  vals_a == nullptr sorts keys only.
@@ -302,6 +384,15 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
     size_t hgrid = (n + 8 * RS_THREADS - 1) / (8 * RS_THREADS);             // >= 8 keys per thread, at most 8 CTAs per SM
     if (hgrid > 148 * 8) hgrid = 148 * 8;
     if (!hist_ready) os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, n_dev, pass0, npasses, hist);
+    // small inputs: all passes in one cooperative kernel, one CTA per tile (every tile co-resident)
+    if (small && ntiles <= (size_t)rs_coop_tile_limit(vals_a != nullptr)) {
+        unsigned *barrier_word = ticket + 15;                               // zeroed with the rest of `temp`
+        void *args[] = {&keys_a, &keys_b, &vals_a, &vals_b, &n, &n_dev, (void *)&pass0, (void *)&npasses, &hist, &barrier_word, &status};
+        const void *fn = vals_a ? (const void *)os_sort_all_kernel<true, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<false, RS_ROWS_SMALL>;
+        if ((e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, st)) != cudaSuccess) return e;
+        if (launches) *launches += (hist_ready ? 0 : 1) + 1;
+        return cudaGetLastError();
+    }
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
     for (int p = 0; p < npasses; ++p) {

@@ -288,3 +288,25 @@ def test_build_paths_and_fused_walk_bitexact(sort_impl):
     for o in outs:
         for f in ("pos", "vel", "acc"):
             assert np.array_equal(bits(o[f]), bits(want[f])), f
+
+
+def test_per_frame_calls_replay_one_step_graphs_bit_identically():
+    """a caller that steps once per call (viewer loop, upload / step / download cycle) is switched to one-step CUDA graphs
+    (one per buffer parity) after a few calls: same state as one long call, bit for bit; a changed dt re-captures"""
+    b = ic.reference_disc(6000)
+    kw = dict(theta=1.0, eps=1.0, collide=1, integ_flags=capi.INTEG_CLAMP | capi.INTEG_BOUNDARY)
+    with bh_sim(b, dt=0.01, **kw) as s:
+        s.step(14)
+        s.dt = 0.005
+        s.step(9)
+        want = s.bodies.copy()
+    with bh_sim(b, dt=0.01, **kw) as s:
+        for _ in range(14):
+            s.step(1)
+        assert s.info()["graph"] == 1
+        s.dt = 0.005
+        for _ in range(3):
+            s.step(3)
+        got = s.bodies.copy()
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(got[f]), bits(want[f])), f
