@@ -290,9 +290,10 @@ int ipc_barrier(nbody_ctx *ctx);
 // PCIe; the packed shard then reaches the other ranks over NVLink -- copies into the peers' mapped buffers (CUDA
 // IPC exchange) or one in-place ncclAllGather -- bracketed by stream-ordered barriers so that no rank's buffer is
 // written while a peer still reads it, and every rank's copies have landed before anyone proceeds.
-int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies, bool shard_only)
+int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies, bool shard_only, bool check_masses)
 {
-    const float check_mass = (ctx->uniform && shard_only) ? ctx->uniform_mass : 0.f;
+    // the uniform-mass kernel stays valid only while the masses stay as first uploaded: the pack kernel compares
+    const float check_mass = (ctx->uniform && check_masses) ? ctx->uniform_mass : 0.f;
     if (shard_only && ctx->ipc) {
         int rc = ipc_barrier(ctx);
         if (rc != NBODY_OK) return rc;
@@ -305,7 +306,7 @@ int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies, bool shard_only)
         if (!shard_only) {
             CU(cudaMemcpyAsync(d.aos, bodies, ctx->n * sizeof(nbody_body_t), cudaMemcpyHostToDevice, d.stream));
             CU(launch_pack(d.aos, 0, 0, ctx->n_padded, ctx->n, d.shard_start, d.shard_count, d.posm[0], d.vel,
-                           d.acc, ctx->f64, ctx->p.dims, 0.f, nullptr, d.stream));
+                           d.acc, ctx->f64, ctx->p.dims, check_mass, d.d_status, d.stream));
             ctx->launches++;
             // padding must also be valid in the other buffer (masses are copied by the integrator only
             // for the shard's own blocks, so seed both buffers with the full packed state)
@@ -338,6 +339,9 @@ int upload_state(nbody_ctx *ctx, const nbody_body_t *bodies, bool shard_only)
         CU(cudaSetDevice(d.device));
         CU(cudaStreamSynchronize(d.stream)); // `bodies` may be pageable and reused by the caller
         if (d.h_status && ((volatile unsigned *)d.h_status)[2]) {
+            // the new state is on the device but must not be stepped with the uniform-mass kernel: report, and let a
+            // later upload of equal masses (or a new context) make the context usable again
+            ((volatile unsigned *)d.h_status)[2] = 0;
             set_err(ctx, "nbody_gpu_upload: masses changed; re-create the context (uniform-mass kernel in use)");
             return NBODY_ESTATE;
         }
@@ -919,7 +923,7 @@ int nbody_gpu_init(nbody_ctx **out, const nbody_params *p, const nbody_body_t *b
     if (multiproc && p->exchange != 1) {
         if ((rc = setup_ipc(ctx)) != NBODY_OK) return fail(rc);
     }
-    if ((rc = upload_state(ctx, bodies, false)) != NBODY_OK) return fail(rc);
+    if ((rc = upload_state(ctx, bodies, false, false)) != NBODY_OK) return fail(rc);
     *out = ctx;
     return NBODY_OK;
 }
@@ -1107,16 +1111,9 @@ int nbody_gpu_upload(nbody_ctx *ctx, const nbody_body_t *bodies, size_t n)
     int rc = sync_all(ctx);
     if (rc != NBODY_OK) return rc;
     // one process per GPU: only this rank's shard is read and crosses PCIe; the exchange carries it to the peers.
-    // (the uniform-mass kernel stays valid only while the masses stay as uploaded: checked by the pack kernel)
-    if (ctx->p.world > 1) return upload_state(ctx, bodies, true);
-    if (ctx->uniform) {
-        for (size_t i = 0; i < n; ++i)
-            if (bodies[i].mass != ctx->uniform_mass) {
-                set_err(ctx, "nbody_gpu_upload: masses changed; re-create the context (uniform-mass kernel in use)");
-                return NBODY_ESTATE;
-            }
-    }
-    return upload_state(ctx, bodies, false);
+    // (the uniform-mass kernel stays valid only while the masses stay as uploaded: checked by the pack kernel, on the
+    //  device, instead of a host loop over every record)
+    return upload_state(ctx, bodies, ctx->p.world > 1, true);
 }
 
 int nbody_gpu_download_f64(nbody_ctx *ctx, double *pos3, double *vel3, double *acc3, size_t n)
