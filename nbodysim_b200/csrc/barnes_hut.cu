@@ -298,7 +298,6 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
         // everything about the parent that does not depend on its other children, requested at once
         const unsigned pinfo = __ldcg(&arrive[par]);                   // low byte: number of children (counted by the emit kernel)
         const uint4 pa = __ldcg(nodes.aux(par));
-        float4 dp = __ldcg(nodes.data(par));
         float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
         if ((pinfo & 0xffu) == 1u) {
             // an only child (the chains of single-child cells above two close bodies): nobody to wait for, nothing to
@@ -309,8 +308,9 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
             ms = __fadd_rn(ms, mass);
             cells += 1;
         } else {
-            __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, z, mass));
-            __stcg(&nodes.slot_cells[(size_t)par * NCHILD + q], cells);
+            // the subtree size rides in the slot's unused z word in 2-D, in a parallel array for the octree
+            __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, (DIMS == 3) ? z : __uint_as_float(cells), mass));
+            if (DIMS == 3) __stcg(&nodes.slot_cells[(size_t)par * NCHILD + q], cells);
             __threadfence();                                           // my deposit is visible before I announce it
             const unsigned old = atomicAdd(&arrive[par], 0x100u);
             if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;     // a sibling will arrive later and do the work
@@ -322,7 +322,7 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
             for (unsigned k = 0; k < NCHILD; ++k) {
                 const bool occ = (mask >> k) & 1u;
                 ch[k] = occ ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                sub[k] = occ ? __ldcg(&nodes.slot_cells[(size_t)par * NCHILD + k]) : 0u;
+                sub[k] = !occ ? 0u : (DIMS == 3) ? __ldcg(&nodes.slot_cells[(size_t)par * NCHILD + k]) : __float_as_uint(ch[k].z);
             }
             cells = 1;
 #pragma unroll
@@ -342,8 +342,9 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
             py = __fmul_rn(py, inv);
             if (DIMS == 3) pz = __fmul_rn(pz, inv);
         }
-        dp.x = px; dp.y = py; dp.z = ms;
-        __stcg(nodes.data(par), dp);
+        // position and mass of the parent's record; its fourth word (size^2, written by the emit kernel) stays untouched
+        __stcg(reinterpret_cast<float2 *>(nodes.data(par)), make_float2(px, py));
+        __stcg(reinterpret_cast<float *>(nodes.data(par)) + 2, ms);
         if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(par)), pz);
         reinterpret_cast<unsigned *>(nodes.aux(par))[1] = (par + cells < total) ? par + cells : 0u;
         x = px; y = py; z = pz; mass = ms;
