@@ -121,10 +121,14 @@ def ncu_traffic_bytes():
     """DRAM bytes per force launch from the newest committed ncu capture of the headline kernel (None if absent)."""
     for name in ("r2_force_streamk_ncu.txt", "r1_force_uniform_ncu.txt"):
         try:
-            tot = 0.0
+            tot, kernels = 0.0, 0
             for line in open(os.path.join(ROOT, "profiles", name)):
                 f = line.split()
-                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if f and f[0] == "kernel:":
+                    kernels += 1
+                    if kernels > 1:
+                        break                        # only the first kernel of the capture: the force kernel
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and "nan" not in f[1]:
                     tot += float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
             if tot:
                 return {"bytes": tot, "file": "profiles/" + name}
