@@ -219,6 +219,14 @@ int nbody_gpu_collide_stats(nbody_ctx *ctx, uint32_t *candidate_pairs, uint32_t 
  * Writes min(cap, count) nodes; *count receives the total. */
 int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f8, uint32_t *u2, size_t cap, size_t *count);
 
+/* Planning arithmetic of the stream-K force kernel, exposed for tests and capacity planning (pure host functions, no
+ * device needed).  A launch is `tiles` target tiles x `stages` source stages = U units dealt to `ctas` persistent CTAs in
+ * equal contiguous runs: unit u belongs to CTA nbody_gpu_streamk_owner(u, U, ctas); a tile's partial sums land in
+ * owner(last unit of the tile) - owner(first unit) + 1 consecutive slots, and nbody_gpu_streamk_slots is the most any tile
+ * needs (what the library reserves).  Requires 1 <= ctas <= tiles * stages. */
+int nbody_gpu_streamk_owner(long long unit, long long units, int ctas);
+int nbody_gpu_streamk_slots(int tiles, int stages, int ctas);
+
 /* rank 0 creates the NCCL id that every rank passes in nbody_params.nccl_id. */
 int nbody_gpu_nccl_unique_id(uint8_t id[NBODY_NCCL_ID_BYTES]);
 

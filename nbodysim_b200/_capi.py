@@ -106,6 +106,8 @@ GPU_SYMBOLS = {
     "nbody_gpu_collide": (C.c_int, [C.c_void_p]),
     "nbody_gpu_collide_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "nbody_gpu_bh_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "nbody_gpu_streamk_owner": (C.c_int, [C.c_longlong, C.c_longlong, C.c_int]),
+    "nbody_gpu_streamk_slots": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "nbody_gpu_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "nbody_gpu_shutdown": (None, [C.c_void_p]),
     "nbody_gpu_strerror": (C.c_char_p, [C.c_int]),

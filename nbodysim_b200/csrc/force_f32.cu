@@ -165,6 +165,8 @@ static cudaError_t launch_streamk_t(const ForceLaunch &L, cudaStream_t st)
     return L.dims == 2 ? launch_streamk_d<LargeCfg, FORM, GUARD, 2>(L, st) : launch_streamk_d<LargeCfg, FORM, GUARD, 3>(L, st);
 }
 
+int force_f32_streamk_owner(long long unit, long long units, int ctas) { return sk_owner(unit, units, ctas); }
+
 int force_f32_streamk_slots(int tiles, int stages, int ctas)
 {
     const long long U = (long long)tiles * stages;

@@ -105,6 +105,7 @@ int force_f32_fast_ctas_per_sm(bool uniform_mass, bool small_tile = false);
 int force_f32_streamk_ctas_per_sm(bool uniform_mass, bool small_tile);
 // slots a stream-K launch of `tiles` target tiles x `stages` source stages on `ctas` CTAs needs (the most any tile uses)
 int force_f32_streamk_slots(int tiles, int stages, int ctas);
+int force_f32_streamk_owner(long long unit, long long units, int ctas);   // CTA that owns a unit (sk_owner)
 int force_f32_fast_grid(const ForceLaunch &L);
 
 cudaError_t launch_integrate_f32(const IntegLaunch &L, cudaStream_t st);

@@ -1264,6 +1264,18 @@ int nbody_gpu_bh_nodes(nbody_ctx *ctx, float *f8, uint32_t *u2, size_t cap, size
     return NBODY_OK;
 }
 
+int nbody_gpu_streamk_owner(long long unit, long long units, int ctas)
+{
+    if (units <= 0 || ctas <= 0 || unit < 0 || unit >= units || (long long)ctas > units) return NBODY_EINVAL;
+    return force_f32_streamk_owner(unit, units, ctas);
+}
+
+int nbody_gpu_streamk_slots(int tiles, int stages, int ctas)
+{
+    if (tiles <= 0 || stages <= 0 || ctas <= 0 || (long long)ctas > (long long)tiles * stages) return NBODY_EINVAL;
+    return force_f32_streamk_slots(tiles, stages, ctas);
+}
+
 int nbody_gpu_nccl_unique_id(uint8_t id[NBODY_NCCL_ID_BYTES])
 {
     if (!id) return NBODY_EINVAL;

@@ -146,3 +146,30 @@ def test_shard_plan_covers_everything_once(n, world):
         assert np_ == npad and start == pos and count == npad // world and count % 2048 == 0
         pos += count
     assert pos == npad
+
+
+def test_streamk_partition_arithmetic():
+    """the stream-K force kernel and the integrator agree on who owns which (tile, stage) unit through one piece of integer
+    arithmetic (sk_owner): every unit has exactly one owner, owners are non-decreasing in unit order and every CTA owns a
+    non-empty contiguous run of nearly equal length, so the CTAs that share a tile are consecutive -- its partial slots
+    0 .. ns-1 are all written -- and no tile needs more slots than the library reserves"""
+    lib = capi.gpu_lib()
+    rng = np.random.default_rng(5)
+    cases = [(512, 2048, 148), (8, 16, 128), (1, 1, 1), (13, 7, 91), (49, 98, 592), (3, 1000, 148), (2048, 3, 148)]
+    cases += [(int(t), int(s), int(g)) for t, s, g in zip(rng.integers(1, 300, 20), rng.integers(1, 300, 20), rng.integers(1, 700, 20))]
+    for tiles, stages, ctas in cases:
+        U = tiles * stages
+        ctas = min(ctas, U)
+        owner = np.array([lib.nbody_gpu_streamk_owner(u, U, ctas) for u in range(U)]) if U <= 20000 else None
+        worst = lib.nbody_gpu_streamk_slots(tiles, stages, ctas)
+        assert worst >= 1
+        if owner is None:
+            continue
+        assert owner[0] == 0 and owner[-1] == ctas - 1 and (np.diff(owner) >= 0).all() and (np.diff(owner) <= 1).all()
+        runs = np.bincount(owner, minlength=ctas)
+        assert runs.min() >= 1 and runs.max() - runs.min() <= 1                  # equal runs to within one unit
+        starts = np.array([(k * U) // ctas for k in range(ctas)])              # the kernel's sk_start
+        assert np.array_equal(np.searchsorted(owner, np.arange(ctas)), starts)
+        ns = owner[stages - 1::stages] - owner[0::stages] + 1                     # slots per tile
+        assert ns.max() == worst
+    assert lib.nbody_gpu_streamk_slots(4, 4, 17) == capi.EINVAL and lib.nbody_gpu_streamk_owner(5, 4, 2) == capi.EINVAL
