@@ -20,8 +20,9 @@
 // walking its pairs in the canonical (first, second) order, each resolve reading what the previous one
 // wrote, as in the reference.  Pair keys sort as (component, first, second).
 //
-// The phases are written as grid-stride device functions so that the same code runs either as one kernel
-// per phase (any n) or inside the single-cluster kernel of small scenes (cluster barriers between phases).
+// Every pass starts with a hash grid over the bodies' cells (collide.cuh).  Small scenes take their sweep pairs
+// straight from it and finish in one CTA; large scenes use it to decide whether anything overlaps at all before
+// running one kernel per phase.  The phases are grid-stride device functions shared by both.
 #include "collide.cuh"
 #include "cluster_prims.cuh"
 #include <cstring>

@@ -1,6 +1,6 @@
 // collide.cuh -- phases of the collision pass (see collide.cu for the algorithm), as grid-stride device functions:
-// `gtid` of `gthreads` cooperating threads.  Shared by the one-kernel-per-phase path (collide.cu) and the
-// single-cluster step kernels of small scenes (small_scene.cu).
+// `gtid` of `gthreads` cooperating threads, so that the same code runs as one kernel per phase (large scenes) and inside
+// the one-CTA finishing kernel of small scenes (collide.cu).
 #pragma once
 #include "kernels.h"
 #include "radix_sort.cuh"
