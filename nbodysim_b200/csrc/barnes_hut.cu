@@ -199,7 +199,11 @@ bh_emit_kernel(const float *__restrict__ posm, const unsigned long long *__restr
     constexpr int BITS = BhT<DIMS>::BITS;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     // more cells than reserved: the tree is truncated, so raise the context's sticky (host-visible) status word
-    if (s == 0 && offs[n] > cap && status) *reinterpret_cast<volatile unsigned *>(status) = 1u;
+    if (s == 0 && status) {
+        const unsigned cells = offs[n];
+        reinterpret_cast<volatile unsigned *>(status)[4] = cells;          // latest cell count: the host grows the reservation early
+        if (cells > cap) *reinterpret_cast<volatile unsigned *>(status) = 1u;
+    }
     if (s >= n || count[s] == 0) return;
     const unsigned long long k = keys[s];
     const unsigned body = idx[s];

@@ -962,6 +962,33 @@ static int step_with_graph(nbody_ctx *ctx, float dt, int &remaining)
     return NBODY_OK;
 }
 
+// The Barnes-Hut cell reservation follows the tree: every build reports its cell count through the mapped status words,
+// and before new steps are enqueued a reservation that is more than 3/4 full is doubled (up to the 33 cells per body a
+// tree can need), so that a scene whose bodies cluster over time does not run into the overflow error.
+static int grow_bh_reservation_if_needed(nbody_ctx *ctx)
+{
+    for (Dev &d : ctx->devs) {
+        if (!d.h_status) continue;
+        const unsigned cells = ((volatile unsigned *)d.h_status)[4];
+        const unsigned long long limit = 33ull * ctx->n + 1024ull;
+        if ((unsigned long long)cells * 4ull <= (unsigned long long)d.bh.node_cap * 3ull || d.bh.node_cap >= limit) continue;
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.stream));
+        const double factor = std::min(33.0, 2.0 * (double)d.bh.node_cap / (double)ctx->n);
+        const int cluster_mode = d.bh.cluster_ctas > 0 ? 2 : 1;
+        const bool warp_walk = d.bh.warp_walk;
+        const unsigned window = d.bh.walk_window;
+        unsigned *status = d.bh.status;
+        d.bh.release();
+        CU(d.bh.alloc(ctx->n, ctx->p.dims, factor, cluster_mode, (size_t)-1));
+        d.bh.status = status; d.bh.warp_walk = warp_walk; d.bh.walk_window = window;
+        if (d.graph) { cudaGraphExecDestroy(d.graph); d.graph = nullptr; }       // the graphs hold the old buffers
+        for (int k = 0; k < 2; ++k) if (d.graph1[k]) { cudaGraphExecDestroy(d.graph1[k]); d.graph1[k] = nullptr; }
+        ((volatile unsigned *)d.h_status)[4] = 0;
+    }
+    return NBODY_OK;
+}
+
 // One step per call (nbody_gpu_step(ctx, dt, 1) from a viewer loop or an upload / step / download cycle): one graph per
 // buffer parity, so such a caller pays one graph launch instead of ~18 kernel launches per step.
 static int step_with_single_graph(nbody_ctx *ctx, float dt)
@@ -1003,6 +1030,10 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
     // auto: graphs pay off only when the step is launch-bound (small shards) and the call is long enough
     // (the Barnes-Hut build and the collision pass are fully asynchronous -- sorts, scan, COM pass, pair
     //  discovery and resolve keep their counters on the device -- so they capture too)
+    if (ctx->bh) {
+        const int rc = grow_bh_reservation_if_needed(ctx);
+        if (rc != NBODY_OK) return rc;
+    }
     const bool graph_ok = ctx->world == 1 && ctx->devs.size() == 1 && !ctx->profile_next;
     const bool want = ctx->p.use_graph == 1 || (ctx->p.use_graph < 0 && (ctx->n_padded <= 32768 || (ctx->bh && ctx->n_padded <= 262144)));
     if (graph_ok && want && nsteps >= 8) {

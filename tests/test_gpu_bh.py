@@ -310,3 +310,32 @@ def test_per_frame_calls_replay_one_step_graphs_bit_identically():
         got = s.bodies.copy()
     for f in ("pos", "vel", "acc"):
         assert np.array_equal(bits(got[f]), bits(want[f])), f
+
+
+def test_bh_reservation_grows_before_it_overflows():
+    """a tree that fills more than 3/4 of the cell reservation makes the next nbody_gpu_step call double it (buffers
+    reallocated, graphs dropped): the steps before and after stay bit-exact and nothing overflows"""
+    from nbodysim_b200.bodies import empty_bodies
+
+    r = np.random.default_rng(31)
+    n_pairs, n_single = 350, 2000
+    n = 2 * n_pairs + n_single
+    b = empty_bodies(n)
+    p = r.uniform(500.0, 1000.0, (n_pairs, 2)).astype(np.float32)
+    b["pos"][0:2 * n_pairs:2] = p
+    b["pos"][1:2 * n_pairs:2] = np.nextafter(np.nextafter(p, np.float32(2000)), np.float32(2000))
+    b["pos"][2 * n_pairs:] = r.uniform(500.0, 1000.0, (n_single, 2)).astype(np.float32)
+    b["mass"] = r.uniform(0.5, 2.0, n).astype(np.float32)
+    ncells = oracle_preorder(O.orc_bh_build(b)).shape[0]
+    assert 0.75 * (4 * n + 1024) < ncells < 4 * n + 1024
+    want = b.copy()
+    for _ in range(4):
+        want["acc"] = O.orc_bh_acc(want, 1.0, 1.0)
+        O.oracle().orc_iterate_after_attract(want.ctypes.data, n, 0.01, 0, 2)
+    with bh_sim(b, dt=0.01, theta=1.0, eps=1.0) as s:
+        s.step(1)
+        s.sync()
+        s.step(3)                      # the reservation is doubled here, before the steps are enqueued
+        got = s.bodies.copy()
+    for f in ("pos", "vel", "acc"):
+        assert np.array_equal(bits(got[f]), bits(want[f])), f
