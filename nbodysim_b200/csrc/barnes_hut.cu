@@ -357,6 +357,274 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
     }
 }
 
+// ---- 5 + 6 in one kernel for everything but the top of the tree -------------------------------------------------------------
+// The climb above pays two or three dependent L2 round trips, a fence and an atomic PER TREE LEVEL (22 levels on the
+// reference's scene: 44 us of a 200 us step) although almost every cell covers a handful of neighbouring sorted bodies.
+// Here a CTA owns BHL_MAIN consecutive sorted bodies and sees a window of BHL_MAIN + BHL_HALO of them.  A cell is LOCAL
+// iff its span (owner .. last body) is at most BHL_HALO bodies long -- then the whole subtree lies inside the owner's
+// window and is finished there, level by level from the deepest, through shared memory: a thread keeps the datum of the
+// chain cell it is working on; when a cell is complete the owner of its parent adds the children up IN QUADRANT ORDER
+// (its own chain child first, then the published first cells of the following threads, each of which also says where
+// its span ends, i.e. where the next sibling starts) with exactly Quadtree::propagate's arithmetic.  Skip pointers fall
+// out: next = first cell of the body after the span.  The halo threads redo the next CTAs' subtrees (no writes), which
+// costs nothing next to a round trip through L2.  Only cells LONGER than the halo (a few hundred at n = 25,000) are left
+// to the climb: every thread reports the cell where its chain leaves the local part (`gstart`) and counts it as a
+// child of its parent; bh_climb_kernel then runs the arrival protocol of bh_propagate_kernel from there.
+// The length criterion is one both sides can evaluate: the parent's owner sees its whole window, a child finds the
+// owner by the gallop-and-bisect of bh_emit_kernel and the span's end by following its siblings.
+constexpr int BHL_MAIN = 256, BHL_HALO = 256, BHL_THREADS = BHL_MAIN + BHL_HALO;
+
+template <int DIMS>
+__global__ void __launch_bounds__(BHL_THREADS)
+bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *__restrict__ keys,
+                     const unsigned *__restrict__ idx, size_t n, const BhRoot *__restrict__ root,
+                     const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
+                     const unsigned char *__restrict__ first, const unsigned char *__restrict__ leaf,
+                     BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap, unsigned *status, unsigned *__restrict__ gstart)
+{
+    constexpr int BITS = BhT<DIMS>::BITS;
+    constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
+    constexpr int M = BHL_MAIN, H = BHL_HALO, W = BHL_THREADS;
+    constexpr unsigned short NOT_LOCAL = 0xffffu;
+    __shared__ int sA[W + 1];                 // levels shared with the previous sorted body (-1: none); [W] = the body after the window
+    __shared__ unsigned soffs[W + 1];         // first cell of every body of the window
+    __shared__ float4 sval[W];                // datum of a thread's FIRST cell once complete: (x, y, z, mass)
+    __shared__ unsigned short send[W];        // ... and the window index where that cell's span ends; NOT_LOCAL: not computed here
+    __shared__ unsigned char spulled[W];      // the first cell was added to its parent by the parent's owner in this CTA
+    __shared__ int s_maxd;
+    const unsigned i = threadIdx.x;
+    const size_t s0 = (size_t)blockIdx.x * M, s = s0 + i;
+    const unsigned total = offs[n];
+    if (s == 0 && status) {                   // more cells than reserved: see bh_emit_kernel
+        reinterpret_cast<volatile unsigned *>(status)[4] = total;
+        if (total > cap) *reinterpret_cast<volatile unsigned *>(status) = 1u;
+    }
+    const bool exists = s < n;
+    const unsigned long long k = exists ? keys[s] : 0ull;
+    sA[i] = (exists && s > 0) ? lcp_levels<DIMS>(keys[s - 1], k) : -1;
+    soffs[i] = s <= n ? offs[s] : total;
+    if (i == W - 1) {
+        const size_t sw = s0 + W;
+        sA[W] = sw < n ? lcp_levels<DIMS>(keys[sw - 1], keys[sw]) : -1;
+        soffs[W] = sw <= n ? offs[sw] : total;
+    }
+    spulled[i] = 0;
+    send[i] = NOT_LOCAL;
+    if (i == 0) s_maxd = 0;
+    const unsigned cnt = exists ? count[s] : 0u;
+    const bool main_thread = i < (unsigned)M;
+    int firstd = 0, leafd = 0;
+    unsigned off = 0, tp = i + 1;            // tp: window index where the span of the cell in `cur` ends
+    float cx_ = 0.f, cy_ = 0.f, cz_ = 0.f, cm_ = 0.f;   // `cur`: datum of the deepest unfinished... of the chain cell at depth dcur
+    if (cnt) {
+        firstd = first[s]; leafd = leaf[s]; off = offs[s];
+        const size_t g = blk_index(idx[s], 0);
+        cx_ = posm[g]; cy_ = posm[g + BLK]; cz_ = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
+        // merged mass of coincident bodies, added in body-index order (stable sort) like insert() :56-60
+        cm_ = posm[g + 3 * BLK];
+        size_t t = s + 1;
+        for (; t < n && keys[t] == k; ++t) cm_ = __fadd_rn(cm_, posm[blk_index(idx[t], 0) + 3 * BLK]);
+        tp = (unsigned)min(t - s0, (size_t)W + 1);
+    }
+    __syncthreads();
+    if (cnt) atomicMax(&s_maxd, leafd);
+
+    // ---- skeleton of the cells this body owns (top-down: the fp32 quad recursion), leaf record complete
+    if (cnt && main_thread) {
+        float qx = root->cx, qy = root->cy, qz = root->cz, size = root->size;
+        for (int d = 0; d <= leafd; ++d) {
+            if (d >= firstd) {
+                const unsigned c = off + (unsigned)(d - firstd);
+                if (c < cap) {
+                    const bool is_leaf = (d == leafd);
+                    *nodes.data(c) = make_float4(is_leaf ? cx_ : 0.f, is_leaf ? cy_ : 0.f, is_leaf ? cm_ : 0.f, __fmul_rn(size, size));
+                    nodes.quad[c] = make_float4(qx, qy, size, qz);
+                    const unsigned qd = (d > 0) ? ((unsigned)(k >> (64 - BITS * d)) & (NCHILD - 1u)) : 0u;
+                    *nodes.aux(c) = make_uint4(__float_as_uint((DIMS == 3 && is_leaf) ? cz_ : 0.f),
+                                               (is_leaf && c + 1u < total) ? c + 1u : 0u,
+                                               (unsigned)d | (is_leaf ? 256u : 0u) | (qd << 9), (d > firstd) ? c - 1u : 0xffffffffu);
+                }
+            }
+            if (d < leafd) {
+                const unsigned q = (unsigned)(k >> (64 - BITS * (d + 1))) & (NCHILD - 1u);
+                const float ns = __fmul_rn(size, 0.5f);
+                qx = __fadd_rn(qx, __fmul_rn((q & 1u) ? 0.5f : -0.5f, ns));
+                qy = __fadd_rn(qy, __fmul_rn((q & 2u) ? 0.5f : -0.5f, ns));
+                if (DIMS == 3) qz = __fadd_rn(qz, __fmul_rn((q & 4u) ? 0.5f : -0.5f, ns));
+                size = ns;
+            }
+        }
+    }
+
+    // ---- centres of mass of the local cells, deepest level first
+    auto span_ok = [&](unsigned t) { return t <= (unsigned)W && t - i <= (unsigned)H; };
+    bool alive = cnt != 0 && span_ok(tp);     // false: this chain continues in the climb (or the body owns nothing)
+    int dcur = leafd;
+    if (alive && firstd == leafd) { sval[i] = make_float4(cx_, cy_, cz_, cm_); send[i] = (unsigned short)tp; }
+    __syncthreads();
+    for (int d = s_maxd - 1; d >= 0; --d) {
+        if (alive && d >= firstd && d < leafd) {              // the cell at depth d of this chain; `cur` is its first child
+            float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+            px = __fadd_rn(px, __fmul_rn(cx_, cm_));
+            py = __fadd_rn(py, __fmul_rn(cy_, cm_));
+            if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(cz_, cm_));
+            ms = __fadd_rn(ms, cm_);
+            unsigned t = tp;
+            bool ok = true;
+            while (t <= (unsigned)W && sA[t] == d) {          // the following children: first cells of later threads, in key order
+                const unsigned short e = (t < (unsigned)W) ? send[t] : NOT_LOCAL;
+                if (e == NOT_LOCAL) { ok = false; break; }
+                const float4 ch = sval[t];
+                px = __fadd_rn(px, __fmul_rn(ch.x, ch.w));
+                py = __fadd_rn(py, __fmul_rn(ch.y, ch.w));
+                if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch.z, ch.w));
+                ms = __fadd_rn(ms, ch.w);
+                t = e;
+            }
+            ok = ok && span_ok(t);
+            if (ok) {
+                for (unsigned u = tp; u < t; u = send[u]) spulled[u] = 1;
+                if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
+                    const float inv = __fdiv_rn(1.0f, ms);
+                    px = __fmul_rn(px, inv);
+                    py = __fmul_rn(py, inv);
+                    if (DIMS == 3) pz = __fmul_rn(pz, inv);
+                }
+                cx_ = px; cy_ = py; cz_ = pz; cm_ = ms;
+                tp = t; dcur = d;
+                const unsigned c = off + (unsigned)(d - firstd);
+                if (main_thread && c < cap) {
+                    *reinterpret_cast<float2 *>(nodes.data(c)) = make_float2(px, py);
+                    reinterpret_cast<float *>(nodes.data(c))[2] = ms;
+                    if (DIMS == 3) reinterpret_cast<float *>(nodes.aux(c))[0] = pz;
+                    reinterpret_cast<unsigned *>(nodes.aux(c))[1] = (s0 + t < n) ? soffs[t] : 0u;
+                }
+                if (d == firstd) { sval[i] = make_float4(px, py, pz, ms); send[i] = (unsigned short)t; }
+            } else alive = false;
+        }
+        if (!__syncthreads_or(alive && dcur > firstd)) break;
+    }
+    __syncthreads();
+
+    // ---- hand-over to the climb: count every cell that the local part did not attach to its parent as a child of that parent
+    if (!(cnt && main_thread)) return;
+    unsigned start = 0xffffffffu;
+    // cells of the chain above the local part (depths firstd .. dcur-1) and the local part's top cell (depth dcur) hang from the chain
+    for (int d = dcur; d > firstd; --d) {
+        const unsigned c = off + (unsigned)(d - firstd), par = c - 1u;
+        if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + ((unsigned)(k >> (64 - BITS * d)) & (NCHILD - 1u)))));
+    }
+    if (dcur > firstd) start = off + (unsigned)(dcur - firstd);
+    if (firstd > 0 && !(dcur == firstd && spulled[i])) {
+        // owner of the parent cell (depth firstd - 1): the first sorted body with that prefix -- gallop backwards, then bisect
+        const int shp = 64 - BITS * (firstd - 1);
+        const unsigned long long pp = k >> shp;
+        size_t lo = 0, hi = s, step = 1;
+        while (lo < hi) {
+            const size_t probe = (hi >= lo + step) ? hi - step : lo;
+            if ((keys[probe] >> shp) < pp) { lo = probe + 1; break; }
+            hi = probe;
+            step <<= 1;
+        }
+        while (lo < hi) {
+            const size_t mid = (lo + hi) >> 1;
+            if ((keys[mid] >> shp) >= pp) hi = mid; else lo = mid + 1;
+        }
+        // is the parent local to ITS owner's CTA?  Only if this cell is local and the parent's span (owner .. end of my last sibling) is short
+        bool parent_local = false;
+        if (dcur == firstd && alive) {
+            unsigned t = tp;
+            bool ok = true;
+            while (t <= (unsigned)W && sA[t] == firstd - 1) {
+                const unsigned short e = (t < (unsigned)W) ? send[t] : NOT_LOCAL;
+                if (e == NOT_LOCAL) { ok = false; break; }
+                t = e;
+            }
+            parent_local = ok && t <= (unsigned)W && (s0 + t) - lo <= (size_t)H;
+        }
+        if (!parent_local) {
+            const unsigned par = offs[lo] + (unsigned)(firstd - 1 - (int)first[lo]);
+            if (off < cap) reinterpret_cast<unsigned *>(nodes.aux(off))[3] = par;
+            if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + ((unsigned)(k >> (64 - BITS * firstd)) & (NCHILD - 1u)))));
+            if (dcur == firstd) start = off;
+        }
+    }
+    gstart[s] = start;
+}
+
+// The climb over the cells the local kernel left: bh_propagate_kernel's protocol, started from `gstart` instead of the leaves.
+template <int DIMS>
+__global__ void __launch_bounds__(256)
+bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
+                const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive, unsigned cap)
+{
+    constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || count[s] == 0) return;
+    unsigned c = gstart[s];
+    const unsigned total = offs[n], m = min(total, cap);
+    if (c >= m) return;                                                // 0xffffffff: nothing of this chain is left
+    uint4 a = __ldcg(nodes.aux(c));
+    const float4 d0 = __ldcg(nodes.data(c));
+    float x = d0.x, y = d0.y, z = (DIMS == 3) ? __uint_as_float(a.x) : 0.f, mass = d0.z;
+    unsigned cells = (a.y ? a.y : total) - c;                          // cells in the subtree of c (from its skip pointer)
+    for (;;) {
+        const unsigned par = a.w;
+        if (par == 0xffffffffu || par >= m) break;                     // reached the root
+        const unsigned q = (a.z >> 9) & (NCHILD - 1u);
+        const unsigned pinfo = __ldcg(&arrive[par]);                   // low byte: number of children
+        const uint4 pa = __ldcg(nodes.aux(par));
+        float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+        if ((pinfo & 0xffu) == 1u) {                                   // an only child: nobody to wait for
+            px = __fadd_rn(px, __fmul_rn(x, mass));
+            py = __fadd_rn(py, __fmul_rn(y, mass));
+            if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(z, mass));
+            ms = __fadd_rn(ms, mass);
+            cells += 1;
+        } else {
+            __stcg(&nodes.slots[(size_t)par * NCHILD + q], make_float4(x, y, (DIMS == 3) ? z : __uint_as_float(cells), mass));
+            if (DIMS == 3) __stcg(&nodes.slot_cells[(size_t)par * NCHILD + q], cells);
+            __threadfence();                                           // my deposit is visible before I announce it
+            const unsigned old = atomicAdd(&arrive[par], 0x100u);
+            if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;     // a sibling will arrive later and do the work
+            __threadfence();
+            const unsigned mask = (old >> 16) & 0xffu;
+            float4 ch[NCHILD];
+            unsigned sub[NCHILD];
+#pragma unroll
+            for (unsigned k = 0; k < NCHILD; ++k) {
+                const bool occ = (mask >> k) & 1u;
+                ch[k] = occ ? __ldcg(&nodes.slots[(size_t)par * NCHILD + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                sub[k] = !occ ? 0u : (DIMS == 3) ? __ldcg(&nodes.slot_cells[(size_t)par * NCHILD + k]) : __float_as_uint(ch[k].z);
+            }
+            cells = 1;
+#pragma unroll
+            for (unsigned k = 0; k < NCHILD; ++k) {
+                if ((mask >> k) & 1u) {                                // children in quadrant order
+                    px = __fadd_rn(px, __fmul_rn(ch[k].x, ch[k].w));
+                    py = __fadd_rn(py, __fmul_rn(ch[k].y, ch[k].w));
+                    if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch[k].z, ch[k].w));
+                    ms = __fadd_rn(ms, ch[k].w);
+                    cells += sub[k];
+                }
+            }
+        }
+        if (ms > 0.f) {
+            const float inv = __fdiv_rn(1.0f, ms);
+            px = __fmul_rn(px, inv);
+            py = __fmul_rn(py, inv);
+            if (DIMS == 3) pz = __fmul_rn(pz, inv);
+        }
+        __stcg(reinterpret_cast<float2 *>(nodes.data(par)), make_float2(px, py));
+        __stcg(reinterpret_cast<float *>(nodes.data(par)) + 2, ms);
+        if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(par)), pz);
+        reinterpret_cast<unsigned *>(nodes.aux(par))[1] = (par + cells < total) ? par + cells : 0u;
+        x = px; y = py; z = pz; mass = ms;
+        a = pa;
+        c = par;
+    }
+}
+
 // ---- the whole build as ONE cluster kernel (small scenes) ----------------------------------------------------------------
 // Same tree, same bits as the launch-per-phase build above (tests compare both with the oracle); what changes is the
 // execution model: one thread-block cluster walks through the phases, separated by hardware cluster barriers.
@@ -885,6 +1153,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int clus
     BH_ALLOC(node_slot_cells, (size_t)node_cap * (dims == 3 ? 8 : 4) * 4)
     BH_ALLOC(node_owner, (size_t)node_cap * 4)
     BH_ALLOC(shard_targets, (n + 1) * 4)
+    BH_ALLOC(climb_start, (n + 1) * 4)
     // everything that must be zero at the start of a build lives in ONE region cleared by one memset per step:
     // bounding box | radix-sort scratch (histograms, tickets, status words) | scan scratch | arrival counters
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -901,7 +1170,7 @@ cudaError_t BhWorkspace::alloc(size_t n, int dims_, double node_factor, int clus
 
 void BhWorkspace::release()
 {
-    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_slot_cells, node_owner, shard_targets, zero_region, trace};
+    void *ptrs[] = {root, keys_in, keys, idx_in, idx, count, offs, first, leaf, node_data, node_quad, node_slots, node_slot_cells, node_owner, shard_targets, climb_start, zero_region, trace};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = BhWorkspace();
 }
@@ -925,18 +1194,32 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     // stable LSD sort; the result lands back in the first buffer pair -> swap roles
     bh_keys_kernel<DIMS, true><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
                                                      (unsigned *)w.idx_in, (unsigned *)w.sort_temp);
+    // high digits first: the leading 32 bits (16 quadtree levels; 48 bits = 16 octree levels) order all bodies but the few
+    // that share a deeper cell, which the sort's run repair puts right (radix_sort.cuh)
     if ((e = radix_sort_u64((unsigned long long *)w.keys_in, (unsigned long long *)w.keys, (unsigned *)w.idx_in, (unsigned *)w.idx,
-                            n, w.sort_temp, st, 0, 64, launches, nullptr, true)) != cudaSuccess) return e;
+                            n, w.sort_temp, st, 0, 64, launches, nullptr, true, DIMS == 3 ? 16 : 32)) != cudaSuccess) return e;
     std::swap(w.keys_in, w.keys);
     std::swap(w.idx_in, w.idx);
     bh_count_kernel<DIMS><<<g256, 256, 0, st>>>((const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first, (unsigned char *)w.leaf);
     if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.scan_temp, st, launches, true)) != cudaSuccess) return e;
-    bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
-                                               (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,
-                                               (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, w.node_cap, w.status);
-    bh_propagate_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned char *)w.first,
-                                                    (const unsigned char *)w.leaf, (const unsigned *)w.count, (unsigned *)w.node_arrive,
-                                                    w.node_cap);
+    // cells, centres of mass and skip pointers: the local kernel + the climb over the few long cells (default), or the
+    // round-1/2 pair emit + climb-from-the-leaves (NBODY_BH_LOCAL=0; bit-identical trees, kept for comparison)
+    static const bool local_off = getenv("NBODY_BH_LOCAL") && atoi(getenv("NBODY_BH_LOCAL")) == 0;
+    if (!local_off) {
+        bh_emit_local_kernel<DIMS><<<(unsigned)((n + BHL_MAIN - 1) / BHL_MAIN), BHL_THREADS, 0, st>>>(
+            posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,
+            (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive,
+            w.node_cap, w.status, (unsigned *)w.climb_start);
+        bh_climb_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
+                                                    (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap);
+    } else {
+        bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
+                                                   (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,
+                                                   (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, w.node_cap, w.status);
+        bh_propagate_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned char *)w.first,
+                                                        (const unsigned char *)w.leaf, (const unsigned *)w.count, (unsigned *)w.node_arrive,
+                                                        w.node_cap);
+    }
     w.count_valid = false;
     if (launches) *launches += 5;                            // the sort and the scan count their own launches
     return cudaGetLastError();

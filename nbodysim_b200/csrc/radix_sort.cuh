@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 
 namespace nb {
 
@@ -31,6 +32,15 @@ constexpr int RS_MIN_TILE = RS_THREADS * RS_ROWS_SMALL;
 #define RS_SMALL_TILE_MAX_N (8u << 20)
 #endif
 constexpr int RS_MAX_PASSES = 8;
+// scratch layout: [RS_MAX_PASSES][256] digit histograms | RS_MISC_WORDS words (tickets of up to 2 x RS_MAX_PASSES pass
+// launches, the grid-barrier word, the "tie runs too long" flag) | status words
+constexpr int RS_MISC_WORDS = 64, RS_MISC_BARRIER = 2 * RS_MAX_PASSES, RS_MISC_FLAG = 2 * RS_MAX_PASSES + 1;
+// HIGH DIGITS FIRST (`lazy_low_bits` = L > 0).  Quadrant-path keys of distinct bodies almost always differ within their
+// leading bits; the low digits only order the few bodies that share a deep cell.  So: LSD passes over the digits at and
+// above bit L only, then ONE in-place repair: the first key of every run of keys that agree above bit L insertion-sorts
+// its run by the full key (stable; runs are 2-3 keys in practice).  A run longer than RS_TIE_RUN_MAX raises a flag and
+// the full sort over all digits runs after all (same result: LSD passes are stable whatever order they start from).
+constexpr int RS_TIE_RUN_MAX = 16;
 
 __device__ __forceinline__ unsigned rs_digit(unsigned long long k, int shift) { return (unsigned)(k >> shift) & 255u; }
 
@@ -275,15 +285,60 @@ os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__rest
     }
 }
 
+// `run_if` (the tie-run flag of a high-digits-first sort): the pass belongs to the full sort that only runs when the
+// repair gave up; a launch that finds the flag clear returns at once.
 template <bool HAS_VALS, int RS_ROWS>
 static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
 os_pass_kernel(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, const unsigned *__restrict__ n_dev,
                int shift, unsigned pass,
                const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, unsigned long long *status,
-               unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
+               unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out, const unsigned *run_if)
 {
+    if (run_if && *run_if == 0u) return;
     if (n_dev) n = (*n_dev < n) ? *n_dev : n;             // live item count kept on the device (n is its bound)
     os_pass_tile<HAS_VALS, RS_ROWS, true>(keys, vals, n, shift, pass, hist_p, ticket, -1, status, keys_out, vals_out);
+}
+
+// ---- repair after a high-digits-first sort ---------------------------------------------------------------------------------
+// Element i: if it is the FIRST of a run of keys that agree above bit `low_bits`, insertion-sort the run in place by the
+// full key (strict comparison => stable).  Runs are disjoint, so the leaders never touch each other's elements; everything
+// goes through L2 (the keys were scattered by other SMs moments ago).  A run longer than RS_TIE_RUN_MAX is left alone and
+// reported through `flag`.
+template <bool HAS_VALS>
+__device__ __forceinline__ void rs_repair_run(unsigned long long *keys, unsigned *vals, size_t n, int low_bits, size_t i, unsigned *flag)
+{
+    if (i + 1 >= n) return;
+    const unsigned long long hi = __ldcg(keys + i) >> low_bits;
+    if ((__ldcg(keys + i + 1) >> low_bits) != hi) return;
+    if (i > 0 && (__ldcg(keys + i - 1) >> low_bits) == hi) return;           // not the first of its run
+    size_t e = i + 2;
+    while (e < n && e - i <= (size_t)RS_TIE_RUN_MAX && (__ldcg(keys + e) >> low_bits) == hi) ++e;
+    if (e - i > (size_t)RS_TIE_RUN_MAX) { *reinterpret_cast<volatile unsigned *>(flag) = 1u; return; }
+    for (size_t a = i + 1; a < e; ++a) {
+        const unsigned long long ka = __ldcg(keys + a);
+        const unsigned va = HAS_VALS ? __ldcg(vals + a) : 0u;
+        size_t b = a;
+        while (b > i) {
+            const unsigned long long kb = __ldcg(keys + b - 1);
+            if (!(kb > ka)) break;
+            __stcg(keys + b, kb);
+            if (HAS_VALS) __stcg(vals + b, __ldcg(vals + b - 1));
+            --b;
+        }
+        if (b != a) {
+            __stcg(keys + b, ka);
+            if (HAS_VALS) __stcg(vals + b, va);
+        }
+    }
+}
+
+template <bool HAS_VALS>
+static __global__ void __launch_bounds__(RS_THREADS)
+os_repair_kernel(unsigned long long *keys, unsigned *vals, size_t n, const unsigned *__restrict__ n_dev, int low_bits, unsigned *flag)
+{
+    if (n_dev) n = (*n_dev < n) ? *n_dev : n;
+    for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_THREADS)
+        rs_repair_run<HAS_VALS>(keys, vals, n, low_bits, i, flag);
 }
 
 // ---- all digit passes in ONE kernel (small inputs: every tile co-resident) -------------------------------------------------
@@ -307,27 +362,39 @@ __device__ __forceinline__ void rs_grid_barrier(unsigned *counter, unsigned targ
 template <bool HAS_VALS, int RS_ROWS>
 static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
 os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b, size_t n,
-                   const unsigned *__restrict__ n_dev, int pass0, int npasses, const unsigned *__restrict__ hist,
-                   unsigned *__restrict__ barrier_word, unsigned long long *status)
+                   const unsigned *__restrict__ n_dev, int pass0, int npasses, int lazy_passes, const unsigned *__restrict__ hist,
+                   unsigned *__restrict__ misc, unsigned long long *status)
 {
     if (n_dev) n = (*n_dev < n) ? *n_dev : n;
+    unsigned *barrier_word = misc + RS_MISC_BARRIER, *flag = misc + RS_MISC_FLAG;
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
-    unsigned syncs = 0;
+    unsigned syncs = 0, pass_id = 0;
     bool flipped = false;
-    for (int p = 0; p < npasses; ++p) {
-        const unsigned *hist_p = hist + p * 256;
-        if (__syncthreads_or(hist_p[threadIdx.x] == (unsigned)n)) continue;        // uniform over the grid: identity pass
-        os_pass_tile<HAS_VALS, RS_ROWS, false>(kin, vin, n, 8 * (pass0 + p), (unsigned)p, hist_p, nullptr, (int)blockIdx.x, status, kout, vout);
+    const size_t ntiles = (n + (size_t)RS_THREADS * RS_ROWS - 1) / ((size_t)RS_THREADS * RS_ROWS);
+    // lazy_passes > 0: only the digits from `lazy_passes` upwards first, then the repair, then -- if a tie run was too
+    // long -- every digit after all
+    for (int round = 0, first = lazy_passes; round < 2; ++round, first = 0) {
+        for (int p = first; p < npasses; ++p, ++pass_id) {
+            const unsigned *hist_p = hist + p * 256;
+            if (__syncthreads_or(hist_p[threadIdx.x] == (unsigned)n)) continue;    // uniform over the grid: identity pass
+            for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x)               // tiles in increasing order: look-back never waits on a later one
+                os_pass_tile<HAS_VALS, RS_ROWS, false>(kin, vin, n, 8 * (pass0 + p), pass_id, hist_p, nullptr, (int)t, status, kout, vout);
+            rs_grid_barrier(barrier_word, ++syncs * gridDim.x);
+            unsigned long long *tk = kin; kin = kout; kout = tk;
+            unsigned *tv = vin; vin = vout; vout = tv;
+            flipped = !flipped;
+        }
+        if (round == 1 || lazy_passes == 0) break;
+        for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_THREADS)
+            rs_repair_run<HAS_VALS>(kin, vin, n, 8 * (pass0 + lazy_passes), i, flag);
         rs_grid_barrier(barrier_word, ++syncs * gridDim.x);
-        unsigned long long *tk = kin; kin = kout; kout = tk;
-        unsigned *tv = vin; vin = vout; vout = tv;
-        flipped = !flipped;
+        if (*reinterpret_cast<volatile unsigned *>(flag) == 0u) break;             // the usual case: sorted
     }
     if (flipped) {                                         // bring the result back to the first buffer pair
         for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_THREADS) {
-            keys_a[i] = keys_b[i];
-            if (HAS_VALS) vals_a[i] = vals_b[i];
+            keys_a[i] = __ldcg(kin + i);
+            if (HAS_VALS) vals_a[i] = __ldcg(vin + i);
         }
     }
 }
@@ -335,15 +402,15 @@ os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsig
 inline size_t radix_sort_temp_bytes(size_t n)
 {
     const size_t ntiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
-    return (size_t)RS_MAX_PASSES * 256 * sizeof(unsigned) + 64 + ntiles * 256 * sizeof(unsigned long long);
+    return (size_t)(RS_MAX_PASSES * 256 + RS_MISC_WORDS) * sizeof(unsigned) + ntiles * 256 * sizeof(unsigned long long);
 }
 
-// tiles the all-passes kernel may be launched with (one CTA per tile, all co-resident); 0 disables it
-// (NBODY_SORT_COOP=0, or a device without cooperative launch)
-static inline int rs_coop_tile_limit(bool has_vals)
+// CTAs the all-passes kernel may be launched with (all co-resident; a CTA takes tiles blockIdx, blockIdx + grid, ...);
+// 0 disables it (NBODY_SORT_COOP=0, or a device without cooperative launch)
+static inline int rs_coop_cta_limit(bool has_vals, bool small)
 {
-    static int limit[2] = {-1, -1};
-    int &l = limit[has_vals ? 1 : 0];
+    static int limit[4] = {-1, -1, -1, -1};
+    int &l = limit[(has_vals ? 1 : 0) + (small ? 2 : 0)];
     if (l < 0) {
         l = 0;
         const char *env = getenv("NBODY_SORT_COOP");
@@ -351,9 +418,9 @@ static inline int rs_coop_tile_limit(bool has_vals)
         if (!(env && atoi(env) == 0) && cudaGetDevice(&dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
-            const cudaError_t e = has_vals ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, os_sort_all_kernel<true, RS_ROWS_SMALL>, RS_THREADS, 0)
-                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, os_sort_all_kernel<false, RS_ROWS_SMALL>, RS_THREADS, 0);
-            if (e == cudaSuccess) l = sms * per_sm;
+            const void *fn = has_vals ? (small ? (const void *)os_sort_all_kernel<true, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<true, RS_ROWS_LARGE>)
+                                      : (small ? (const void *)os_sort_all_kernel<false, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<false, RS_ROWS_LARGE>);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RS_THREADS, 0) == cudaSuccess) l = sms * per_sm;
             else cudaGetLastError();
         }
     }
@@ -364,19 +431,23 @@ static inline int rs_coop_tile_limit(bool has_vals)
 // `temp` holds radix_sort_temp_bytes(n).  begin_bit/end_bit (multiples of 8) restrict the passes when the caller
 // knows which key bits can differ.  With `n_dev` the number of live items is read from device memory by the kernels
 // (n is then only the bound the grids are sized for), so a producer's counter never has to travel to the host.
+// `lazy_low_bits` (multiple of 8, 0 = off): high digits first, the bits below it only through the run repair (see
+// RS_TIE_RUN_MAX above); honoured when the pass counts keep the ping-pong parity, silently a plain sort otherwise.
 // Fully asynchronous on `st` (graph-capturable).
 static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b,
                                   size_t n, void *temp, cudaStream_t st, int begin_bit = 0, int end_bit = 64, int *launches = nullptr,
-                                  const unsigned *n_dev = nullptr, bool hist_ready = false)
+                                  const unsigned *n_dev = nullptr, bool hist_ready = false, int lazy_low_bits = 0)
 {
     if (n == 0 || end_bit <= begin_bit) return cudaSuccess;
     const int pass0 = begin_bit / 8, npasses = (end_bit - begin_bit + 7) / 8;
     if (begin_bit % 8 || npasses > RS_MAX_PASSES) return cudaErrorInvalidValue;
+    static const bool lazy_off = getenv("NBODY_SORT_LAZY") && atoi(getenv("NBODY_SORT_LAZY")) == 0;
+    int lazy_passes = (lazy_low_bits > begin_bit && lazy_low_bits < end_bit && lazy_low_bits % 8 == 0 && !lazy_off) ? (lazy_low_bits - begin_bit) / 8 : 0;
     const bool small = n <= (size_t)RS_SMALL_TILE_MAX_N;
     const size_t tile = (size_t)RS_THREADS * (small ? RS_ROWS_SMALL : RS_ROWS_LARGE), ntiles = (n + tile - 1) / tile;
     unsigned *hist = (unsigned *)temp;                                    // [npasses][256]
-    unsigned *ticket = hist + RS_MAX_PASSES * 256;                        // [npasses]
-    unsigned long long *status = (unsigned long long *)((char *)temp + (size_t)RS_MAX_PASSES * 256 * sizeof(unsigned) + 64);
+    unsigned *misc = hist + RS_MAX_PASSES * 256;                          // tickets [2 x npasses], barrier word, tie-run flag
+    unsigned long long *status = (unsigned long long *)(misc + RS_MISC_WORDS);
     // hist_ready: the caller zeroed `temp` and the producer of the keys already accumulated the digit histograms
     // of these passes into it (rs_hist_add_key / rs_hist_flush): one memset, one kernel and one read of the keys less
     cudaError_t e = cudaSuccess;
@@ -384,30 +455,48 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
     size_t hgrid = (n + 8 * RS_THREADS - 1) / (8 * RS_THREADS);             // >= 8 keys per thread, at most 8 CTAs per SM
     if (hgrid > 148 * 8) hgrid = 148 * 8;
     if (!hist_ready) os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, n_dev, pass0, npasses, hist);
-    // small inputs: all passes in one cooperative kernel, one CTA per tile (every tile co-resident)
-    if (small && ntiles <= (size_t)rs_coop_tile_limit(vals_a != nullptr)) {
-        unsigned *barrier_word = ticket + 15;                               // zeroed with the rest of `temp`
-        void *args[] = {&keys_a, &keys_b, &vals_a, &vals_b, &n, &n_dev, (void *)&pass0, (void *)&npasses, &hist, &barrier_word, &status};
-        const void *fn = vals_a ? (const void *)os_sort_all_kernel<true, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<false, RS_ROWS_SMALL>;
-        if ((e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, st)) != cudaSuccess) return e;
+    // all passes in ONE cooperative kernel: every CTA co-resident, a grid-wide barrier between the passes; at small sizes one
+    // CTA per tile, beyond that each CTA takes every grid-th tile
+    const int coop_ctas = rs_coop_cta_limit(vals_a != nullptr, small);
+    if (coop_ctas > 0) {
+        void *args[] = {&keys_a, &keys_b, &vals_a, &vals_b, &n, &n_dev, (void *)&pass0, (void *)&npasses, &lazy_passes, &hist, &misc, &status};
+        const void *fn = vals_a ? (small ? (const void *)os_sort_all_kernel<true, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<true, RS_ROWS_LARGE>)
+                                : (small ? (const void *)os_sort_all_kernel<false, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<false, RS_ROWS_LARGE>);
+        const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)coop_ctas);
+        if ((e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RS_THREADS), args, 0, st)) != cudaSuccess) return e;
         if (launches) *launches += (hist_ready ? 0 : 1) + 1;
         return cudaGetLastError();
     }
+    // one launch per pass.  High digits first needs both pass counts even: the repair works in place in the first
+    // buffer pair, and the conditional full sort must bring the data back there as well
+    if (lazy_passes && (((npasses - lazy_passes) & 1) || (npasses & 1))) lazy_passes = 0;
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
-    for (int p = 0; p < npasses; ++p) {
-        const int shift = 8 * (pass0 + p);
+    unsigned pass_id = 0;
+    const unsigned *run_if = nullptr;
+    int nl = hist_ready ? 0 : 1;
+    for (int round = 0, first = lazy_passes; round < 2; ++round, first = 0) {
+        for (int p = first; p < npasses; ++p, ++pass_id, ++nl) {
+            const int shift = 8 * (pass0 + p);
 #define RS_LAUNCH(V, R)                                                                                                   \
-    os_pass_kernel<V, R><<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, vin, n, n_dev, shift, (unsigned)p, hist + p * 256, ticket + p, \
-                                                                  status, kout, vout)
-        if (vals_a) { if (small) RS_LAUNCH(true, RS_ROWS_SMALL); else RS_LAUNCH(true, RS_ROWS_LARGE); }
-        else        { if (small) RS_LAUNCH(false, RS_ROWS_SMALL); else RS_LAUNCH(false, RS_ROWS_LARGE); }
+    os_pass_kernel<V, R><<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, vin, n, n_dev, shift, pass_id, hist + p * 256, misc + pass_id, \
+                                                                  status, kout, vout, run_if)
+            if (vals_a) { if (small) RS_LAUNCH(true, RS_ROWS_SMALL); else RS_LAUNCH(true, RS_ROWS_LARGE); }
+            else        { if (small) RS_LAUNCH(false, RS_ROWS_SMALL); else RS_LAUNCH(false, RS_ROWS_LARGE); }
 #undef RS_LAUNCH
-        unsigned long long *tk = kin; kin = kout; kout = tk;
-        unsigned *tv = vin; vin = vout; vout = tv;
+            unsigned long long *tk = kin; kin = kout; kout = tk;
+            unsigned *tv = vin; vin = vout; vout = tv;
+        }
+        if (round == 1 || lazy_passes == 0) break;
+        size_t rgrid = (n + RS_THREADS - 1) / RS_THREADS;
+        if (rgrid > 148 * 8) rgrid = 148 * 8;
+        if (vals_a) os_repair_kernel<true><<<(unsigned)rgrid, RS_THREADS, 0, st>>>(keys_a, vals_a, n, n_dev, 8 * (pass0 + lazy_passes), misc + RS_MISC_FLAG);
+        else os_repair_kernel<false><<<(unsigned)rgrid, RS_THREADS, 0, st>>>(keys_a, vals_a, n, n_dev, 8 * (pass0 + lazy_passes), misc + RS_MISC_FLAG);
+        ++nl;
+        run_if = misc + RS_MISC_FLAG;                                       // the passes of the second round run only if a run was too long
     }
-    if (launches) *launches += (hist_ready ? 0 : 1) + npasses;
-    if (npasses & 1) {   // odd number of passes: bring the result back to the first buffer
+    if (launches) *launches += nl;
+    if (!lazy_passes && (npasses & 1)) {   // odd number of passes: bring the result back to the first buffer
         if ((e = cudaMemcpyAsync(keys_a, keys_b, n * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
         if (vals_a && (e = cudaMemcpyAsync(vals_a, vals_b, n * 4, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
     }

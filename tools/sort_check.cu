@@ -12,7 +12,7 @@
 using namespace nb;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(2); } } while (0)
 
-static int run_case(size_t n, int mode, bool with_vals)
+static int run_case(size_t n, int mode, bool with_vals, int lazy = 0)
 {
     std::mt19937_64 rng(n * 7 + mode);
     std::vector<unsigned long long> k(n);
@@ -21,6 +21,9 @@ static int run_case(size_t n, int mode, bool with_vals)
         if (mode == 1) x &= 0xffull;                    // heavy duplicates: stability matters
         if (mode == 2) x = (x & 0xffffull) << 40;       // only the middle bits differ
         if (mode == 3) x = (unsigned long long)(long long)(int)(x & 0xffffffffu);   // sign-extended 32-bit hashes
+        if (mode == 4) x &= 0x0000ffffffffffffull;      // 16 random high bits above bit 32: short tie runs for the repair
+        if (mode == 5) x = ((x >> 20) & 0x3fffull) << 32 | (x & 3ull);   // short runs with identical full keys: stability
+        if (mode == 6) x = ((x >> 20) & 0x7ffull) << 32 | (x & 0xffffffffull);   // runs around the repair's limit: some fall back
     }
     std::vector<unsigned> v(n);
     std::iota(v.begin(), v.end(), 0u);
@@ -36,7 +39,7 @@ static int run_case(size_t n, int mode, bool with_vals)
     for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up; best of the rest
         CK(cudaMemcpy(ka, k.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(va, v.data(), n * 4, cudaMemcpyHostToDevice));
         CK(cudaEventRecord(e0));
-        CK(radix_sort_u64(ka, kb, with_vals ? va : nullptr, vb, n, tmp, 0));
+        CK(radix_sort_u64(ka, kb, with_vals ? va : nullptr, vb, n, tmp, 0, 0, 64, nullptr, nullptr, false, lazy));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float t; CK(cudaEventElapsedTime(&t, e0, e1));
         if (rep > 0 && t < ms) ms = t;
@@ -65,7 +68,7 @@ static int run_case(size_t n, int mode, bool with_vals)
         }
         cudaFree(ct);
     }
-    printf("n=%9zu mode=%d vals=%d : %s   own %.3f ms   cub %.3f ms\n", n, mode, (int)with_vals, bad ? "MISMATCH" : "ok", ms, cms);
+    printf("n=%9zu mode=%d vals=%d lazy=%2d : %s   own %.3f ms   cub %.3f ms\n", n, mode, (int)with_vals, lazy, bad ? "MISMATCH" : "ok", ms, cms);
     cudaFree(ka); cudaFree(kb); cudaFree(va); cudaFree(vb); cudaFree(tmp);
     return bad;
 }
@@ -111,11 +114,20 @@ int main(int argc, char **argv)
 {
     int bad = 0;
     if (argc > 1) {   // single case: sort_check N [mode] [with_vals]
-        bad = run_case(strtoull(argv[1], nullptr, 10), argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atoi(argv[3]) != 0 : true);
+        bad = run_case(strtoull(argv[1], nullptr, 10), argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atoi(argv[3]) != 0 : true, argc > 4 ? atoi(argv[4]) : 0);
         return bad ? 1 : 0;
     }
     for (size_t n : {1ul, 2ul, 31ul, 33ul, 511ul, 4096ul, 4097ul, 25000ul, 100003ul, 1000000ul, 4194304ul})
         for (int mode = 0; mode < 4; ++mode) bad += run_case(n, mode, true);
+    // high digits first + run repair (lazy_low_bits): few ties, stability inside runs, runs beyond the limit (full sort after all)
+    for (size_t n : {2ul, 33ul, 4097ul, 25000ul, 100003ul, 1000000ul, 10000000ul})
+        for (int mode : {0, 1, 2, 4, 5, 6}) bad += run_case(n, mode, true, 32);
+    bad += run_case(25000, 4, false, 32);
+    bad += run_case(1000000, 6, false, 32);
+    bad += run_case(25000, 0, true, 16);
+    bad += run_case(4194304, 0, true, 16);
+    bad += run_case(25000, 0, true, 24);      // odd pass counts: falls back to the plain sort in the launch-per-pass form
+    bad += run_case(9000000, 0, true, 24);
     bad += run_case(77777, 0, false);
     bad += run_case(1000000, 3, false);
     bad += run_case(1000000, 0, false);
