@@ -372,19 +372,25 @@ bh_propagate_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, 
 // child of its parent; bh_climb_kernel then runs the arrival protocol of bh_propagate_kernel from there.
 // The length criterion is one both sides can evaluate: the parent's owner sees its whole window, a child finds the
 // owner by the gallop-and-bisect of bh_emit_kernel and the span's end by following its siblings.
-constexpr int BHL_MAIN = 256, BHL_HALO = 256, BHL_THREADS = BHL_MAIN + BHL_HALO;
-
-template <int DIMS>
-__global__ void __launch_bounds__(BHL_THREADS)
+template <int DIMS, bool TRACE, int BHL_MAIN, int BHL_HALO>
+__global__ void __launch_bounds__(BHL_MAIN + BHL_HALO)
 bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *__restrict__ keys,
                      const unsigned *__restrict__ idx, size_t n, const BhRoot *__restrict__ root,
                      const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
                      const unsigned char *__restrict__ first, const unsigned char *__restrict__ leaf,
-                     BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap, unsigned *status, unsigned *__restrict__ gstart)
+                     BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap, unsigned *status, unsigned *__restrict__ gstart,
+                     unsigned long long *trace)
 {
+    // tuning aid (NBODY_BH_TRACE): per phase, the largest number of SM cycles any thread needed to get there
+    const long long trace_t0 = TRACE ? clock64() : 0;
+    int trace_k = 0;
+#define BHL_TRACE() do { if (TRACE) { const unsigned am = __activemask();                                                          \
+                                      const unsigned cyc = __reduce_max_sync(am, (unsigned)(clock64() - trace_t0));                  \
+                                      if ((threadIdx.x & 31) == (unsigned)(__ffs(am) - 1)) atomicMax(trace + trace_k, (unsigned long long)cyc); \
+                                      ++trace_k; } } while (0)
     constexpr int BITS = BhT<DIMS>::BITS;
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
-    constexpr int M = BHL_MAIN, H = BHL_HALO, W = BHL_THREADS;
+    constexpr int M = BHL_MAIN, H = BHL_HALO, W = BHL_MAIN + BHL_HALO;
     constexpr unsigned short NOT_LOCAL = 0xffffu;
     __shared__ int sA[W + 1];                 // levels shared with the previous sorted body (-1: none); [W] = the body after the window
     __shared__ unsigned soffs[W + 1];         // first cell of every body of the window
@@ -427,7 +433,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
         tp = (unsigned)min(t - s0, (size_t)W + 1);
     }
     __syncthreads();
-    if (cnt) atomicMax(&s_maxd, leafd);
+    BHL_TRACE();   // 0: loads
 
     // ---- skeleton of the cells this body owns (top-down: the fp32 quad recursion), leaf record complete
     if (cnt && main_thread) {
@@ -456,11 +462,15 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
         }
     }
 
-    // ---- centres of mass of the local cells, deepest level first
+    BHL_TRACE();   // 1: skeleton
+    // ---- centres of mass of the local cells, deepest level first (one CTA barrier per level)
+    // (Tried: letting every thread climb as far as its children are published, rounds instead of levels -- same time: the
+    //  loop is bound by the instructions all warps issue per step, not by the barriers.)
     auto span_ok = [&](unsigned t) { return t <= (unsigned)W && t - i <= (unsigned)H; };
     bool alive = cnt != 0 && span_ok(tp);     // false: this chain continues in the climb (or the body owns nothing)
     int dcur = leafd;
     if (alive && firstd == leafd) { sval[i] = make_float4(cx_, cy_, cz_, cm_); send[i] = (unsigned short)tp; }
+    if (cnt) atomicMax(&s_maxd, leafd);
     __syncthreads();
     for (int d = s_maxd - 1; d >= 0; --d) {
         if (alive && d >= firstd && d < leafd) {              // the cell at depth d of this chain; `cur` is its first child
@@ -469,21 +479,28 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
             py = __fadd_rn(py, __fmul_rn(cy_, cm_));
             if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(cz_, cm_));
             ms = __fadd_rn(ms, cm_);
-            unsigned t = tp;
+            unsigned t = tp, kids[NCHILD - 1];
+            int nk = 0;
             bool ok = true;
-            while (t <= (unsigned)W && sA[t] == d) {          // the following children: first cells of later threads, in key order
-                const unsigned short e = (t < (unsigned)W) ? send[t] : NOT_LOCAL;
-                if (e == NOT_LOCAL) { ok = false; break; }
-                const float4 ch = sval[t];
-                px = __fadd_rn(px, __fmul_rn(ch.x, ch.w));
-                py = __fadd_rn(py, __fmul_rn(ch.y, ch.w));
-                if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch.z, ch.w));
-                ms = __fadd_rn(ms, ch.w);
-                t = e;
+#pragma unroll
+            for (int c = 0; c < (int)NCHILD - 1; ++c) {        // the following children: first cells of later threads, in key order
+                if (ok && t <= (unsigned)W && sA[t] == d) {
+                    const unsigned short e = (t < (unsigned)W) ? send[t] : NOT_LOCAL;
+                    if (e == NOT_LOCAL) ok = false;
+                    else {
+                        const float4 ch = sval[t];
+                        px = __fadd_rn(px, __fmul_rn(ch.x, ch.w));
+                        py = __fadd_rn(py, __fmul_rn(ch.y, ch.w));
+                        if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch.z, ch.w));
+                        ms = __fadd_rn(ms, ch.w);
+                        kids[c] = t; nk = c + 1;
+                        t = e;
+                    }
+                }
             }
-            ok = ok && span_ok(t);
-            if (ok) {
-                for (unsigned u = tp; u < t; u = send[u]) spulled[u] = 1;
+            if (ok && span_ok(t)) {
+#pragma unroll
+                for (int c = 0; c < (int)NCHILD - 1; ++c) if (c < nk) spulled[kids[c]] = 1;
                 if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
                     const float inv = __fdiv_rn(1.0f, ms);
                     px = __fmul_rn(px, inv);
@@ -506,6 +523,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
     }
     __syncthreads();
 
+    BHL_TRACE();   // 2: local levels
     // ---- hand-over to the climb: count every cell that the local part did not attach to its parent as a child of that parent
     if (!(cnt && main_thread)) return;
     unsigned start = 0xffffffffu;
@@ -516,21 +534,11 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
     }
     if (dcur > firstd) start = off + (unsigned)(dcur - firstd);
     if (firstd > 0 && !(dcur == firstd && spulled[i])) {
-        // owner of the parent cell (depth firstd - 1): the first sorted body with that prefix -- gallop backwards, then bisect
         const int shp = 64 - BITS * (firstd - 1);
         const unsigned long long pp = k >> shp;
-        size_t lo = 0, hi = s, step = 1;
-        while (lo < hi) {
-            const size_t probe = (hi >= lo + step) ? hi - step : lo;
-            if ((keys[probe] >> shp) < pp) { lo = probe + 1; break; }
-            hi = probe;
-            step <<= 1;
-        }
-        while (lo < hi) {
-            const size_t mid = (lo + hi) >> 1;
-            if ((keys[mid] >> shp) >= pp) hi = mid; else lo = mid + 1;
-        }
-        // is the parent local to ITS owner's CTA?  Only if this cell is local and the parent's span (owner .. end of my last sibling) is short
+        // Is the parent local to ITS owner's CTA (then that CTA's halo threads redid this cell and added it there)?  Only if
+        // this cell is local and the parent's span -- its owner .. the end of my last sibling -- is at most H bodies long:
+        // the body H + 1 places before the span's end must lie outside the parent (ONE key; no search for the owner)
         bool parent_local = false;
         if (dcur == firstd && alive) {
             unsigned t = tp;
@@ -540,9 +548,24 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
                 if (e == NOT_LOCAL) { ok = false; break; }
                 t = e;
             }
-            parent_local = ok && t <= (unsigned)W && (s0 + t) - lo <= (size_t)H;
+            if (ok && t <= (unsigned)W) {
+                const size_t e = s0 + t;
+                parent_local = e <= (size_t)H || (keys[e - H - 1] >> shp) != pp;
+            }
         }
         if (!parent_local) {
+            // owner of the parent cell: the first sorted body with that prefix -- gallop backwards, then bisect
+            size_t lo = 0, hi = s, step = 1;
+            while (lo < hi) {
+                const size_t probe = (hi >= lo + step) ? hi - step : lo;
+                if ((keys[probe] >> shp) < pp) { lo = probe + 1; break; }
+                hi = probe;
+                step <<= 1;
+            }
+            while (lo < hi) {
+                const size_t mid = (lo + hi) >> 1;
+                if ((keys[mid] >> shp) >= pp) hi = mid; else lo = mid + 1;
+            }
             const unsigned par = offs[lo] + (unsigned)(firstd - 1 - (int)first[lo]);
             if (off < cap) reinterpret_cast<unsigned *>(nodes.aux(off))[3] = par;
             if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + ((unsigned)(k >> (64 - BITS * firstd)) & (NCHILD - 1u)))));
@@ -550,6 +573,8 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
         }
     }
     gstart[s] = start;
+    BHL_TRACE();   // 3: hand-over
+#undef BHL_TRACE
 }
 
 // The climb over the cells the local kernel left: bh_propagate_kernel's protocol, started from `gstart` instead of the leaves.
@@ -1027,7 +1052,9 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
     // NEXT node is requested as soon as the opening test has chosen it, and the force arithmetic of the current node
     // (the Quake rsqrt chain) runs while that load is in flight.  Same visits, same operations, same order of additions
     // as Quadtree::acc.  (Measured and dropped, profiles/r2_walk_experiments.txt: prefetching the following records
-    // into L1, and requesting BOTH possible successors before the test -- neither shortens the chain.)
+    // into L1, requesting BOTH possible successors before the test, and thin warps -- 16 / 8 / 4 targets per warp so that
+    // every scheduler has several warps: none shortens the chain, whose length is the LONGEST walk of the scene, 173
+    // visits of ~450 cycles on the shipped scene, tools/bh_walk_stats.py.)
     unsigned i = 0, nvis = 0;
     float4 nd;
     uint4 na;
@@ -1206,10 +1233,28 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     // round-1/2 pair emit + climb-from-the-leaves (NBODY_BH_LOCAL=0; bit-identical trees, kept for comparison)
     static const bool local_off = getenv("NBODY_BH_LOCAL") && atoi(getenv("NBODY_BH_LOCAL")) == 0;
     if (!local_off) {
-        bh_emit_local_kernel<DIMS><<<(unsigned)((n + BHL_MAIN - 1) / BHL_MAIN), BHL_THREADS, 0, st>>>(
-            posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,
-            (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive,
-            w.node_cap, w.status, (unsigned *)w.climb_start);
+        static const bool want_trace = getenv("NBODY_BH_TRACE") != nullptr;
+        static const int geom = getenv("NBODY_BHL_GEOM") ? atoi(getenv("NBODY_BHL_GEOM")) : 0;   // tuning: bodies per CTA / halo
+#define BHL_ARGS posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,      \
+                 (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, \
+                 w.node_cap, w.status, (unsigned *)w.climb_start
+#define BHL_LAUNCH(T, M, H, TR) bh_emit_local_kernel<DIMS, T, M, H><<<(unsigned)((n + (M) - 1) / (M)), (M) + (H), 0, st>>>(BHL_ARGS, TR)
+        if (want_trace) {
+            if (!w.trace && cudaMalloc(&w.trace, 64 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+            cudaMemsetAsync(w.trace, 0, 64 * sizeof(long long), st);
+            BHL_LAUNCH(true, 256, 128, (unsigned long long *)w.trace);
+            unsigned long long h[4];
+            if (cudaMemcpyAsync(h, w.trace, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess)
+                fprintf(stderr, "[emit_local n=%zu] max cycles to the end of: loads %llu, skeleton %llu, local levels %llu, hand-over %llu\n", n, h[0], h[1], h[2], h[3]);
+        } else if (geom == 1) BHL_LAUNCH(false, 128, 128, nullptr);
+        else if (geom == 2) BHL_LAUNCH(false, 64, 64, nullptr);
+        else if (geom == 3) BHL_LAUNCH(false, 128, 256, nullptr);
+        else if (geom == 5) BHL_LAUNCH(false, 64, 192, nullptr);
+        else if (geom == 6) BHL_LAUNCH(false, 512, 512, nullptr);
+        else if (geom == 7) BHL_LAUNCH(false, 256, 256, nullptr);
+        else BHL_LAUNCH(false, 256, 128, nullptr);           // sweep on B200 (profiles/): best at 1M and 4M bodies, no difference at 25,000
+#undef BHL_LAUNCH
+#undef BHL_ARGS
         bh_climb_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
                                                     (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap);
     } else {

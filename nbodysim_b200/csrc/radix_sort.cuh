@@ -35,12 +35,14 @@ constexpr int RS_MAX_PASSES = 8;
 // scratch layout: [RS_MAX_PASSES][256] digit histograms | RS_MISC_WORDS words (tickets of up to 2 x RS_MAX_PASSES pass
 // launches, the grid-barrier word, the "tie runs too long" flag) | status words
 constexpr int RS_MISC_WORDS = 64, RS_MISC_BARRIER = 2 * RS_MAX_PASSES, RS_MISC_FLAG = 2 * RS_MAX_PASSES + 1;
+constexpr int RS_MISC_STAMPS = 20, RS_MISC_NSTAMPS = (RS_MISC_WORDS - RS_MISC_STAMPS) / 2;   // 64-bit time stamps of the all-passes kernel
 // HIGH DIGITS FIRST (`lazy_low_bits` = L > 0).  Quadrant-path keys of distinct bodies almost always differ within their
 // leading bits; the low digits only order the few bodies that share a deep cell.  So: LSD passes over the digits at and
 // above bit L only, then ONE in-place repair: the first key of every run of keys that agree above bit L insertion-sorts
-// its run by the full key (stable; runs are 2-3 keys in practice).  A run longer than RS_TIE_RUN_MAX raises a flag and
+// its run by the full key (stable; runs are 2-3 keys in practice; one thread, ~1 us per element moved, so the limit is
+// small).  A run longer than RS_TIE_RUN_MAX raises a flag and
 // the full sort over all digits runs after all (same result: LSD passes are stable whatever order they start from).
-constexpr int RS_TIE_RUN_MAX = 16;
+constexpr int RS_TIE_RUN_MAX = 6;
 
 __device__ __forceinline__ unsigned rs_digit(unsigned long long k, int shift) { return (unsigned)(k >> shift) & 255u; }
 
@@ -130,11 +132,50 @@ constexpr int RS_LOOKBACK_WINDOW = 4;                     // predecessors' statu
 // One tile of one digit pass (the body of both kernels below).  `tile` < 0: take the next tile by ticket.  IDENTITY_COPY:
 // a digit on which all keys agree makes the pass a plain copy (the launch-per-pass form keeps its ping-pong fixed);
 // the all-passes kernel tests that itself and skips such a pass altogether.
+// keys of digit `tid` in all tiles before `tile` (> 0): walk back over the tiles' status words, WINDOW at a time
+template <int WINDOW>
+__device__ __forceinline__ unsigned rs_lookback(const unsigned long long *status, unsigned tile, int tid, unsigned pass)
+{
+    unsigned excl = 0;
+    long long t = (long long)tile - 1;
+    bool done = false;
+    while (!done) {
+        unsigned long long v[WINDOW];
+#pragma unroll
+        for (int j = 0; j < WINDOW; ++j) {
+            const long long tj = t - j > 0 ? t - j : 0;
+            v[j] = rs_ld_status(status + (size_t)tj * 256 + tid);
+        }
+#pragma unroll
+        for (int j = 0; j < WINDOW; ++j) {
+            if (done) break;
+            const long long tj = t - j > 0 ? t - j : 0;
+            unsigned vt = (unsigned)(v[j] >> 32);
+            while ((vt >> 1) != pass + 1u) {                               // not published yet: poll again
+                v[j] = rs_ld_status(status + (size_t)tj * 256 + tid);
+                vt = (unsigned)(v[j] >> 32);
+            }
+            excl += (unsigned)v[j];
+            done = (vt & 1u) != 0u;                                        // an inclusive prefix ends the walk
+        }
+        t -= WINDOW;
+    }
+    return excl;
+}
+
+#ifdef RS_FINE_TRACE   // tools only: the LAST CTA stamps the global timer inside a pass (fine_stamps[] in global memory)
+__device__ unsigned long long rs_fine_stamps[64];
+__device__ int rs_fine_k;
+#define RS_FINE() do { if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && rs_fine_k < 64) { unsigned long long t_; \
+                       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); rs_fine_stamps[rs_fine_k++] = t_; } } while (0)
+#else
+#define RS_FINE() do { } while (0)
+#endif
 template <bool HAS_VALS, int RS_ROWS, bool IDENTITY_COPY>
 __device__ __forceinline__ void
 os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, size_t n, int shift, unsigned pass,
              const unsigned *__restrict__ hist_p, unsigned *__restrict__ ticket, int fixed_tile, unsigned long long *status,
-             unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out)
+             unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out, bool lb_wide = false)
 {
     constexpr int RS_ITEMS = RS_ROWS, RS_CHUNK = 32 * RS_ROWS, RS_TILE = RS_THREADS * RS_ROWS;
     __shared__ unsigned long long skeys[RS_TILE];        // the tile in digit order; reused for the values afterwards
@@ -146,6 +187,7 @@ os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__rest
     __shared__ unsigned s_tile;
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    RS_FINE();   // 0: start
     __syncthreads();                                      // a previous tile / pass of this CTA may still read the shared arrays
     if (tid == 0) s_tile = fixed_tile >= 0 ? (unsigned)fixed_tile : atomicAdd(ticket, 1u);
 #pragma unroll
@@ -180,22 +222,37 @@ os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__rest
         k[r] = (i < cnt) ? keys[tile0 + i] : ~0ull;
         if (EARLY_VALS) v[r] = (i < cnt) ? vals[tile0 + i] : 0u;
     }
-    // A group of lanes holding the same digit is ranked by ONE shared-memory atomic of its first lane (the
-    // atomics of a warp on one counter execute in program order, i.e. row order); no barrier between rows, so the
-    // matches, atomics and shuffles of all rows overlap.
+    // A group of lanes holding the same digit is ranked by its first lane, which advances the warp's counter of that
+    // digit; rows in program order => stable.
+#ifdef RS_FINE_TRACE
+    if (__syncthreads_or(k[RS_ROWS - 1] == 1ull && v[0] == 7u)) return;       // tools only: all loads have landed
+    RS_FINE();   // 0a: keys (and values) loaded
+#endif
 #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) {
         const unsigned i = (unsigned)w * RS_CHUNK + (unsigned)r * 32 + lane;
         const bool valid = i < cnt;
-        const unsigned d = valid ? rs_digit(k[r], shift) : 256u + lane;       // invalid lanes match nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned d = valid ? rs_digit(k[r], shift) : 0u;
+        // lanes holding the same digit: eight ballots, one per digit bit (measured on B200: __match_any_sync on 32 mostly
+        // distinct digits costs ~600 cycles per row, this ~60; profiles/r2_sort_pass_trace.txt)
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        }
+        if (!valid) peers = 1u << lane;                                       // invalid lanes match nobody
         const int leader = __ffs(peers) - 1;
         unsigned base = 0;
-        if (valid && lane == leader) base = atomicAdd(&counts[w][d], (unsigned)__popc(peers));
+        // the warp owns its row of counters and a digit has ONE leader per row: a plain read-modify-write, ordered across
+        // the rows (whose leaders for a digit may be different lanes) by __syncwarp -- no shared-memory atomic
+        if (valid && lane == leader) { base = counts[w][d]; counts[w][d] = base + (unsigned)__popc(peers); }
+        __syncwarp();
         base = __shfl_sync(0xffffffffu, base, leader);
         rank[r] = base + __popc(peers & ((1u << lane) - 1u));
     }
     __syncthreads();
+    RS_FINE();   // 1: keys loaded and ranked
 
     // ---- thread d: digit d's count in this tile, bases of the warps inside the digit
     unsigned total = 0;
@@ -209,39 +266,19 @@ os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__rest
     const unsigned gstart = rs_block_excl_scan(hist_p[tid], warp_sums);        // start of digit d in the whole output
     dig_excl[tid] = dexcl;
 
+    RS_FINE();   // 2: published, scans done
     // ---- decoupled look-back: keys of digit d in all earlier tiles
     // The walk goes tile-1, tile-2, ... adding aggregates until it meets an inclusive prefix (tile 0 always
     // publishes one).  Each step is an L2 round trip, so RS_LOOKBACK_WINDOW predecessors are fetched at once
     // and consumed in order; a word that is not published yet is polled again.
     unsigned excl = 0;
     if (tile > 0) {
-        long long t = (long long)tile - 1;
-        bool done = false;
-        while (!done) {
-            unsigned long long v[RS_LOOKBACK_WINDOW];
-#pragma unroll
-            for (int j = 0; j < RS_LOOKBACK_WINDOW; ++j) {
-                const long long tj = t - j > 0 ? t - j : 0;
-                v[j] = rs_ld_status(status + (size_t)tj * 256 + tid);
-            }
-#pragma unroll
-            for (int j = 0; j < RS_LOOKBACK_WINDOW; ++j) {
-                if (done) break;
-                const long long tj = t - j > 0 ? t - j : 0;
-                unsigned vt = (unsigned)(v[j] >> 32);
-                while ((vt >> 1) != pass + 1u) {                               // not published yet: poll again
-                    v[j] = rs_ld_status(status + (size_t)tj * 256 + tid);
-                    vt = (unsigned)(v[j] >> 32);
-                }
-                excl += (unsigned)v[j];
-                done = (vt & 1u) != 0u;                                        // an inclusive prefix ends the walk
-            }
-            t -= RS_LOOKBACK_WINDOW;
-        }
+        excl = lb_wide ? rs_lookback<16>(status, tile, tid, pass) : rs_lookback<RS_LOOKBACK_WINDOW>(status, tile, tid, pass);
         rs_st_status(status + sidx, rs_pack(tag + 1u, excl + total));
     }
     gbase[tid] = gstart + excl - dexcl;
     __syncthreads();
+    RS_FINE();   // 3: look-back done
 
     // ---- permute the keys into digit order in shared memory
     unsigned pos[RS_ROWS];
@@ -269,6 +306,7 @@ os_pass_tile(const unsigned long long *__restrict__ keys, const unsigned *__rest
             keys_out[dst[j]] = key;
         }
     }
+    RS_FINE();   // 4: keys permuted and stored
     if (HAS_VALS) {      // the same permutation for the values, through the same shared-memory buffer
         __syncthreads();
 #pragma unroll
@@ -360,27 +398,51 @@ __device__ __forceinline__ void rs_grid_barrier(unsigned *counter, unsigned targ
 }
 
 template <bool HAS_VALS, int RS_ROWS>
-static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 4 : 3))
+static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 2 : 3))
 os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b, size_t n,
                    const unsigned *__restrict__ n_dev, int pass0, int npasses, int lazy_passes, const unsigned *__restrict__ hist,
                    unsigned *__restrict__ misc, unsigned long long *status)
 {
     if (n_dev) n = (*n_dev < n) ? *n_dev : n;
     unsigned *barrier_word = misc + RS_MISC_BARRIER, *flag = misc + RS_MISC_FLAG;
+    // tuning aid: CTA 0 leaves the global timer (ns) at the start, after every pass / the repair, and at the end in the
+    // spare scratch words (read by tools/sort_check.cu --trace); a handful of instructions of one thread
+    unsigned long long *stamps = reinterpret_cast<unsigned long long *>(misc + RS_MISC_STAMPS);
+    int stamp_k = 0;
+#define RS_STAMP() do { if (blockIdx.x == 0 && threadIdx.x == 0 && stamp_k < RS_MISC_NSTAMPS) { unsigned long long t_;                \
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[stamp_k++] = t_; } } while (0)
+    RS_STAMP();
     unsigned long long *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
     unsigned syncs = 0, pass_id = 0;
     bool flipped = false;
     const size_t ntiles = (n + (size_t)RS_THREADS * RS_ROWS - 1) / ((size_t)RS_THREADS * RS_ROWS);
+    // digits on which all keys agree (identity passes), for all passes at once: one round trip instead of one per pass
+    __shared__ unsigned s_skip;
+    if (threadIdx.x == 0) s_skip = 0;
+    __syncthreads();
+    {
+        unsigned m = 0;
+        for (int p = 0; p < npasses; ++p) m |= (hist[p * 256 + threadIdx.x] == (unsigned)n) ? (1u << p) : 0u;
+        if (m) atomicOr(&s_skip, m);
+    }
+    __syncthreads();
+    const unsigned skip = s_skip;
+    // one CTA per tile: all tiles start a pass together, nobody finds an inclusive prefix early and the look-back runs
+    // all the way to tile 0 -- fetch 16 predecessors per round trip instead of 4
+    const bool wide = ntiles <= gridDim.x && ntiles <= 64;
     // lazy_passes > 0: only the digits from `lazy_passes` upwards first, then the repair, then -- if a tie run was too
     // long -- every digit after all
     for (int round = 0, first = lazy_passes; round < 2; ++round, first = 0) {
         for (int p = first; p < npasses; ++p, ++pass_id) {
             const unsigned *hist_p = hist + p * 256;
-            if (__syncthreads_or(hist_p[threadIdx.x] == (unsigned)n)) continue;    // uniform over the grid: identity pass
+            if ((skip >> p) & 1u) continue;                                        // uniform over the grid: identity pass
             for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x)               // tiles in increasing order: look-back never waits on a later one
-                os_pass_tile<HAS_VALS, RS_ROWS, false>(kin, vin, n, 8 * (pass0 + p), pass_id, hist_p, nullptr, (int)t, status, kout, vout);
+                os_pass_tile<HAS_VALS, RS_ROWS, false>(kin, vin, n, 8 * (pass0 + p), pass_id, hist_p, nullptr, (int)t, status, kout, vout, wide);
+            RS_FINE();   // 5: values stored
             rs_grid_barrier(barrier_word, ++syncs * gridDim.x);
+            RS_FINE();   // 6: grid barrier passed
+            RS_STAMP();
             unsigned long long *tk = kin; kin = kout; kout = tk;
             unsigned *tv = vin; vin = vout; vout = tv;
             flipped = !flipped;
@@ -389,6 +451,7 @@ os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsig
         for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_THREADS)
             rs_repair_run<HAS_VALS>(kin, vin, n, 8 * (pass0 + lazy_passes), i, flag);
         rs_grid_barrier(barrier_word, ++syncs * gridDim.x);
+        RS_STAMP();
         if (*reinterpret_cast<volatile unsigned *>(flag) == 0u) break;             // the usual case: sorted
     }
     if (flipped) {                                         // bring the result back to the first buffer pair
@@ -397,6 +460,8 @@ os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsig
             if (HAS_VALS) vals_a[i] = __ldcg(vin + i);
         }
     }
+    RS_STAMP();
+#undef RS_STAMP
 }
 
 inline size_t radix_sort_temp_bytes(size_t n)

@@ -44,6 +44,22 @@ static int run_case(size_t n, int mode, bool with_vals, int lazy = 0)
         float t; CK(cudaEventElapsedTime(&t, e0, e1));
         if (rep > 0 && t < ms) ms = t;
     }
+#ifdef RS_FINE_TRACE
+    {
+        unsigned long long st[64]; int kk = 0;
+        CK(cudaMemcpyFromSymbol(st, rs_fine_stamps, sizeof st)); CK(cudaMemcpyFromSymbol(&kk, rs_fine_k, sizeof kk));
+        printf("  fine trace of the last CTA, first repetition (us, per stamp):");
+        for (int q = 1; q < kk && q < 64; ++q) printf("%s %.2f", (q % 8 == 0) ? " |" : "", (double)(st[q] - st[q - 1]) * 1e-3);
+        printf("\n");
+    }
+#endif
+    if (getenv("SORT_TRACE")) {   // time stamps the all-passes kernel left in its scratch (last repetition)
+        unsigned long long st[RS_MISC_NSTAMPS];
+        CK(cudaMemcpy(st, (char *)tmp + (RS_MAX_PASSES * 256 + RS_MISC_STAMPS) * 4, sizeof st, cudaMemcpyDeviceToHost));
+        printf("  trace (us since kernel start):");
+        for (int q = 1; q < RS_MISC_NSTAMPS && st[q]; ++q) printf(" %.2f", (double)(st[q] - st[0]) * 1e-3);
+        printf("\n");
+    }
     std::vector<unsigned long long> ko(n); std::vector<unsigned> vo(n);
     CK(cudaMemcpy(ko.data(), ka, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(vo.data(), va, n * 4, cudaMemcpyDeviceToHost));
     int bad = 0;
