@@ -186,6 +186,8 @@ ColArgs CollideWorkspace::args(float *posm, float *vel, size_t n) const
     a.hot = (unsigned char *)hot; a.parent = (unsigned *)parent; a.counters = (unsigned *)counters;
     a.status = status;
     a.gate = (const unsigned *)grid;       // flags[0] of the screening
+    static const float strip_env = getenv("NBODY_COL_STRIP") ? (float)atof(getenv("NBODY_COL_STRIP")) : COL_STRIP;   // tuning
+    a.strip = strip_env;
     int idx_bits = 1;
     while (((size_t)1 << idx_bits) < n) ++idx_bits;
     a.idx_bits = idx_bits;

@@ -32,6 +32,7 @@ struct ColArgs {
     unsigned *status;                      // host-visible sticky flags ([1] = collision buffers overflowed), may be null
     const unsigned *gate;                  // screening result ([0] = pairs sharing a cell that overlap now); 0 there: nothing to do
     int idx_bits, rooted;
+    float strip;                           // width of the x strips the screening grid splits a cell into (0: none)
 };
 
 __device__ __forceinline__ unsigned long long col_hash(int x, int y)
@@ -81,58 +82,128 @@ __device__ __forceinline__ bool col_cell_range(const ColBody &b, int &minX, int 
     return cells > 0 && cells <= 4096;
 }
 
+// A cell's list is split by x STRIPS of COL_STRIP units (the reference's cells are 600 wide and the shipped scene packs 56
+// bodies into its busiest cell: a list is a chain of dependent loads, and the pair kernel's time is the longest chain).  A body
+// is entered under (cell, strip) for every strip its x interval touches; two bodies whose x intervals overlap -- the only
+// ones the sweep pairs up -- both touch the strip in which the overlap STARTS, and that is where the pair is taken, once
+// per shared cell as before.  Bodies of different strips cannot form a sweep pair, so nothing is lost.
+constexpr float COL_STRIP = 37.5f;
+__device__ __forceinline__ int col_strip_of(float x, float strip) { return strip > 0.f ? __float2int_rd(__fdiv_rn(x, strip)) : 0; }
+__device__ __forceinline__ unsigned long long col_table_key(int x, int y, int strip)
+{
+    return ((unsigned long long)((unsigned)strip & 0x7fffffffu) << 33) | (1ull << 32) | (unsigned)col_hash(x, y);
+}
+// (cells x strips) a body is entered under; false: more than 65,536 (reported as an overflow like a body spanning > 4096 cells)
+__device__ __forceinline__ bool col_strip_range(const ColBody &b, float strip, int minX, int maxX, int minY, int maxY, int &s0, int &s1)
+{
+    s0 = col_strip_of(__fsub_rn(b.x, b.r), strip); s1 = col_strip_of(__fadd_rn(b.x, b.r), strip);
+    const long long entries = (long long)(maxX - minX + 1) * (long long)(maxY - minY + 1) * (long long)(s1 - s0 + 1);
+    return s1 >= s0 && entries <= 65536;
+}
+
+// ---- one (body, cell, strip) unit of the three grid passes --------------------------------------------------------------
+__device__ __forceinline__ unsigned col_find_slot(const ColGrid &g, unsigned long long key)
+{
+    unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
+    for (unsigned probes = 0; probes <= g.tmask; ++probes) {
+        const unsigned long long k = g.tkeys[slot];
+        if (k == key) return slot;
+        if (k == 0ull) break;
+        slot = (slot + 1) & g.tmask;
+    }
+    return 0xffffffffu;
+}
+
+struct ColInsertOp {
+    __device__ __forceinline__ void operator()(const ColArgs &a, const ColGrid &g, const ColBody &b, unsigned i, int x, int y, int st,
+                                               unsigned &) const
+    {
+        const unsigned long long key = col_table_key(x, y, st);
+        unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
+        unsigned probes = 0;
+        for (;;) {                                              // find or claim the cell's slot
+            const unsigned long long old = atomicCAS(&g.tkeys[slot], 0ull, key);
+            if (old == 0ull || old == key) break;
+            slot = (slot + 1) & g.tmask;
+            if (++probes > g.tmask) break;
+        }
+        const unsigned e = atomicAdd(&g.flags[1], 1u);
+        if (e >= g.ecap || probes > g.tmask) { col_overflow(a); atomicAdd(&g.flags[0], 1u); return; }
+        g.edata[e] = make_float4(b.x, b.y, b.r, __uint_as_float(i));
+        g.enext[e] = atomicExch(&g.heads[slot], e + 1u);
+    }
+};
+
+struct ColDetectOp {
+    __device__ __forceinline__ void operator()(const ColArgs &, const ColGrid &g, const ColBody &A, unsigned i, int x, int y, int st,
+                                               unsigned &overlaps) const
+    {
+        const unsigned slot = col_find_slot(g, col_table_key(x, y, st));
+        if (slot == 0xffffffffu) return;
+        for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
+            const float4 E = g.edata[e - 1u];
+            const unsigned j = __float_as_uint(E.w);
+            if (j <= i) continue;                                // every pair at least once (a count; repeats do no harm)
+            ColBody B; B.x = E.x; B.y = E.y; B.r = E.z;
+            const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
+            if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r))) ++overlaps;
+        }
+    }
+};
+
+// the three passes share one driver: a body covering one or two (cell, strip) units handles them itself; a body covering
+// more -- the shipped scene's central mass of radius 200 sits on 4 cells x 11 strips of the busiest lists -- would be the
+// kernel's critical path, so its units are spread over the lanes of its warp
+template <typename Op>
+__device__ __forceinline__ void col_grid_for_each_unit(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads, bool report,
+                                                       const Op &op, unsigned &acc)
+{
+    const unsigned lane = gtid & 31u;
+    for (unsigned base = gtid - lane; base < a.n; base += gthreads) {                 // trip count uniform over the warp
+        const unsigned i = base + lane;
+        ColBody b; b.x = 0.f; b.y = 0.f; b.r = 0.f;
+        int minX = 0, maxX = -1, minY = 0, maxY = -1, s0 = 0, s1 = -1;
+        unsigned units = 0;
+        if (i < a.n) {
+            b = col_load(a.posm, a.vel, i);
+            if (col_cell_range(b, minX, maxX, minY, maxY) && col_strip_range(b, a.strip, minX, maxX, minY, maxY, s0, s1))
+                units = (unsigned)((maxX - minX + 1) * (maxY - minY + 1) * (s1 - s0 + 1));
+            else if (report) { col_overflow(a); atomicAdd(&g.flags[0], 1u); }      // let the full pass report it
+        }
+        if (units <= 2u) {
+            for (int y = minY; y <= maxY && units; ++y)
+                for (int x = minX; x <= maxX; ++x)
+                    for (int st = s0; st <= s1; ++st) op(a, g, b, i, x, y, st, acc);
+        }
+        unsigned bigs = __ballot_sync(0xffffffffu, units > 2u);
+        while (bigs) {
+            const int src = __ffs(bigs) - 1;
+            bigs &= bigs - 1u;
+            ColBody B;
+            B.x = __shfl_sync(0xffffffffu, b.x, src); B.y = __shfl_sync(0xffffffffu, b.y, src); B.r = __shfl_sync(0xffffffffu, b.r, src);
+            const int bx0 = __shfl_sync(0xffffffffu, minX, src), bx1 = __shfl_sync(0xffffffffu, maxX, src);
+            const int by0 = __shfl_sync(0xffffffffu, minY, src);
+            const int bs0 = __shfl_sync(0xffffffffu, s0, src), bs1 = __shfl_sync(0xffffffffu, s1, src);
+            const unsigned total = __shfl_sync(0xffffffffu, units, src);
+            const unsigned nx = (unsigned)(bx1 - bx0 + 1), ns = (unsigned)(bs1 - bs0 + 1);
+            for (unsigned u = lane; u < total; u += 32u) {
+                const unsigned st = u % ns, xy = u / ns;
+                op(a, g, B, base + (unsigned)src, bx0 + (int)(xy % nx), by0 + (int)(xy / nx), bs0 + (int)st, acc);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void col_grid_insert(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads)
 {
-    for (unsigned i = gtid; i < a.n; i += gthreads) {
-        const ColBody b = col_load(a.posm, a.vel, i);
-        int minX, maxX, minY, maxY;
-        if (!col_cell_range(b, minX, maxX, minY, maxY)) { col_overflow(a); atomicAdd(&g.flags[0], 1u); continue; }   // let the full pass report it
-        for (int y = minY; y <= maxY; ++y)
-            for (int x = minX; x <= maxX; ++x) {
-                const unsigned long long key = (1ull << 32) | (unsigned)col_hash(x, y);
-                unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
-                unsigned probes = 0;
-                for (;;) {                                              // find or claim the cell's slot
-                    const unsigned long long old = atomicCAS(&g.tkeys[slot], 0ull, key);
-                    if (old == 0ull || old == key) break;
-                    slot = (slot + 1) & g.tmask;
-                    if (++probes > g.tmask) break;
-                }
-                const unsigned e = atomicAdd(&g.flags[1], 1u);
-                if (e >= g.ecap || probes > g.tmask) { col_overflow(a); atomicAdd(&g.flags[0], 1u); continue; }
-                g.edata[e] = make_float4(b.x, b.y, b.r, __uint_as_float(i));
-                g.enext[e] = atomicExch(&g.heads[slot], e + 1u);
-            }
-    }
+    unsigned unused = 0;
+    col_grid_for_each_unit(a, g, gtid, gthreads, true, ColInsertOp(), unused);
 }
 
 __device__ __forceinline__ void col_grid_detect(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads)
 {
     unsigned overlaps = 0;
-    for (unsigned i = gtid; i < a.n; i += gthreads) {
-        const ColBody A = col_load(a.posm, a.vel, i);
-        int minX, maxX, minY, maxY;
-        if (!col_cell_range(A, minX, maxX, minY, maxY)) continue;
-        for (int y = minY; y <= maxY; ++y)
-            for (int x = minX; x <= maxX; ++x) {
-                const unsigned long long key = (1ull << 32) | (unsigned)col_hash(x, y);
-                unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
-                for (unsigned probes = 0; probes <= g.tmask; ++probes) {
-                    const unsigned long long k = g.tkeys[slot];
-                    if (k == key || k == 0ull) break;
-                    slot = (slot + 1) & g.tmask;
-                }
-                if (g.tkeys[slot] != key) continue;
-                for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
-                    const float4 E = g.edata[e - 1u];
-                    const unsigned j = __float_as_uint(E.w);
-                    if (j <= i) continue;                                // every pair once (per shared cell)
-                    ColBody B; B.x = E.x; B.y = E.y; B.r = E.z;
-                    const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
-                    if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r))) ++overlaps;
-                }
-            }
-    }
+    col_grid_for_each_unit(a, g, gtid, gthreads, false, ColDetectOp(), overlaps);
     if (overlaps) atomicAdd(&g.flags[0], overlaps);
 }
 
@@ -204,39 +275,34 @@ __device__ __forceinline__ bool col_sweep_pair(const ColBody &a, unsigned ia, co
 // cell) is produced exactly once, as by the reference's sweep) -- key (first, second), bit 63 = the pair overlaps now.
 // flags[2] counts the pairs, flags[0] the overlapping ones.
 constexpr unsigned long long COL_OVERLAP_BIT = 1ull << 63;
+struct ColPairsOp {
+    __device__ __forceinline__ void operator()(const ColArgs &a, const ColGrid &g, const ColBody &A, unsigned i, int x, int y, int st,
+                                               unsigned &overlaps) const
+    {
+        const unsigned slot = col_find_slot(g, col_table_key(x, y, st));
+        if (slot == 0xffffffffu) return;
+        const float amin = __fsub_rn(A.x, A.r);
+        for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
+            const float4 E = g.edata[e - 1u];
+            const unsigned j = __float_as_uint(E.w);
+            if (j == i) continue;
+            ColBody B; B.x = E.x; B.y = E.y; B.r = E.z;
+            unsigned first, second;
+            if (!col_sweep_pair(A, i, B, j, first, second) || first != i) continue;
+            if (col_strip_of(fmaxf(amin, __fsub_rn(B.x, B.r)), a.strip) != st) continue;      // taken in the strip where the overlap starts
+            const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
+            const bool overlap = !(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r));
+            const unsigned p = atomicAdd(&g.flags[2], 1u);
+            if (p < a.pair_cap) a.pairs[p] = ((unsigned long long)first << a.idx_bits) | second | (overlap ? COL_OVERLAP_BIT : 0ull);
+            else col_overflow(a);
+            overlaps += overlap ? 1u : 0u;
+        }
+    }
+};
 __device__ __forceinline__ void col_grid_pairs(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads)
 {
     unsigned overlaps = 0;
-    for (unsigned i = gtid; i < a.n; i += gthreads) {
-        const ColBody A = col_load(a.posm, a.vel, i);
-        int minX, maxX, minY, maxY;
-        if (!col_cell_range(A, minX, maxX, minY, maxY)) continue;
-        for (int y = minY; y <= maxY; ++y)
-            for (int x = minX; x <= maxX; ++x) {
-                const unsigned long long key = (1ull << 32) | (unsigned)col_hash(x, y);
-                unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ull >> 40) & g.tmask;
-                for (unsigned probes = 0; probes <= g.tmask; ++probes) {
-                    const unsigned long long k = g.tkeys[slot];
-                    if (k == key || k == 0ull) break;
-                    slot = (slot + 1) & g.tmask;
-                }
-                if (g.tkeys[slot] != key) continue;
-                for (unsigned e = g.heads[slot]; e != 0u; e = g.enext[e - 1u]) {
-                    const float4 E = g.edata[e - 1u];
-                    const unsigned j = __float_as_uint(E.w);
-                    if (j == i) continue;
-                    ColBody B; B.x = E.x; B.y = E.y; B.r = E.z;
-                    unsigned first, second;
-                    if (!col_sweep_pair(A, i, B, j, first, second) || first != i) continue;
-                    const float dx = __fsub_rn(B.x, A.x), dy = __fsub_rn(B.y, A.y), r = __fadd_rn(A.r, B.r);
-                    const bool overlap = !(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > __fmul_rn(r, r));
-                    const unsigned p = atomicAdd(&g.flags[2], 1u);
-                    if (p < a.pair_cap) a.pairs[p] = ((unsigned long long)first << a.idx_bits) | second | (overlap ? COL_OVERLAP_BIT : 0ull);
-                    else col_overflow(a);
-                    overlaps += overlap ? 1u : 0u;
-                }
-            }
-    }
+    col_grid_for_each_unit(a, g, gtid, gthreads, false, ColPairsOp(), overlaps);
     if (overlaps) atomicAdd(&g.flags[0], overlaps);
 }
 

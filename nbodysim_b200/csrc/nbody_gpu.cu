@@ -571,7 +571,7 @@ int sync_all(nbody_ctx *ctx)
                 return NBODY_ENOMEM;
             }
             if (hs[1]) {
-                set_err(ctx, "collision pass: cell-entry or pair buffer overflow (a body spans more than 4096 grid cells, or a dense "
+                set_err(ctx, "collision pass: cell-entry or pair buffer overflow (a body spans more than 4096 grid cells or 65536 cell strips, or a dense "
                              "clump produced more than %u pairs): the pass was abandoned for at least one step", d.col.pair_cap);
                 return NBODY_ESTATE;
             }
