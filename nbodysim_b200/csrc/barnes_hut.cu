@@ -187,6 +187,61 @@ struct BhNodes {
     __device__ __forceinline__ uint4 *aux(unsigned c) const { return reinterpret_cast<uint4 *>(rec + 2 * (size_t)c + 1); }
 };
 
+// First sorted body whose key has the prefix `pp` above bit `shp`, given that body `s` has it: the owner of the cell with
+// that prefix.  The bodies with the prefix are a run ending at or after s, so this is the first j in [0, s] with
+// (keys[j] >> shp) >= pp.  A search of DEPENDENT loads is what a thread of the build waits for longest, so every round
+// issues up to 7 independent probes: one round brackets the answer between two powers of 8 behind s, the following rounds
+// cut the bracket in 8 -- about 1 + log8(distance) round trips instead of 2 log2(distance).
+__device__ __forceinline__ size_t bh_first_with_prefix(const unsigned long long *__restrict__ keys, size_t s, int shp, unsigned long long pp)
+{
+    // bracket: lo = a position known to lie before the run (or 0), hi = a position known to lie in the run
+    size_t lo = 0, hi = s;
+    {
+        bool in_run[7];
+        size_t pos[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const size_t back = (size_t)1 << (3 * j);                         // 1, 8, 64, ... 262144 behind s
+            pos[j] = s >= back ? s - back : 0;
+            in_run[j] = (keys[pos[j]] >> shp) >= pp;
+        }
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (found) continue;
+            if (in_run[j]) hi = pos[j];
+            else { lo = pos[j] + 1; found = true; }
+        }
+        // (beyond 8^6 bodies behind s the bracket is [0, hi): the loop below still narrows it 8-fold per round)
+    }
+    while (hi > lo) {                                                         // invariant: the answer is in [lo, hi]
+        const size_t len = hi - lo;
+        if (len <= 7) {
+            bool in_run[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) in_run[j] = (size_t)j < len ? (keys[lo + j] >> shp) >= pp : true;
+            size_t ans = hi;
+#pragma unroll
+            for (int j = 6; j >= 0; --j) if ((size_t)j < len && in_run[j]) ans = lo + j;
+            return ans;
+        }
+        bool in_run[7];
+        size_t pos[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { pos[j] = lo + (len * (size_t)(j + 1)) / 8; in_run[j] = (keys[pos[j]] >> shp) >= pp; }
+        size_t nlo = lo, nhi = hi;
+        bool closed = false;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (closed) continue;
+            if (in_run[j]) { nhi = pos[j]; closed = true; }
+            else nlo = pos[j] + 1;
+        }
+        lo = nlo; hi = nhi;
+    }
+    return lo;
+}
+
 // ---- 5. emit the pre-order node array -------------------------------------------------------------
 template <int DIMS>
 __global__ void __launch_bounds__(128)
@@ -383,6 +438,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
 {
     // tuning aid (NBODY_BH_TRACE): per phase, the largest number of SM cycles any thread needed to get there
     const long long trace_t0 = TRACE ? clock64() : 0;
+    const unsigned exp_ = TRACE ? (unsigned)trace[15] : 0u;      // timing experiments (results invalid): 1 no stores, 2 no rcp, 4 no marks
     int trace_k = 0;
 #define BHL_TRACE() do { if (TRACE) { const unsigned am = __activemask();                                                          \
                                       const unsigned cyc = __reduce_max_sync(am, (unsigned)(clock64() - trace_t0));                  \
@@ -395,7 +451,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
     __shared__ int sA[W + 1];                 // levels shared with the previous sorted body (-1: none); [W] = the body after the window
     __shared__ unsigned soffs[W + 1];         // first cell of every body of the window
     __shared__ float4 sval[W];                // datum of a thread's FIRST cell once complete: (x, y, z, mass)
-    __shared__ unsigned short send[W];        // ... and the window index where that cell's span ends; NOT_LOCAL: not computed here
+    __shared__ unsigned spk[W + 1];           // ... its parent's depth and the window index where its span ends (see below)
     __shared__ unsigned char spulled[W];      // the first cell was added to its parent by the parent's owner in this CTA
     __shared__ int s_maxd;
     const unsigned i = threadIdx.x;
@@ -415,7 +471,6 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
         soffs[W] = sw <= n ? offs[sw] : total;
     }
     spulled[i] = 0;
-    send[i] = NOT_LOCAL;
     if (i == 0) s_maxd = 0;
     const unsigned cnt = exists ? count[s] : 0u;
     const bool main_thread = i < (unsigned)M;
@@ -466,13 +521,22 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
     // ---- centres of mass of the local cells, deepest level first (one CTA barrier per level)
     // (Tried: letting every thread climb as far as its children are published, rounds instead of levels -- same time: the
     //  loop is bound by the instructions all warps issue per step, not by the barriers.)
+    // spk[t] packs what a parent needs to know about thread t's first cell in ONE word: bits 0..7 the levels t shares with its
+    // predecessor (= the depth of that cell's parent; 0xff: none), bits 8.. the window index where the cell's span ends
+    // (NOT_LOCAL until the cell is complete, and for good if it is not local) -- one shared-memory round trip per child.
     auto span_ok = [&](unsigned t) { return t <= (unsigned)W && t - i <= (unsigned)H; };
     bool alive = cnt != 0 && span_ok(tp);     // false: this chain continues in the climb (or the body owns nothing)
     int dcur = leafd;
-    if (alive && firstd == leafd) { sval[i] = make_float4(cx_, cy_, cz_, cm_); send[i] = (unsigned short)tp; }
+    const unsigned myA = (unsigned)sA[i] & 0xffu;
+    if (alive && firstd == leafd) { sval[i] = make_float4(cx_, cy_, cz_, cm_); spk[i] = myA | (tp << 8); }
+    else spk[i] = myA | ((unsigned)NOT_LOCAL << 8);
+    if (i == W - 1) spk[W] = ((unsigned)sA[W] & 0xffu) | ((unsigned)NOT_LOCAL << 8);
     if (cnt) atomicMax(&s_maxd, leafd);
     __syncthreads();
+    const long long trace_lv0 = TRACE ? clock64() : 0;
+    int trace_iters = 0;
     for (int d = s_maxd - 1; d >= 0; --d) {
+        if (TRACE) ++trace_iters;
         if (alive && d >= firstd && d < leafd) {              // the cell at depth d of this chain; `cur` is its first child
             float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
             px = __fadd_rn(px, __fmul_rn(cx_, cm_));
@@ -481,47 +545,54 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
             ms = __fadd_rn(ms, cm_);
             unsigned t = tp, kids[NCHILD - 1];
             int nk = 0;
-            bool ok = true;
+            bool ok = true, more = true;
 #pragma unroll
             for (int c = 0; c < (int)NCHILD - 1; ++c) {        // the following children: first cells of later threads, in key order
-                if (ok && t <= (unsigned)W && sA[t] == d) {
-                    const unsigned short e = (t < (unsigned)W) ? send[t] : NOT_LOCAL;
-                    if (e == NOT_LOCAL) ok = false;
-                    else {
-                        const float4 ch = sval[t];
-                        px = __fadd_rn(px, __fmul_rn(ch.x, ch.w));
-                        py = __fadd_rn(py, __fmul_rn(ch.y, ch.w));
-                        if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch.z, ch.w));
-                        ms = __fadd_rn(ms, ch.w);
-                        kids[c] = t; nk = c + 1;
-                        t = e;
+                if (more) {
+                    const unsigned tt = min(t, (unsigned)W);
+                    const unsigned w_ = spk[tt];                // requested together with the datum it may announce
+                    const float4 ch = sval[min(tt, (unsigned)W - 1u)];
+                    more = t <= (unsigned)W && (w_ & 0xffu) == (unsigned)d;
+                    if (more) {
+                        const unsigned e = w_ >> 8;
+                        if (e == (unsigned)NOT_LOCAL) { ok = false; more = false; }
+                        else {
+                            px = __fadd_rn(px, __fmul_rn(ch.x, ch.w));
+                            py = __fadd_rn(py, __fmul_rn(ch.y, ch.w));
+                            if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch.z, ch.w));
+                            ms = __fadd_rn(ms, ch.w);
+                            kids[c] = t; nk = c + 1;
+                            t = e;
+                        }
                     }
                 }
             }
             if (ok && span_ok(t)) {
 #pragma unroll
-                for (int c = 0; c < (int)NCHILD - 1; ++c) if (c < nk) spulled[kids[c]] = 1;
-                if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv
-                    const float inv = __fdiv_rn(1.0f, ms);
+                for (int c = 0; c < (int)NCHILD - 1; ++c) if (c < nk && !(exp_ & 4u)) spulled[kids[c]] = 1;
+                if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv   (1/m correctly rounded: rcp.rn)
+                    const float inv = (exp_ & 2u) ? 0.5f : __frcp_rn(ms);
                     px = __fmul_rn(px, inv);
                     py = __fmul_rn(py, inv);
                     if (DIMS == 3) pz = __fmul_rn(pz, inv);
                 }
                 cx_ = px; cy_ = py; cz_ = pz; cm_ = ms;
                 tp = t; dcur = d;
+                if (d == firstd) { sval[i] = make_float4(px, py, pz, ms); spk[i] = myA | (t << 8); }
                 const unsigned c = off + (unsigned)(d - firstd);
-                if (main_thread && c < cap) {
+                if (main_thread && c < cap && !(exp_ & 1u)) {
                     *reinterpret_cast<float2 *>(nodes.data(c)) = make_float2(px, py);
                     reinterpret_cast<float *>(nodes.data(c))[2] = ms;
                     if (DIMS == 3) reinterpret_cast<float *>(nodes.aux(c))[0] = pz;
                     reinterpret_cast<unsigned *>(nodes.aux(c))[1] = (s0 + t < n) ? soffs[t] : 0u;
                 }
-                if (d == firstd) { sval[i] = make_float4(px, py, pz, ms); send[i] = (unsigned short)t; }
             } else alive = false;
         }
+        if (TRACE && i == 0) { atomicAdd(trace + 8 + (blockIdx.x == 0 ? 0 : 1), 1ull); atomicMax(trace + 10, (unsigned long long)(s_maxd - d)); }
         if (!__syncthreads_or(alive && dcur > firstd)) break;
     }
     __syncthreads();
+    if (TRACE && i == 0 && blockIdx.x < 1000) { trace[16 + 2 * blockIdx.x] = (unsigned long long)(clock64() - trace_lv0); trace[17 + 2 * blockIdx.x] = (unsigned long long)trace_iters; }
 
     BHL_TRACE();   // 2: local levels
     // ---- hand-over to the climb: count every cell that the local part did not attach to its parent as a child of that parent
@@ -544,8 +615,8 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
             unsigned t = tp;
             bool ok = true;
             while (t <= (unsigned)W && sA[t] == firstd - 1) {
-                const unsigned short e = (t < (unsigned)W) ? send[t] : NOT_LOCAL;
-                if (e == NOT_LOCAL) { ok = false; break; }
+                const unsigned e = spk[t] >> 8;
+                if (e == (unsigned)NOT_LOCAL) { ok = false; break; }
                 t = e;
             }
             if (ok && t <= (unsigned)W) {
@@ -554,18 +625,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
             }
         }
         if (!parent_local) {
-            // owner of the parent cell: the first sorted body with that prefix -- gallop backwards, then bisect
-            size_t lo = 0, hi = s, step = 1;
-            while (lo < hi) {
-                const size_t probe = (hi >= lo + step) ? hi - step : lo;
-                if ((keys[probe] >> shp) < pp) { lo = probe + 1; break; }
-                hi = probe;
-                step <<= 1;
-            }
-            while (lo < hi) {
-                const size_t mid = (lo + hi) >> 1;
-                if ((keys[mid] >> shp) >= pp) hi = mid; else lo = mid + 1;
-            }
+            const size_t lo = bh_first_with_prefix(keys, s, shp, pp);        // owner of the parent cell
             const unsigned par = offs[lo] + (unsigned)(firstd - 1 - (int)first[lo]);
             if (off < cap) reinterpret_cast<unsigned *>(nodes.aux(off))[3] = par;
             if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + ((unsigned)(k >> (64 - BITS * firstd)) & (NCHILD - 1u)))));
@@ -1240,12 +1300,22 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
                  w.node_cap, w.status, (unsigned *)w.climb_start
 #define BHL_LAUNCH(T, M, H, TR) bh_emit_local_kernel<DIMS, T, M, H><<<(unsigned)((n + (M) - 1) / (M)), (M) + (H), 0, st>>>(BHL_ARGS, TR)
         if (want_trace) {
-            if (!w.trace && cudaMalloc(&w.trace, 64 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
-            cudaMemsetAsync(w.trace, 0, 64 * sizeof(long long), st);
+            const unsigned lgrid_trace = (unsigned)((n + 255) / 256);
+            if (!w.trace && cudaMalloc(&w.trace, 2048 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+            cudaMemsetAsync(w.trace, 0, 2048 * sizeof(long long), st);
+            const unsigned long long expv = getenv("NBODY_BHL_EXP") ? strtoull(getenv("NBODY_BHL_EXP"), nullptr, 10) : 0ull;
+            cudaMemcpyAsync((unsigned long long *)w.trace + 15, &expv, 8, cudaMemcpyHostToDevice, st);
             BHL_LAUNCH(true, 256, 128, (unsigned long long *)w.trace);
-            unsigned long long h[4];
-            if (cudaMemcpyAsync(h, w.trace, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess)
-                fprintf(stderr, "[emit_local n=%zu] max cycles to the end of: loads %llu, skeleton %llu, local levels %llu, hand-over %llu\n", n, h[0], h[1], h[2], h[3]);
+            unsigned long long h[2048];
+            if (cudaMemcpyAsync(h, w.trace, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
+                if (getenv("NBODY_BH_TRACE_CTAS")) {
+                    fprintf(stderr, "[emit_local] per CTA (cycles in the level loop / iterations):");
+                    for (unsigned c = 0; c < lgrid_trace && c < 1000; ++c) fprintf(stderr, " %llu/%llu", h[16 + 2 * c], h[17 + 2 * c]);
+                    fprintf(stderr, "\n");
+                }
+                fprintf(stderr, "[emit_local n=%zu] max cycles to the end of: loads %llu, skeleton %llu, local levels %llu, hand-over %llu; level iterations: CTA 0 %llu, mean of the others %.1f, most %llu\n",
+                        n, h[0], h[1], h[2], h[3], h[8], (double)h[9] / (double)std::max<size_t>(1, (n + 255) / 256 - 1), h[10]);
+            }
         } else if (geom == 1) BHL_LAUNCH(false, 128, 128, nullptr);
         else if (geom == 2) BHL_LAUNCH(false, 64, 64, nullptr);
         else if (geom == 3) BHL_LAUNCH(false, 128, 256, nullptr);
@@ -1326,7 +1396,7 @@ cudaError_t BhWorkspace::build(const float *posm, size_t n, cudaStream_t st, int
         static const bool want_trace = getenv("NBODY_CLUSTER_TRACE") != nullptr;
         a.trace = nullptr;
         if (want_trace) {
-            if (!trace && cudaMalloc(&trace, 64 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+            if (!trace && cudaMalloc(&trace, 2048 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
             cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st);
             a.trace = (long long *)trace;
         }

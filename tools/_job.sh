@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_collide.py tests/test_reference_scene.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-for sw in 0 150 75 37.5 18.75 9.375 0 37.5; do echo "== strip $sw"; NBODY_COL_STRIP=$sw python tools/bench_refscene.py 25000 2>&1 | sed -n 2p | cut -c1-330; done
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 200 --csv --log-file gpurun_out/r2b_launches_refscene_warm.csv python tools/bh_profile.py 25000 0 1.0 6 > gpurun_out/ncu1.log 2>&1
+python tools/bench_refscene.py 25000 2>&1 | sed -n 2p | cut -c1-330
