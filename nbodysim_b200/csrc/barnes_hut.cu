@@ -434,7 +434,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
                      const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
                      const unsigned char *__restrict__ first, const unsigned char *__restrict__ leaf,
                      BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap, unsigned *status, unsigned *__restrict__ gstart,
-                     unsigned long long *trace)
+                     uint4 *__restrict__ edge_list, unsigned *__restrict__ edge_count, unsigned edge_cap, unsigned long long *trace)
 {
     // tuning aid (NBODY_BH_TRACE): per phase, the largest number of SM cycles any thread needed to get there
     const long long trace_t0 = TRACE ? clock64() : 0;
@@ -599,9 +599,17 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
     if (!(cnt && main_thread)) return;
     unsigned start = 0xffffffffu;
     // cells of the chain above the local part (depths firstd .. dcur-1) and the local part's top cell (depth dcur) hang from the chain
+    // small scenes also LIST every such (child, parent) edge for the one-CTA climb: (child cell, parent cell, quadrant | depth << 8
+    // | "the child's datum is complete" << 16)
+    auto list_edge = [&](unsigned child, unsigned parent, unsigned qd, int d, bool complete) {
+        if (!edge_list) return;
+        const unsigned e = atomicAdd(edge_count, 1u);
+        if (e < edge_cap) edge_list[e] = make_uint4(child, parent, qd | ((unsigned)d << 8) | (complete ? 65536u : 0u), 0u);
+    };
     for (int d = dcur; d > firstd; --d) {
-        const unsigned c = off + (unsigned)(d - firstd), par = c - 1u;
-        if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + ((unsigned)(k >> (64 - BITS * d)) & (NCHILD - 1u)))));
+        const unsigned c = off + (unsigned)(d - firstd), par = c - 1u, qd = (unsigned)(k >> (64 - BITS * d)) & (NCHILD - 1u);
+        if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + qd)));
+        list_edge(c, par, qd, d, d == dcur);
     }
     if (dcur > firstd) start = off + (unsigned)(dcur - firstd);
     if (firstd > 0 && !(dcur == firstd && spulled[i])) {
@@ -628,7 +636,9 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
             const size_t lo = bh_first_with_prefix(keys, s, shp, pp);        // owner of the parent cell
             const unsigned par = offs[lo] + (unsigned)(firstd - 1 - (int)first[lo]);
             if (off < cap) reinterpret_cast<unsigned *>(nodes.aux(off))[3] = par;
-            if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + ((unsigned)(k >> (64 - BITS * firstd)) & (NCHILD - 1u)))));
+            const unsigned qd = (unsigned)(k >> (64 - BITS * firstd)) & (NCHILD - 1u);
+            if (par < cap) atomicAdd(&arrive[par], 1u | (1u << (16 + qd)));
+            list_edge(off, par, qd, firstd, dcur == firstd);
             if (dcur == firstd) start = off;
         }
     }
@@ -637,18 +647,13 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
 #undef BHL_TRACE
 }
 
-// The climb over the cells the local kernel left: bh_propagate_kernel's protocol, started from `gstart` instead of the leaves.
+// The climb over the cells the local kernel left: bh_propagate_kernel's protocol, started from the cell where a chain leaves
+// the local part instead of from the leaves.  Returns (cells finished, of which with several children) for the tuning trace.
 template <int DIMS>
-__global__ void __launch_bounds__(256)
-bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
-                const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive, unsigned cap)
+__device__ __forceinline__ uint2 bh_climb_chain(const BhNodes &nodes, unsigned c, unsigned total, unsigned m, unsigned *__restrict__ arrive)
 {
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
-    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n || count[s] == 0) return;
-    unsigned c = gstart[s];
-    const unsigned total = offs[n], m = min(total, cap);
-    if (c >= m) return;                                                // 0xffffffff: nothing of this chain is left
+    unsigned levels = 0, waits = 0;
     uint4 a = __ldcg(nodes.aux(c));
     const float4 d0 = __ldcg(nodes.data(c));
     float x = d0.x, y = d0.y, z = (DIMS == 3) ? __uint_as_float(a.x) : 0.f, mass = d0.z;
@@ -672,7 +677,9 @@ bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, cons
             __threadfence();                                           // my deposit is visible before I announce it
             const unsigned old = atomicAdd(&arrive[par], 0x100u);
             if (((old >> 8) & 0xffu) + 1u != (old & 0xffu)) break;     // a sibling will arrive later and do the work
-            __threadfence();
+            // no second fence: the loads below are issued only after the atomic has returned (the branch above depends on
+            // its result and a GPU does not speculate), every sibling fenced its deposit before ITS arrival, and the loads
+            // bypass L1 -- one fence per level instead of two on the build's longest dependent chain
             const unsigned mask = (old >> 16) & 0xffu;
             float4 ch[NCHILD];
             unsigned sub[NCHILD];
@@ -693,9 +700,10 @@ bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, cons
                     cells += sub[k];
                 }
             }
+            ++waits;
         }
-        if (ms > 0.f) {
-            const float inv = __fdiv_rn(1.0f, ms);
+        if (ms > 0.f) {                                                // 1/m correctly rounded, as the reference's division
+            const float inv = __frcp_rn(ms);
             px = __fmul_rn(px, inv);
             py = __fmul_rn(py, inv);
             if (DIMS == 3) pz = __fmul_rn(pz, inv);
@@ -707,7 +715,144 @@ bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, cons
         x = px; y = py; z = pz; mass = ms;
         a = pa;
         c = par;
+        ++levels;
     }
+    return make_uint2(levels, waits);
+}
+
+template <int DIMS, bool TRACE>
+__global__ void __launch_bounds__(256)
+bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
+                const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive, unsigned cap, unsigned long long *trace)
+{
+    const long long trace_t0 = TRACE ? clock64() : 0;
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || count[s] == 0) return;
+    const unsigned c = gstart[s];
+    const unsigned total = offs[n], m = min(total, cap);
+    if (c >= m) return;                                                // 0xffffffff: nothing of this chain is left
+    const uint2 t = bh_climb_chain<DIMS>(nodes, c, total, m, arrive);
+    if (TRACE) {
+        atomicAdd(trace + 0, 1ull);                                    // chains that reach the climb
+        atomicMax(trace + 1, (unsigned long long)t.x);                 // most cells finished by one thread ...
+        atomicMax(trace + 2, (unsigned long long)t.y);                 // ... of which with more than one child (slot + fence + atomic)
+        atomicMax(trace + 3, (unsigned long long)(clock64() - trace_t0));
+    }
+}
+
+// Small scenes: the top of the tree in the SHARED MEMORY of one CTA.  Whatever climbs through global memory pays one or two
+// L2 round trips (and a fence) per tree level -- ~3,000 cycles x 8 levels on the shipped scene, whether many CTAs use atomics or
+// one CTA uses barriers (both measured, profiles/).  But the cells involved are few: the local kernel lists every (child, parent)
+// edge it could not close, ~1,000 at 25,000 bodies.  One CTA loads the list and the data of the complete children once (two
+// round trips for everything), finds every edge's parent through a small hash table, and then sums level by level out of shared
+// memory -- children in quadrant order, Quadtree::propagate's arithmetic -- storing each finished cell's record on the way.
+// More than BTC_MAX_EDGES edges (a pathological scene at these sizes): the CTA runs the atomic protocol over `gstart` instead.
+constexpr int BTC_THREADS = 1024, BTC_MAX_EDGES = 2047, BTC_HASH = 4096;
+template <int DIMS> struct BtcSmem {
+    float4 val[BTC_MAX_EDGES + 1];                        // (x, y, z, mass) of node e = the child cell of edge e; [E] = the root
+    unsigned cell[BTC_MAX_EDGES + 1], sub[BTC_MAX_EDGES + 1], info[BTC_MAX_EDGES + 1];   // cell index, cells in its subtree, quadrant | depth << 8 | complete << 16
+    unsigned short pid[BTC_MAX_EDGES + 1];                // node of the parent cell
+    unsigned short kids[(BTC_MAX_EDGES + 1) * (1 << DIMS)];   // node of the child in each quadrant, 0xffff = none
+    unsigned hkey[BTC_HASH];                              // cell index + 1 -> node (open addressing)
+    unsigned short hval[BTC_HASH];
+    int maxd, bad;
+};
+
+template <int DIMS, bool TRACE>
+__global__ void __launch_bounds__(BTC_THREADS, 1)
+bh_top_cta_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned *__restrict__ count, const uint4 *__restrict__ edges,
+                  const unsigned *__restrict__ nedges, unsigned edge_cap, const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive,
+                  unsigned cap, unsigned long long *trace)
+{
+    constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
+    extern __shared__ __align__(16) unsigned char btc_raw[];
+    BtcSmem<DIMS> &sm = *reinterpret_cast<BtcSmem<DIMS> *>(btc_raw);
+    const long long trace_t0 = TRACE ? clock64() : 0;
+    const unsigned tid = threadIdx.x;
+    const unsigned total = offs[n], m = min(total, cap), E = *nedges;
+    if (E == 0u) return;                                               // everything was local (n <= halo)
+    if (E > (unsigned)BTC_MAX_EDGES || E > edge_cap || total > cap) {  // too many edges (or a truncated tree): the atomic climb, by this CTA
+        for (size_t s = tid; s < n; s += BTC_THREADS) {
+            if (count[s] == 0) continue;
+            const unsigned c = gstart[s];
+            if (c < m) bh_climb_chain<DIMS>(nodes, c, total, m, arrive);
+        }
+        return;
+    }
+    for (unsigned h = tid; h < (unsigned)BTC_HASH; h += BTC_THREADS) sm.hkey[h] = 0u;
+    for (unsigned k = tid; k < (E + 1u) * NCHILD; k += BTC_THREADS) sm.kids[k] = 0xffffu;
+    if (tid == 0) { sm.maxd = 0; sm.bad = 0; sm.cell[E] = 0u; sm.info[E] = 0u; sm.pid[E] = 0xffffu; }   // node E: the root (cell 0, depth 0)
+    __syncthreads();
+    // nodes, hash of their cells, data of the complete ones
+    for (unsigned e = tid; e < E; e += BTC_THREADS) {
+        const uint4 ed = edges[e];
+        sm.cell[e] = ed.x; sm.info[e] = ed.z;
+        unsigned h = (ed.x * 2654435761u) >> 20;                       // 12 bits
+        while (atomicCAS(&sm.hkey[h], 0u, ed.x + 1u) != 0u) h = (h + 1u) & (BTC_HASH - 1u);
+        sm.hval[h] = (unsigned short)e;
+        if (ed.z & 65536u) {
+            const uint4 a = __ldcg(nodes.aux(ed.x));
+            const float4 d0 = __ldcg(nodes.data(ed.x));
+            sm.val[e] = make_float4(d0.x, d0.y, (DIMS == 3) ? __uint_as_float(a.x) : 0.f, d0.z);
+            sm.sub[e] = (a.y ? a.y : total) - ed.x;
+        }
+        atomicMax(&sm.maxd, (int)((ed.z >> 8) & 0xffu));
+    }
+    __syncthreads();
+    // every edge finds its parent's node and enters itself as the child of its quadrant
+    for (unsigned e = tid; e < E; e += BTC_THREADS) {
+        const unsigned parent = edges[e].y;
+        unsigned pnode = E;                                            // cell 0 is the root
+        if (parent != 0u) {
+            unsigned h = (parent * 2654435761u) >> 20, probes = 0;
+            while (sm.hkey[h] != parent + 1u && sm.hkey[h] != 0u && probes < (unsigned)BTC_HASH) { h = (h + 1u) & (BTC_HASH - 1u); ++probes; }
+            if (sm.hkey[h] == parent + 1u) pnode = sm.hval[h];
+            else { sm.bad = 1; pnode = 0xffffu; }                      // cannot happen with a consistent list
+        }
+        sm.pid[e] = (unsigned short)pnode;
+        if (pnode != 0xffffu) sm.kids[pnode * NCHILD + (sm.info[e] & 0xffu)] = (unsigned short)e;
+    }
+    __syncthreads();
+    const int top = sm.maxd;
+    if (sm.bad) return;
+    // level by level: the incomplete cells of depth d - 1 sum their children (all of depth d, all finished)
+    for (int d = top; d >= 1; --d) {
+        for (unsigned e = tid; e <= E; e += BTC_THREADS) {
+            const unsigned inf = sm.info[e];
+            if ((int)((inf >> 8) & 0xffu) != d - 1 || (inf & 65536u)) continue;
+            float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+            unsigned cells = 1;
+#pragma unroll
+            for (unsigned c = 0; c < NCHILD; ++c) {
+                const unsigned kid = sm.kids[e * NCHILD + c];
+                if (kid != 0xffffu) {                                  // children in quadrant order
+                    const float4 ch = sm.val[kid];
+                    px = __fadd_rn(px, __fmul_rn(ch.x, ch.w));
+                    py = __fadd_rn(py, __fmul_rn(ch.y, ch.w));
+                    if (DIMS == 3) pz = __fadd_rn(pz, __fmul_rn(ch.z, ch.w));
+                    ms = __fadd_rn(ms, ch.w);
+                    cells += sm.sub[kid];
+                }
+            }
+            if (ms > 0.f) {                                            // 1/m correctly rounded, as the reference's division
+                const float inv = __frcp_rn(ms);
+                px = __fmul_rn(px, inv);
+                py = __fmul_rn(py, inv);
+                if (DIMS == 3) pz = __fmul_rn(pz, inv);
+            }
+            sm.val[e] = make_float4(px, py, pz, ms);
+            sm.sub[e] = cells;
+            const unsigned c = sm.cell[e];
+            if (c < m) {
+                __stcg(reinterpret_cast<float2 *>(nodes.data(c)), make_float2(px, py));
+                __stcg(reinterpret_cast<float *>(nodes.data(c)) + 2, ms);
+                if (DIMS == 3) __stcg(reinterpret_cast<float *>(nodes.aux(c)), pz);
+                reinterpret_cast<unsigned *>(nodes.aux(c))[1] = (c + cells < total) ? c + cells : 0u;
+            }
+        }
+        __syncthreads();
+    }
+    if (TRACE && tid == 0) { trace[0] = E; trace[1] = (unsigned long long)top; trace[3] = (unsigned long long)(clock64() - trace_t0); }
 }
 
 // ---- the whole build as ONE cluster kernel (small scenes) ----------------------------------------------------------------
@@ -1295,9 +1440,15 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     if (!local_off) {
         static const bool want_trace = getenv("NBODY_BH_TRACE") != nullptr;
         static const int geom = getenv("NBODY_BHL_GEOM") ? atoi(getenv("NBODY_BHL_GEOM")) : 0;   // tuning: bodies per CTA / halo
+        // small scenes: the (child, parent) edges left to the climb are listed (word 8 of the zeroed box region counts them) and
+        // ONE CTA finishes the top of the tree in shared memory; NBODY_BH_CTA_CLIMB=0 keeps the atomic climb at every size
+        static const bool cta_climb_off = getenv("NBODY_BH_CTA_CLIMB") && atoi(getenv("NBODY_BH_CTA_CLIMB")) == 0;
+        static const bool cta_climb_ok = cudaFuncSetAttribute(bh_top_cta_kernel<DIMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtcSmem<DIMS>)) == cudaSuccess &&
+                                         cudaFuncSetAttribute(bh_top_cta_kernel<DIMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtcSmem<DIMS>)) == cudaSuccess;
+        const bool cta_climb = !cta_climb_off && cta_climb_ok && n <= 32768;
 #define BHL_ARGS posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,      \
                  (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, \
-                 w.node_cap, w.status, (unsigned *)w.climb_start
+                 w.node_cap, w.status, (unsigned *)w.climb_start, cta_climb ? (uint4 *)w.node_owner : nullptr, (unsigned *)w.box + 8, w.node_cap / 4
 #define BHL_LAUNCH(T, M, H, TR) bh_emit_local_kernel<DIMS, T, M, H><<<(unsigned)((n + (M) - 1) / (M)), (M) + (H), 0, st>>>(BHL_ARGS, TR)
         if (want_trace) {
             const unsigned lgrid_trace = (unsigned)((n + 255) / 256);
@@ -1325,8 +1476,24 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
         else BHL_LAUNCH(false, 256, 128, nullptr);           // sweep on B200 (profiles/): best at 1M and 4M bodies, no difference at 25,000
 #undef BHL_LAUNCH
 #undef BHL_ARGS
-        bh_climb_kernel<DIMS><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
-                                                    (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap);
+#define BCC_ARGS bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count, (const uint4 *)w.node_owner, (const unsigned *)w.box + 8, w.node_cap / 4, \
+                 (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap
+        if (want_trace) {
+            unsigned long long *tr = (unsigned long long *)w.trace + 32;
+            cudaMemsetAsync(tr, 0, 4 * sizeof(long long), st);
+            if (cta_climb) bh_top_cta_kernel<DIMS, true><<<1, BTC_THREADS, sizeof(BtcSmem<DIMS>), st>>>(BCC_ARGS, tr);
+            else bh_climb_kernel<DIMS, true><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
+                                                                   (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap, tr);
+            unsigned long long h[4];
+            if (cudaMemcpyAsync(h, tr, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess)
+                fprintf(stderr, cta_climb ? "[top of the tree, one CTA, n=%zu] edges %llu, deepest %llu, (%llu), cycles %llu\n"
+                                          : "[climb n=%zu] chains %llu, most cells finished by one thread %llu (%llu with several children), max cycles %llu\n", n, h[0], h[1], h[2], h[3]);
+        } else if (cta_climb)
+            bh_top_cta_kernel<DIMS, false><<<1, BTC_THREADS, sizeof(BtcSmem<DIMS>), st>>>(BCC_ARGS, nullptr);
+        else
+            bh_climb_kernel<DIMS, false><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
+                                                               (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap, nullptr);
+#undef BCC_ARGS
     } else {
         bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
                                                    (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,

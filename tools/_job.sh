@@ -1,2 +1,6 @@
-ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 200 --csv --log-file gpurun_out/r2b_launches_refscene_warm.csv python tools/bh_profile.py 25000 0 1.0 6 > gpurun_out/ncu1.log 2>&1
+NBODY_BH_TRACE=1 python tools/bh_profile.py 25000 0 1.0 2 2>&1 | grep "top of" | tail -1
+timeout 600 python -m pytest tests/test_gpu_bh.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -2
 python tools/bench_refscene.py 25000 2>&1 | sed -n 2p | cut -c1-330
+NBODY_BH_CTA_CLIMB=0 python tools/bench_refscene.py 25000 2>&1 | sed -n 2p | cut -c1-330
+python tools/bench_refscene.py 32000 2>&1 | sed -n 2p | cut -c1-330
+NBODY_BH_CTA_CLIMB=0 python tools/bench_refscene.py 32000 2>&1 | sed -n 2p | cut -c1-330
