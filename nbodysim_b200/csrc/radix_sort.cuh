@@ -26,11 +26,15 @@ namespace nb {
 constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32;
 // keys per thread: 16 (tile of 4096 keys, 512 contiguous keys = 16 rows of 32 per warp) for large inputs, 8 (tile
 // of 2048) while the larger tile would leave SMs without a CTA
+// keys per thread (rows of 32 keys per warp) by input size, measured on B200 (profiles/r2_sort_pass_trace.txt): small
+// inputs are latency-bound, so more and smaller tiles win (25,000 pairs, 4 digits + repair: 29.6 us with 8 rows, 25.2 with 4,
+// 23.8 with 2); large ones want long runs per digit in the scattered writes
 constexpr int RS_ROWS_LARGE = 16, RS_ROWS_SMALL = 8;
-constexpr int RS_MIN_TILE = RS_THREADS * RS_ROWS_SMALL;
+constexpr size_t RS_ROWS2_MAX_N = 40000, RS_ROWS4_MAX_N = 200000;
 #ifndef RS_SMALL_TILE_MAX_N
 #define RS_SMALL_TILE_MAX_N (8u << 20)
 #endif
+constexpr int rs_rows_for(size_t n) { return n <= RS_ROWS2_MAX_N ? 2 : n <= RS_ROWS4_MAX_N ? 4 : n <= (size_t)RS_SMALL_TILE_MAX_N ? RS_ROWS_SMALL : RS_ROWS_LARGE; }
 constexpr int RS_MAX_PASSES = 8;
 // scratch layout: [RS_MAX_PASSES][256] digit histograms | RS_MISC_WORDS words (tickets of up to 2 x RS_MAX_PASSES pass
 // launches, the grid-barrier word, the "tie runs too long" flag) | status words
@@ -466,16 +470,28 @@ os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsig
 
 inline size_t radix_sort_temp_bytes(size_t n)
 {
-    const size_t ntiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
+    // status words for the most tiles any input of up to n items is cut into (the tile grows with the input)
+    size_t ntiles = 0;
+    const size_t tier_max[4] = {RS_ROWS2_MAX_N, RS_ROWS4_MAX_N, (size_t)RS_SMALL_TILE_MAX_N, (size_t)-1};
+    const int tier_rows[4] = {2, 4, RS_ROWS_SMALL, RS_ROWS_LARGE};
+    for (int t = 0; t < 4; ++t) {
+        const size_t m = n < tier_max[t] ? n : tier_max[t], tile = (size_t)RS_THREADS * tier_rows[t];
+        ntiles = std::max(ntiles, (m + tile - 1) / tile);
+    }
     return (size_t)(RS_MAX_PASSES * 256 + RS_MISC_WORDS) * sizeof(unsigned) + ntiles * 256 * sizeof(unsigned long long);
 }
 
 // CTAs the all-passes kernel may be launched with (all co-resident; a CTA takes tiles blockIdx, blockIdx + grid, ...);
 // 0 disables it (NBODY_SORT_COOP=0, or a device without cooperative launch)
-static inline int rs_coop_cta_limit(bool has_vals, bool small)
+template <bool V> static inline const void *rs_all_kernel_for(int rows)
 {
-    static int limit[4] = {-1, -1, -1, -1};
-    int &l = limit[(has_vals ? 1 : 0) + (small ? 2 : 0)];
+    return rows == 2 ? (const void *)os_sort_all_kernel<V, 2> : rows == 4 ? (const void *)os_sort_all_kernel<V, 4>
+         : rows == RS_ROWS_SMALL ? (const void *)os_sort_all_kernel<V, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<V, RS_ROWS_LARGE>;
+}
+static inline int rs_coop_cta_limit(bool has_vals, int rows)
+{
+    static int limit[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};
+    int &l = limit[has_vals ? 1 : 0][rows == 2 ? 0 : rows == 4 ? 1 : rows == RS_ROWS_SMALL ? 2 : 3];
     if (l < 0) {
         l = 0;
         const char *env = getenv("NBODY_SORT_COOP");
@@ -483,8 +499,7 @@ static inline int rs_coop_cta_limit(bool has_vals, bool small)
         if (!(env && atoi(env) == 0) && cudaGetDevice(&dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
-            const void *fn = has_vals ? (small ? (const void *)os_sort_all_kernel<true, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<true, RS_ROWS_LARGE>)
-                                      : (small ? (const void *)os_sort_all_kernel<false, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<false, RS_ROWS_LARGE>);
+            const void *fn = has_vals ? rs_all_kernel_for<true>(rows) : rs_all_kernel_for<false>(rows);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RS_THREADS, 0) == cudaSuccess) l = sms * per_sm;
             else cudaGetLastError();
         }
@@ -508,8 +523,8 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
     if (begin_bit % 8 || npasses > RS_MAX_PASSES) return cudaErrorInvalidValue;
     static const bool lazy_off = getenv("NBODY_SORT_LAZY") && atoi(getenv("NBODY_SORT_LAZY")) == 0;
     int lazy_passes = (lazy_low_bits > begin_bit && lazy_low_bits < end_bit && lazy_low_bits % 8 == 0 && !lazy_off) ? (lazy_low_bits - begin_bit) / 8 : 0;
-    const bool small = n <= (size_t)RS_SMALL_TILE_MAX_N;
-    const size_t tile = (size_t)RS_THREADS * (small ? RS_ROWS_SMALL : RS_ROWS_LARGE), ntiles = (n + tile - 1) / tile;
+    const int rows = rs_rows_for(n);
+    const size_t tile = (size_t)RS_THREADS * rows, ntiles = (n + tile - 1) / tile;
     unsigned *hist = (unsigned *)temp;                                    // [npasses][256]
     unsigned *misc = hist + RS_MAX_PASSES * 256;                          // tickets [2 x npasses], barrier word, tie-run flag
     unsigned long long *status = (unsigned long long *)(misc + RS_MISC_WORDS);
@@ -522,11 +537,10 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
     if (!hist_ready) os_hist_kernel<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys_a, n, n_dev, pass0, npasses, hist);
     // all passes in ONE cooperative kernel: every CTA co-resident, a grid-wide barrier between the passes; at small sizes one
     // CTA per tile, beyond that each CTA takes every grid-th tile
-    const int coop_ctas = rs_coop_cta_limit(vals_a != nullptr, small);
+    const int coop_ctas = rs_coop_cta_limit(vals_a != nullptr, rows);
     if (coop_ctas > 0) {
         void *args[] = {&keys_a, &keys_b, &vals_a, &vals_b, &n, &n_dev, (void *)&pass0, (void *)&npasses, &lazy_passes, &hist, &misc, &status};
-        const void *fn = vals_a ? (small ? (const void *)os_sort_all_kernel<true, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<true, RS_ROWS_LARGE>)
-                                : (small ? (const void *)os_sort_all_kernel<false, RS_ROWS_SMALL> : (const void *)os_sort_all_kernel<false, RS_ROWS_LARGE>);
+        const void *fn = vals_a ? rs_all_kernel_for<true>(rows) : rs_all_kernel_for<false>(rows);
         const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)coop_ctas);
         if ((e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RS_THREADS), args, 0, st)) != cudaSuccess) return e;
         if (launches) *launches += (hist_ready ? 0 : 1) + 1;
@@ -546,8 +560,8 @@ static inline cudaError_t radix_sort_u64(unsigned long long *keys_a, unsigned lo
 #define RS_LAUNCH(V, R)                                                                                                   \
     os_pass_kernel<V, R><<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, vin, n, n_dev, shift, pass_id, hist + p * 256, misc + pass_id, \
                                                                   status, kout, vout, run_if)
-            if (vals_a) { if (small) RS_LAUNCH(true, RS_ROWS_SMALL); else RS_LAUNCH(true, RS_ROWS_LARGE); }
-            else        { if (small) RS_LAUNCH(false, RS_ROWS_SMALL); else RS_LAUNCH(false, RS_ROWS_LARGE); }
+            if (vals_a) { if (rows == 2) RS_LAUNCH(true, 2); else if (rows == 4) RS_LAUNCH(true, 4); else if (rows == RS_ROWS_SMALL) RS_LAUNCH(true, RS_ROWS_SMALL); else RS_LAUNCH(true, RS_ROWS_LARGE); }
+            else        { if (rows == 2) RS_LAUNCH(false, 2); else if (rows == 4) RS_LAUNCH(false, 4); else if (rows == RS_ROWS_SMALL) RS_LAUNCH(false, RS_ROWS_SMALL); else RS_LAUNCH(false, RS_ROWS_LARGE); }
 #undef RS_LAUNCH
             unsigned long long *tk = kin; kin = kout; kout = tk;
             unsigned *tv = vin; vin = vout; vout = tv;
