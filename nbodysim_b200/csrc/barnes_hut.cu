@@ -29,6 +29,7 @@
 #include "force_f32_fast.cuh"      // integrate_body_f32
 #include "radix_sort.cuh"
 #include "cluster_prims.cuh"
+#include "collide.cuh"              // the fused walk enters the new positions into the collision pass's screening grid
 #include <cstring>
 
 namespace nb {
@@ -1213,6 +1214,9 @@ struct BhFuse {
     float *posm_next, *vel, *acc;
     float G;
     IntegParams ip;
+    int insert;          // the collision pass follows: enter the new position into its screening grid (collide.cuh)
+    ColArgs ca;
+    ColGrid cg;
 };
 
 constexpr int WALK_THREADS = 128;
@@ -1221,7 +1225,8 @@ constexpr int WALK_THREADS = 128;
 // Simulation::iterate after attract(): the same integrate_body_f32 as the stand-alone integrator, same operand order.
 template <int DIMS, bool FUSE>
 __device__ __forceinline__ void bh_walk_finish(const float *__restrict__ posm, size_t g, unsigned body, size_t shard_start, float px,
-                                               float py, float pz, float ax, float ay, float az, float *__restrict__ accp, const BhFuse &fz)
+                                               float py, float pz, float ax, float ay, float az, float *__restrict__ accp, const BhFuse &fz,
+                                               float &new_x, float &new_y)
 {
     if (!FUSE) {
         const size_t l = blk_index(body - shard_start, 0);
@@ -1233,6 +1238,7 @@ __device__ __forceinline__ void bh_walk_finish(const float *__restrict__ posm, s
     float vx = fz.vel[g], vy = fz.vel[g + BLK], vz = fz.vel[g + 2 * BLK];
     integrate_body_f32(qx, qy, qz, vx, vy, vz, gx, gy, gz, fz.ip);
     fz.posm_next[g] = qx; fz.posm_next[g + BLK] = qy; fz.posm_next[g + 2 * BLK] = qz; fz.posm_next[g + 3 * BLK] = posm[g + 3 * BLK];
+    new_x = qx; new_y = qy;
     fz.vel[g] = vx; fz.vel[g + BLK] = vy; fz.vel[g + 2 * BLK] = vz;
     fz.acc[g] = gx; fz.acc[g + BLK] = gy; fz.acc[g + 2 * BLK] = gz;
 }
@@ -1246,9 +1252,9 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
 {
     if (n_dev) n = min(n, (size_t)*n_dev);                  // sharded: `idx` is the compacted list of this GPU's targets
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const unsigned body = idx[s];                           // targets in Z-order: neighbouring threads walk alike
-    if (body < shard_start || body >= shard_start + shard_count) return;
+    const unsigned body = s < n ? idx[s] : 0u;              // targets in Z-order: neighbouring threads walk alike
+    const bool active = s < n && body >= shard_start && body < shard_start + shard_count;
+    if (!(FUSE && fz.insert) && !active) return;            // (with the grid insert the whole warp stays: see the end)
     const size_t g = blk_index(body, 0);
     const float px = posm[g], py = posm[g + BLK], pz = (DIMS == 3) ? posm[g + 2 * BLK] : 0.f;
     float ax = 0.f, ay = 0.f, az = 0.f;
@@ -1264,7 +1270,7 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
     float4 nd;
     uint4 na;
     bh_load_node(nodes, 0u, nd, na);
-    for (;;) {
+    while (active) {
         ++nvis;
         float dx, dy, dz, d_sq;
         const bool far = bh_open_test<DIMS, REFCOMPAT>(nd, __uint_as_float(na.x), px, py, pz, t_sq, dx, dy, dz, d_sq);
@@ -1279,8 +1285,20 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
         if (!more) break;
         nd = nd2; na = na2; i = nxt;
     }
-    if (visits) atomicAdd(visits, (unsigned long long)nvis);
-    bh_walk_finish<DIMS, FUSE>(posm, g, body, shard_start, px, py, pz, ax, ay, az, accp, fz);
+    float new_x = 0.f, new_y = 0.f;
+    if (active) {
+        if (visits) atomicAdd(visits, (unsigned long long)nvis);
+        bh_walk_finish<DIMS, FUSE>(posm, g, body, shard_start, px, py, pz, ax, ay, az, accp, fz, new_x, new_y);
+    }
+    if (FUSE && fz.insert) {
+        // Simulation::step(): iterate() ; collide().  The pass starts by entering every body into its screening grid under
+        // the cells and strips it covers; the thread that just computed a body's new position does that here instead of a
+        // kernel of its own (a body covering many units is shared out over the warp's lanes, hence all 32 stay to the end).
+        ColBody b;
+        b.x = new_x; b.y = new_y; b.r = active ? fz.vel[g + 3 * BLK] : 0.f;
+        unsigned unused = 0;
+        col_grid_lane_units(fz.ca, fz.cg, active, b, body, true, ColInsertOp(), unused);
+    }
 }
 
 // Warp-cooperative walk.  The 32 lanes of a warp hold 32 targets that are neighbours in Z-order; the
@@ -1636,7 +1654,10 @@ cudaError_t BhWorkspace::walk(const float *posm, size_t n, float theta, float ep
     const int fix = fix_near_leaves ? 1 : 0;
     BhFuse fz;
     memset(&fz, 0, sizeof fz);
-    if (fuse) { fz.posm_next = fuse->posm_next; fz.vel = fuse->vel; fz.acc = fuse->acc; fz.G = fuse->G; fz.ip = fuse->ip; }
+    if (fuse) {
+        fz.posm_next = fuse->posm_next; fz.vel = fuse->vel; fz.acc = fuse->acc; fz.G = fuse->G; fz.ip = fuse->ip;
+        if (fuse->col_args && fuse->col_grid) { fz.insert = 1; fz.ca = *fuse->col_args; fz.cg = *fuse->col_grid; }
+    }
     if (fuse) {
         if (dims == 3) bh_walk_t<3, true>(*this, posm, n, t_sq, e_sq, refcompat, fix, shard_start, shard_count, accp, visits, fz, st);
         else bh_walk_t<2, true>(*this, posm, n, t_sq, e_sq, refcompat, fix, shard_start, shard_count, accp, visits, fz, st);

@@ -199,7 +199,20 @@ ColArgs CollideWorkspace::args(float *posm, float *vel, size_t n) const
 // entries and candidate pairs stay on the device -- the grids are sized for the buffers' capacities, the kernels
 // and sorts read the live counts (CTAs beyond them exit at once) -- so the pass neither stalls the stream for a
 // read-back nor prevents a whole Simulation::step() from being captured in a CUDA graph.
-cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches)
+ColGrid CollideWorkspace::grid_view() const
+{
+    ColGrid g;
+    g.flags = (unsigned *)grid;
+    g.tkeys = (unsigned long long *)((char *)grid + 64);
+    g.heads = (unsigned *)((char *)grid + 64 + (size_t)table_slots * 8);
+    g.edata = (float4 *)grid_links; g.enext = (unsigned *)((char *)grid_links + (size_t)entry_cap * 16);
+    g.tmask = table_slots - 1; g.ecap = entry_cap;
+    return g;
+}
+
+cudaError_t CollideWorkspace::prepare(cudaStream_t st) { return cudaMemsetAsync(grid, 0, grid_bytes, st); }
+
+cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches, bool grid_filled)
 {
     if (n == 0 || n > n_cap) return cudaErrorInvalidValue;
     cudaError_t e;
@@ -207,15 +220,13 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
     ColArgs a = args(posm, vel, n);
     const int key_bits = std::min(64, (((a.rooted ? 3 : 2) * a.idx_bits + 7) / 8) * 8);
     // the hash grid over the bodies' cells; what follows it is gated on whether anything overlaps
-    ColGrid g;
-    g.flags = (unsigned *)grid;
-    g.tkeys = (unsigned long long *)((char *)grid + 64);
-    g.heads = (unsigned *)((char *)grid + 64 + (size_t)table_slots * 8);
-    g.edata = (float4 *)grid_links; g.enext = (unsigned *)((char *)grid_links + (size_t)entry_cap * 16);
-    g.tmask = table_slots - 1; g.ecap = entry_cap;
-    if ((e = cudaMemsetAsync(grid, 0, grid_bytes, st)) != cudaSuccess) return e;
+    const ColGrid g = grid_view();
     const unsigned gb = (unsigned)((n + 255) / 256);
-    col_grid_insert_kernel<<<gb, 256, 0, st>>>(a, g);
+    if (!grid_filled) {
+        if ((e = prepare(st)) != cudaSuccess) return e;
+        col_grid_insert_kernel<<<gb, 256, 0, st>>>(a, g);
+        if (launches) *launches += 1;
+    }
     if (single_cta) {   // small scene: sweep pairs straight from the grid, everything else in one CTA
         col_grid_pairs_kernel<<<gb, 256, 0, st>>>(a, g);
         // an explicit cluster of ONE CTA: its sort uses the cluster primitives of cluster_prims.cuh
@@ -227,11 +238,11 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
         at.val.clusterDim.x = 1; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         if ((e = cudaLaunchKernelEx(&cfg, col_finish_kernel, a, g, (unsigned long long *)pairs, (unsigned *)ranks, key_bits)) != cudaSuccess) return e;
-        if (launches) *launches += 3;
+        if (launches) *launches += 2;
         return cudaGetLastError();
     }
     col_grid_detect_kernel<<<gb, 256, 0, st>>>(a, g);
-    if (launches) *launches += 2;
+    if (launches) *launches += 1;
     const unsigned gn = (unsigned)((n + 255) / 256), ge = (entry_cap + 255) / 256;
     col_init_kernel<<<gn, 256, 0, st>>>(a);
     col_entries_kernel<<<gn, 256, 0, st>>>(a);

@@ -14,26 +14,8 @@ constexpr float COL_CELL = 600.0f;   // SpatialGrid::CELL_SIZE, Simulation.hpp:2
 constexpr int COL_GROUP_BITS = 16;
 constexpr unsigned long long COL_GROUP_MASK = (1ull << COL_GROUP_BITS) - 1ull;
 
-// counters: [0] cell entries, [1] pairs kept (hot components), [2] overflow flag, [3] pairs resolved (narrow test
-// passed), [4] sweep pairs that overlap now
-struct ColArgs {
-    float *posm, *vel;                     // blocked SoA; radius rides in vel's 4th component
-    unsigned n;
-    unsigned long long *keys_in;           // cell entries as produced (hash, body) ...
-    unsigned *vals_in;
-    const unsigned long long *keys;        // ... and sorted by hash
-    const unsigned *vals;
-    unsigned entry_cap;
-    unsigned long long *pairs;             // pair keys as produced
-    unsigned pair_cap;
-    unsigned char *hot;                    // [0, n): body is in a pair that overlaps now ; [n, 2n): component label is hot
-    unsigned *parent;                      // union-find forest over the bodies
-    unsigned *counters;
-    unsigned *status;                      // host-visible sticky flags ([1] = collision buffers overflowed), may be null
-    const unsigned *gate;                  // screening result ([0] = pairs sharing a cell that overlap now); 0 there: nothing to do
-    int idx_bits, rooted;
-    float strip;                           // width of the x strips the screening grid splits a cell into (0: none)
-};
+// (ColArgs, the arguments of a pass, and ColGrid, the screening hash grid, are declared in kernels.h: the fused Barnes-Hut
+// walk and the per-step driver handle them too)
 
 __device__ __forceinline__ unsigned long long col_hash(int x, int y)
 {
@@ -64,14 +46,6 @@ __device__ __forceinline__ void col_overflow(const ColArgs &a)
 // addressing, one linked list of bodies per cell), then every body tests the later-numbered bodies of its cells.  The
 // test is resolve()'s own, on every pair sharing a cell: a superset of the sweep pairs, so a miss is impossible and a
 // false alarm merely runs the full pass, which applies the reference's rules exactly.
-struct ColGrid {
-    unsigned long long *tkeys;             // [tmask + 1]  0 = empty, else 1 << 32 | cell hash
-    unsigned *heads;                       // [tmask + 1]  entry index + 1 of the cell's list head, 0 = none
-    unsigned *enext;                       // [ecap]       list links (entry index + 1)
-    float4 *edata;                         // [ecap]       (x, y, radius, body index bits) of the entry's body: one load per list element
-    unsigned *flags;                       // [0] overlapping pairs seen, [1] entries used       (zeroed with the table)
-    unsigned tmask, ecap;
-};
 
 __device__ __forceinline__ bool col_cell_range(const ColBody &b, int &minX, int &maxX, int &minY, int &maxY)
 {
@@ -154,6 +128,43 @@ struct ColDetectOp {
 // the three passes share one driver: a body covering one or two (cell, strip) units handles them itself; a body covering
 // more -- the shipped scene's central mass of radius 200 sits on 4 cells x 11 strips of the busiest lists -- would be the
 // kernel's critical path, so its units are spread over the lanes of its warp
+// One body per lane, ALL 32 lanes of the warp calling (valid = false: the lane has no body).
+template <typename Op>
+__device__ __forceinline__ void col_grid_lane_units(const ColArgs &a, const ColGrid &g, bool valid, const ColBody &b, unsigned i, bool report,
+                                                    const Op &op, unsigned &acc)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    int minX = 0, maxX = -1, minY = 0, maxY = -1, s0 = 0, s1 = -1;
+    unsigned units = 0;
+    if (valid) {
+        if (col_cell_range(b, minX, maxX, minY, maxY) && col_strip_range(b, a.strip, minX, maxX, minY, maxY, s0, s1))
+            units = (unsigned)((maxX - minX + 1) * (maxY - minY + 1) * (s1 - s0 + 1));
+        else if (report) { col_overflow(a); atomicAdd(&g.flags[0], 1u); }          // let the full pass report it
+    }
+    if (units <= 2u) {
+        for (int y = minY; y <= maxY && units; ++y)
+            for (int x = minX; x <= maxX; ++x)
+                for (int st = s0; st <= s1; ++st) op(a, g, b, i, x, y, st, acc);
+    }
+    unsigned bigs = __ballot_sync(0xffffffffu, units > 2u);
+    while (bigs) {
+        const int src = __ffs(bigs) - 1;
+        bigs &= bigs - 1u;
+        ColBody B;
+        B.x = __shfl_sync(0xffffffffu, b.x, src); B.y = __shfl_sync(0xffffffffu, b.y, src); B.r = __shfl_sync(0xffffffffu, b.r, src);
+        const unsigned bi = __shfl_sync(0xffffffffu, i, src);
+        const int bx0 = __shfl_sync(0xffffffffu, minX, src), bx1 = __shfl_sync(0xffffffffu, maxX, src);
+        const int by0 = __shfl_sync(0xffffffffu, minY, src);
+        const int bs0 = __shfl_sync(0xffffffffu, s0, src), bs1 = __shfl_sync(0xffffffffu, s1, src);
+        const unsigned total = __shfl_sync(0xffffffffu, units, src);
+        const unsigned nx = (unsigned)(bx1 - bx0 + 1), ns = (unsigned)(bs1 - bs0 + 1);
+        for (unsigned u = lane; u < total; u += 32u) {
+            const unsigned st = u % ns, xy = u / ns;
+            op(a, g, B, bi, bx0 + (int)(xy % nx), by0 + (int)(xy / nx), bs0 + (int)st, acc);
+        }
+    }
+}
+
 template <typename Op>
 __device__ __forceinline__ void col_grid_for_each_unit(const ColArgs &a, const ColGrid &g, unsigned gtid, unsigned gthreads, bool report,
                                                        const Op &op, unsigned &acc)
@@ -162,35 +173,8 @@ __device__ __forceinline__ void col_grid_for_each_unit(const ColArgs &a, const C
     for (unsigned base = gtid - lane; base < a.n; base += gthreads) {                 // trip count uniform over the warp
         const unsigned i = base + lane;
         ColBody b; b.x = 0.f; b.y = 0.f; b.r = 0.f;
-        int minX = 0, maxX = -1, minY = 0, maxY = -1, s0 = 0, s1 = -1;
-        unsigned units = 0;
-        if (i < a.n) {
-            b = col_load(a.posm, a.vel, i);
-            if (col_cell_range(b, minX, maxX, minY, maxY) && col_strip_range(b, a.strip, minX, maxX, minY, maxY, s0, s1))
-                units = (unsigned)((maxX - minX + 1) * (maxY - minY + 1) * (s1 - s0 + 1));
-            else if (report) { col_overflow(a); atomicAdd(&g.flags[0], 1u); }      // let the full pass report it
-        }
-        if (units <= 2u) {
-            for (int y = minY; y <= maxY && units; ++y)
-                for (int x = minX; x <= maxX; ++x)
-                    for (int st = s0; st <= s1; ++st) op(a, g, b, i, x, y, st, acc);
-        }
-        unsigned bigs = __ballot_sync(0xffffffffu, units > 2u);
-        while (bigs) {
-            const int src = __ffs(bigs) - 1;
-            bigs &= bigs - 1u;
-            ColBody B;
-            B.x = __shfl_sync(0xffffffffu, b.x, src); B.y = __shfl_sync(0xffffffffu, b.y, src); B.r = __shfl_sync(0xffffffffu, b.r, src);
-            const int bx0 = __shfl_sync(0xffffffffu, minX, src), bx1 = __shfl_sync(0xffffffffu, maxX, src);
-            const int by0 = __shfl_sync(0xffffffffu, minY, src);
-            const int bs0 = __shfl_sync(0xffffffffu, s0, src), bs1 = __shfl_sync(0xffffffffu, s1, src);
-            const unsigned total = __shfl_sync(0xffffffffu, units, src);
-            const unsigned nx = (unsigned)(bx1 - bx0 + 1), ns = (unsigned)(bs1 - bs0 + 1);
-            for (unsigned u = lane; u < total; u += 32u) {
-                const unsigned st = u % ns, xy = u / ns;
-                op(a, g, B, base + (unsigned)src, bx0 + (int)(xy % nx), by0 + (int)(xy / nx), bs0 + (int)st, acc);
-            }
-        }
+        if (i < a.n) b = col_load(a.posm, a.vel, i);
+        col_grid_lane_units(a, g, i < a.n, b, i, report, op, acc);
     }
 }
 

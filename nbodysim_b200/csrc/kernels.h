@@ -133,10 +133,45 @@ cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, si
 
 // fused kick-drift epilogue of the Barnes-Hut walk (small scenes on one GPU): where the walk threads find velocities
 // and store the new state
+// ---- collision pass (collide.cu / collide.cuh): the arguments of a pass and its screening hash grid
+// counters: [0] cell entries, [1] pairs kept (hot components), [2] overflow flag, [3] pairs resolved (narrow test
+// passed), [4] sweep pairs that overlap now
+struct ColArgs {
+    float *posm, *vel;                     // blocked SoA; radius rides in vel's 4th component
+    unsigned n;
+    unsigned long long *keys_in;           // cell entries as produced (hash, body) ...
+    unsigned *vals_in;
+    const unsigned long long *keys;        // ... and sorted by hash
+    const unsigned *vals;
+    unsigned entry_cap;
+    unsigned long long *pairs;             // pair keys as produced
+    unsigned pair_cap;
+    unsigned char *hot;                    // [0, n): body is in a pair that overlaps now ; [n, 2n): component label is hot
+    unsigned *parent;                      // union-find forest over the bodies
+    unsigned *counters;
+    unsigned *status;                      // host-visible sticky flags ([1] = collision buffers overflowed), may be null
+    const unsigned *gate;                  // screening result ([0] = pairs sharing a cell that overlap now); 0 there: nothing to do
+    int idx_bits, rooted;
+    float strip;                           // width of the x strips the screening grid splits a cell into (0: none)
+};
+
+// open-addressing table keyed by (cell, x strip), one linked list of bodies per key (collide.cuh)
+struct ColGrid {
+    unsigned long long *tkeys;             // [tmask + 1]  0 = empty, else 1 << 32 | cell hash
+    unsigned *heads;                       // [tmask + 1]  entry index + 1 of the cell's list head, 0 = none
+    unsigned *enext;                       // [ecap]       list links (entry index + 1)
+    float4 *edata;                         // [ecap]       (x, y, radius, body index bits) of the entry's body: one load per list element
+    unsigned *flags;                       // [0] overlapping pairs seen, [1] entries used       (zeroed with the table)
+    unsigned tmask, ecap;
+};
+
 struct BhFuseArgs {
     float *posm_next, *vel, *acc;
     float G;
     IntegParams ip;
+    // collision pass follows: the walk threads also enter their (new) positions into its screening grid
+    const ColArgs *col_args = nullptr;
+    const ColGrid *col_grid = nullptr;
 };
 
 // Barnes-Hut path (barnes_hut.cu): per-GPU workspace holding sorted keys and the pre-order node array
@@ -173,7 +208,6 @@ struct BhWorkspace {
 };
 
 // collision pass (collide.cu)
-struct ColArgs;
 struct CollideWorkspace {
     size_t n_cap = 0;
     unsigned entry_cap = 0, pair_cap = 0;
@@ -188,7 +222,10 @@ struct CollideWorkspace {
     cudaError_t alloc(size_t n, int single_cta_mode, size_t single_cta_max_n);
     void release();
     ColArgs args(float *posm, float *vel, size_t n) const;
-    cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches);
+    ColGrid grid_view() const;
+    cudaError_t prepare(cudaStream_t st);    // clears the screening grid (before whoever fills it)
+    // `grid_filled`: prepare() was called and the bodies are in the grid already (the fused Barnes-Hut walk entered them)
+    cudaError_t run(float *posm, float *vel, size_t n, cudaStream_t st, int *launches, bool grid_filled = false);
     cudaError_t stats(cudaStream_t st, unsigned out[4]);
 };
 

@@ -405,7 +405,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         CU(cudaSetDevice(d.device));
         const bool prof = profile && (&d == &ctx->devs[0]);
         if (prof) CU(cudaEventRecord(d.ev_t[0], d.stream));
-        bool waited = false, bh_fused = false;
+        bool waited = false, bh_fused = false, col_grid_filled = false;
         if (ctx->bh) {
             if (d.gathered_pending) { CU(wait_remote(d)); waited = true; }
             int nl = 0;
@@ -417,9 +417,19 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             // small scenes on one GPU: the walk threads integrate their own targets (no separate integrator launch)
             bh_fused = ctx->world == 1 && !acc_only && !d.bh.warp_walk && ctx->n_padded <= 131072 && ctx->p.fuse_integrator != 0;
             BhFuseArgs fa;
+            ColArgs col_a;
+            ColGrid col_g;
             if (bh_fused) {
                 fa.posm_next = (float *)d.posm[d.cur ^ 1]; fa.vel = (float *)d.vel; fa.acc = (float *)d.acc;
                 fa.G = ctx->p.G; fa.ip = make_ip(ctx, dt);
+                static const bool fuse_insert_off = getenv("NBODY_BH_FUSE_INSERT") && atoi(getenv("NBODY_BH_FUSE_INSERT")) == 0;   // A/B switch
+                if (ctx->p.collide && !fuse_insert_off) {   // Simulation::step(): the walk threads also fill the collision pass's screening grid
+                    CU(d.col.prepare(d.stream));
+                    col_a = d.col.args((float *)d.posm[d.cur ^ 1], (float *)d.vel, ctx->n);
+                    col_g = d.col.grid_view();
+                    fa.col_args = &col_a; fa.col_grid = &col_g;
+                    col_grid_filled = true;
+                }
             }
             CU(d.bh.walk((const float *)d.posm[d.cur], ctx->n, ctx->p.theta, ctx->p.eps, refc, ctx->p.bh_fix_near_leaves != 0,
                          d.shard_start, d.shard_count, (float *)d.accp, prof ? d.walk_visits : nullptr, bh_fused ? &fa : nullptr, d.stream));
@@ -503,7 +513,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         if (prof) CU(cudaEventRecord(d.ev_t[4], d.stream));
         if (ctx->p.collide && !acc_only) { // Simulation::step(): iterate(dt) ; collide()
             int nl = 0;
-            CU(d.col.run((float *)d.posm[d.cur ^ 1], (float *)d.vel, ctx->n, d.stream, &nl));
+            CU(d.col.run((float *)d.posm[d.cur ^ 1], (float *)d.vel, ctx->n, d.stream, &nl, col_grid_filled));
             ctx->launches += (unsigned long long)nl;
         }
         if (prof) CU(cudaEventRecord(d.ev_t[2], d.stream));
