@@ -323,7 +323,7 @@ def bh_native(torch, dev, local, cpu_seconds, with_cpu=True):
                    gpu_launches_per_step=(i1["kernel_launches"] - i0["kernel_launches"]) / K, bh_nodes=i1["bh_nodes"])
         # single steps with the L2 flushed before each (cold tree and bodies), phase times from CUDA events in the library
         ph = {"build": [], "walk": [], "integrate": [], "collide": []}
-        visits = 0
+        visits = visits_max = 0
         for _ in range(10):
             flush.fill_(1); s.sync(); torch.cuda.synchronize()
             s.profile_next_step(True)
@@ -332,6 +332,7 @@ def bh_native(torch, dev, local, cpu_seconds, with_cpu=True):
             ph["build"].append(inf["last_bh_build_ms"]); ph["walk"].append(inf["last_force_ms"] - inf["last_bh_build_ms"])
             ph["integrate"].append(inf["last_integ_ms"]); ph["collide"].append(inf["last_collide_ms"])
             visits = inf["last_bh_visits"]
+            visits_max = inf.get("last_bh_visits_max", 0)
         med = {k: statistics.median(v) for k, v in ph.items()}
         out["l2_flushed_single_step"] = {"ms_per_step": sum(med.values()), "phases_ms": med,
                                          "note": "256 MiB write before every step, plain launches (no graph), CUDA events around each phase"}
@@ -357,12 +358,14 @@ def bh_native(torch, dev, local, cpu_seconds, with_cpu=True):
             "kernel": "bh_walk_kernel", "bound": "l2", "achieved": ach, "peak": peak, "unit": "GB/s",
             "frac": ach / peak if ach else None, "traffic": None,
             "algorithmic_bytes": bytes_per_launch, "visits_per_launch": visits, "visits_per_target": visits / n,
-            "kernel_ms": walk_ms,
+            "kernel_ms": walk_ms, "longest_walk_visits": visits_max,
+            "kernel_ms_note": "cold caches; the kernel also integrates its targets and enters them into the collision pass's grid (fused epilogues)",
             "peak_source": f"L2 slice throughput cap {L2_BYTES_PER_CLK:.0f} B/clk x {clk / 1e6:.0f} MHz (B300_MICROARCH.md; not in "
                            "MEASURED_PEAKS.json, which has HBM and bf16 only); the 2 MB tree never leaves L2, so HBM does not bound it",
-            "latency_floor_ms": 1e3 * (visits / n) * L2_HIT_CYCLES / clk,
-            "why": "25,000 targets are 782 warps on 592 schedulers: nothing hides the ~250-cycle L2 hit of each of the ~"
-                   f"{visits / max(n, 1):.0f} dependent visits of a walk, so the kernel sits at its latency floor, far below the L2 bandwidth roof",
+            "latency_floor_ms": 1e3 * max(visits_max, visits / n) * L2_HIT_CYCLES / clk,
+            "why": "one thread per target, every visit a load that depends on the previous opening test: the kernel lasts as long as the "
+                   f"LONGEST walk ({visits_max} visits; mean {visits / max(n, 1):.0f}) x (L2 hit ~{L2_HIT_CYCLES:.0f} cycles + the test), whatever the "
+                   "occupancy (thin warps, prefetch and speculation measured without gain, profiles/r2_walk_experiments.txt) -- latency-, not bandwidth-bound",
         }
     if with_cpu:
         cpu = cpu_reference_step(host0, BH_THETA, BH_EPS, BH_DT, True, cpu_seconds)

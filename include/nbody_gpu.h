@@ -153,6 +153,7 @@ typedef struct nbody_info {
     float    last_bh_build_ms;/* Barnes-Hut: the tree-build part of last_force_ms (keys, sort, cells, centres of mass) */
     float    last_collide_ms; /* device time of the collision pass of the last profiled step (collide = 1) */
     uint64_t last_bh_visits;  /* Barnes-Hut: node records visited by the walk of the last profiled step, all targets */
+    uint64_t last_bh_visits_max; /* ... and by the longest single walk (the per-thread walk kernel's critical path) */
 } nbody_info;
 
 /* Fill *p with the reference's shipped parameters (Simulation.hpp:59,120-124; G=1, dims=2,

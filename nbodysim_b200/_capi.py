@@ -84,6 +84,7 @@ class NbodyInfo(C.Structure):
         ("last_bh_build_ms", C.c_float),
         ("last_collide_ms", C.c_float),
         ("last_bh_visits", C.c_uint64),
+        ("last_bh_visits_max", C.c_uint64),
     ]
 
     def as_dict(self):

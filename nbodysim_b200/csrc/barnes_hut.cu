@@ -1287,7 +1287,11 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
     }
     float new_x = 0.f, new_y = 0.f;
     if (active) {
-        if (visits) atomicAdd(visits, (unsigned long long)nvis);
+        if (visits) {                                       // profiled steps only: one atomic pair per warp, not per thread
+            const unsigned am = __activemask();
+            const unsigned sum = __reduce_add_sync(am, nvis), mx = __reduce_max_sync(am, nvis);
+            if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) { atomicAdd(visits, (unsigned long long)sum); atomicMax(visits + 1, (unsigned long long)mx); }
+        }
         bh_walk_finish<DIMS, FUSE>(posm, g, body, shard_start, px, py, pz, ax, ay, az, accp, fz, new_x, new_y);
     }
     if (FUSE && fz.insert) {
@@ -1350,7 +1354,7 @@ bh_walk_warp_kernel(const float *__restrict__ posm, const unsigned *__restrict__
         const size_t l = blk_index(body - shard_start, 0);
         accp[l] = ax; accp[l + BLK] = ay; accp[l + 2 * BLK] = az;
     }
-    if (visits && nvis) atomicAdd(visits, (unsigned long long)nvis);
+    if (visits && nvis) { atomicAdd(visits, (unsigned long long)nvis); atomicMax(visits + 1, (unsigned long long)nvis); }
 }
 
 // Several GPUs: every GPU builds the whole tree but walks only the targets of its shard (a range of BODY indices,
@@ -1461,9 +1465,13 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
         // small scenes: the (child, parent) edges left to the climb are listed (word 8 of the zeroed box region counts them) and
         // ONE CTA finishes the top of the tree in shared memory; NBODY_BH_CTA_CLIMB=0 keeps the atomic climb at every size
         static const bool cta_climb_off = getenv("NBODY_BH_CTA_CLIMB") && atoi(getenv("NBODY_BH_CTA_CLIMB")) == 0;
-        static const bool cta_climb_ok = cudaFuncSetAttribute(bh_top_cta_kernel<DIMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtcSmem<DIMS>)) == cudaSuccess &&
-                                         cudaFuncSetAttribute(bh_top_cta_kernel<DIMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtcSmem<DIMS>)) == cudaSuccess;
-        const bool cta_climb = !cta_climb_off && cta_climb_ok && n <= 32768;
+        if (w.top_cta_state == 0) {                          // once per workspace, i.e. per device: function attributes are per device
+            const bool ok = cudaFuncSetAttribute(bh_top_cta_kernel<DIMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtcSmem<DIMS>)) == cudaSuccess &&
+                            cudaFuncSetAttribute(bh_top_cta_kernel<DIMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtcSmem<DIMS>)) == cudaSuccess;
+            if (!ok) cudaGetLastError();
+            w.top_cta_state = ok ? 1 : -1;
+        }
+        const bool cta_climb = !cta_climb_off && w.top_cta_state > 0 && n <= 32768;
 #define BHL_ARGS posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,      \
                  (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, \
                  w.node_cap, w.status, (unsigned *)w.climb_start, cta_climb ? (uint4 *)w.node_owner : nullptr, (unsigned *)w.box + 8, w.node_cap / 4

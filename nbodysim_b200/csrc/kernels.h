@@ -185,6 +185,7 @@ struct BhWorkspace {
     void *node_slot_cells = nullptr; // centre-of-mass pass: subtree sizes riding up with the centres of mass (-> skip pointers)
     void *shard_targets = nullptr; // several GPUs: this GPU's targets compacted out of the Z-order (+ their count)
     void *node_owner = nullptr;  // single-cluster build: the sorted body that owns each cell
+    int top_cta_state = 0;       // one-CTA top-of-tree kernel: 0 = not set up on this device yet, 1 = usable, -1 = not
     void *climb_start = nullptr; // per sorted body: the cell where its chain leaves the CTA-local part of the centre-of-mass pass
     int cluster_ctas = 0;        // > 0: scenes of up to cluster_ctas x 49152 bodies are built by ONE cluster kernel of that many CTAs
     static int cluster_ctas_available(int dims);

@@ -94,7 +94,7 @@ struct nbody_ctx {
     int profile_next = 0;
     unsigned long long short_calls = 0;  // nbody_gpu_step calls of fewer than 8 steps so far
     float last_force_ms = 0.f, last_integ_ms = 0.f, last_build_ms = 0.f, last_collide_ms = 0.f;
-    unsigned long long last_visits = 0;
+    unsigned long long last_visits = 0, last_visits_max = 0;
     char err[512];
     nbody_ctx() { err[0] = 0; }
 };
@@ -249,7 +249,7 @@ int alloc_device(nbody_ctx *ctx, Dev &d)
     CU(cudaMalloc(&d.accp, shard * (size_t)std::max(1, d.nslots)));
     CU(cudaMalloc(&d.aos, ctx->n_padded * sizeof(nbody_body_t)));
     CU(cudaMalloc(&d.energy5, 5 * sizeof(double)));
-    CU(cudaMalloc(&d.walk_visits, sizeof(unsigned long long)));
+    CU(cudaMalloc(&d.walk_visits, 2 * sizeof(unsigned long long)));     // total, longest walk
     // sticky overflow flags the kernels raise and sync / download / energy check: host memory mapped into the device
     // address space, so checking them costs no copy
     CU(cudaHostAlloc((void **)&d.h_status, 64, cudaHostAllocMapped));
@@ -412,7 +412,7 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
             CU(d.bh.build((const float *)d.posm[d.cur], ctx->n, d.stream, &nl));
             if (prof) {
                 CU(cudaEventRecord(d.ev_t[3], d.stream));
-                CU(cudaMemsetAsync(d.walk_visits, 0, sizeof(unsigned long long), d.stream));
+                CU(cudaMemsetAsync(d.walk_visits, 0, 2 * sizeof(unsigned long long), d.stream));
             }
             // small scenes on one GPU: the walk threads integrate their own targets (no separate integrator launch)
             bh_fused = ctx->world == 1 && !acc_only && !d.bh.warp_walk && ctx->n_padded <= 131072 && ctx->p.fuse_integrator != 0;
@@ -1071,10 +1071,11 @@ int nbody_gpu_step(nbody_ctx *ctx, float dt, int nsteps)
             CU(cudaEventElapsedTime(&ctx->last_integ_ms, d.ev_t[1], d.ev_t[4]));
             CU(cudaEventElapsedTime(&ctx->last_collide_ms, d.ev_t[4], d.ev_t[2]));
             ctx->last_build_ms = 0.f;
-            ctx->last_visits = 0;
+            ctx->last_visits = 0; ctx->last_visits_max = 0;
             if (ctx->bh) {
                 CU(cudaEventElapsedTime(&ctx->last_build_ms, d.ev_t[0], d.ev_t[3]));
                 CU(cudaMemcpy(&ctx->last_visits, d.walk_visits, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                CU(cudaMemcpy(&ctx->last_visits_max, d.walk_visits + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             }
             ctx->profile_next = 0;
         }
@@ -1251,6 +1252,7 @@ int nbody_gpu_get_info(nbody_ctx *ctx, nbody_info *info)
     info->last_bh_build_ms = ctx->last_build_ms;
     info->last_collide_ms = ctx->last_collide_ms;
     info->last_bh_visits = ctx->last_visits;
+    info->last_bh_visits_max = ctx->last_visits_max;
     if (ctx->bh) {
         unsigned m = 0;
         cudaSetDevice(ctx->devs[0].device);

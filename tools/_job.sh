@@ -1,1 +1,1 @@
-for v in 1 0 1 0; do NBODY_BH_FUSE_INSERT=$v python tools/bench_refscene.py 25000 2>&1 | sed -n 2p | cut -c1-330; done
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_multiproc.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
