@@ -763,7 +763,7 @@ template <int DIMS, bool TRACE>
 __global__ void __launch_bounds__(BTC_THREADS, 1)
 bh_top_cta_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned *__restrict__ count, const uint4 *__restrict__ edges,
                   const unsigned *__restrict__ nedges, unsigned edge_cap, const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive,
-                  unsigned cap, unsigned long long *trace)
+                  unsigned cap, unsigned edge_limit, unsigned long long *trace)
 {
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
     extern __shared__ __align__(16) unsigned char btc_raw[];
@@ -772,7 +772,7 @@ bh_top_cta_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, co
     const unsigned tid = threadIdx.x;
     const unsigned total = offs[n], m = min(total, cap), E = *nedges;
     if (E == 0u) return;                                               // everything was local (n <= halo)
-    if (E > (unsigned)BTC_MAX_EDGES || E > edge_cap || total > cap) {  // too many edges (or a truncated tree): the atomic climb, by this CTA
+    if (E > edge_limit || E > edge_cap || total > cap) {               // too many edges (or a truncated tree): the atomic climb, by this CTA
         for (size_t s = tid; s < n; s += BTC_THREADS) {
             if (count[s] == 0) continue;
             const unsigned c = gstart[s];
@@ -1472,6 +1472,8 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
             w.top_cta_state = ok ? 1 : -1;
         }
         const bool cta_climb = !cta_climb_off && w.top_cta_state > 0 && n <= 32768;
+        // (tests force the kernel's fall-back with a small limit)
+        static const unsigned top_edge_limit = getenv("NBODY_BH_TOP_MAX_EDGES") ? (unsigned)std::min(atoi(getenv("NBODY_BH_TOP_MAX_EDGES")), BTC_MAX_EDGES) : (unsigned)BTC_MAX_EDGES;
 #define BHL_ARGS posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,      \
                  (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, \
                  w.node_cap, w.status, (unsigned *)w.climb_start, cta_climb ? (uint4 *)w.node_owner : nullptr, (unsigned *)w.box + 8, w.node_cap / 4
@@ -1503,7 +1505,7 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
 #undef BHL_LAUNCH
 #undef BHL_ARGS
 #define BCC_ARGS bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count, (const uint4 *)w.node_owner, (const unsigned *)w.box + 8, w.node_cap / 4, \
-                 (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap
+                 (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap, top_edge_limit
         if (want_trace) {
             unsigned long long *tr = (unsigned long long *)w.trace + 32;
             cudaMemsetAsync(tr, 0, 4 * sizeof(long long), st);

@@ -339,3 +339,23 @@ def test_bh_reservation_grows_before_it_overflows():
         got = s.bodies.copy()
     for f in ("pos", "vel", "acc"):
         assert np.array_equal(bits(got[f]), bits(want[f])), f
+
+
+@pytest.mark.parametrize("n", [6000, 30000])
+def test_execution_variants_bit_identical(n):
+    """the A/B switches of the build, the sort and the collision pass change how a step runs, never a bit of its result:
+    tools/step_checksum.py (state after 6 reference steps with collisions + every cell of the next tree) under each switch.
+    NBODY_BH_TOP_MAX_EDGES=100 forces the one-CTA top-of-tree kernel into its fall-back (the atomic climb)."""
+    import subprocess
+    import sys
+
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "step_checksum.py")
+    variants = [{}, {"NBODY_BH_LOCAL": "0"}, {"NBODY_SORT_LAZY": "0"}, {"NBODY_BH_CTA_CLIMB": "0"}, {"NBODY_COL_STRIP": "0"},
+                {"NBODY_BH_FUSE_INSERT": "0"}, {"NBODY_SORT_COOP": "0"}, {"NBODY_BHL_GEOM": "2"}, {"NBODY_BHL_GEOM": "6"}, {"NBODY_BH_TOP_MAX_EDGES": "100"}]
+    lines = []
+    for v in variants:
+        env = dict(os.environ, **v)
+        r = subprocess.run([sys.executable, tool, str(n), "6"], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (v, r.stderr[-2000:])
+        lines.append(r.stdout.strip().splitlines()[-1])
+    assert all(l == lines[0] for l in lines), list(zip(variants, lines))

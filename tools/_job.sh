@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_multiproc.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_bh.py -m gpu -q -x -p no:cacheprovider -k "variants" 2>&1 | tail -12
