@@ -32,7 +32,7 @@ constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ROWS_LARGE = 16, RS_ROWS_SMALL = 8;
 constexpr size_t RS_ROWS2_MAX_N = 40000, RS_ROWS4_MAX_N = 200000;
 #ifndef RS_SMALL_TILE_MAX_N
-#define RS_SMALL_TILE_MAX_N (8u << 20)
+#define RS_SMALL_TILE_MAX_N (6u << 20)
 #endif
 constexpr int rs_rows_for(size_t n) { return n <= RS_ROWS2_MAX_N ? 2 : n <= RS_ROWS4_MAX_N ? 4 : n <= (size_t)RS_SMALL_TILE_MAX_N ? RS_ROWS_SMALL : RS_ROWS_LARGE; }
 constexpr int RS_MAX_PASSES = 8;
@@ -401,8 +401,11 @@ __device__ __forceinline__ void rs_grid_barrier(unsigned *counter, unsigned targ
     __syncthreads();
 }
 
+#ifndef RS_BOUNDS8
+#define RS_BOUNDS8 2
+#endif
 template <bool HAS_VALS, int RS_ROWS>
-static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 8 ? 2 : 3))
+static __global__ void __launch_bounds__(RS_THREADS, (RS_ROWS <= 4 ? 2 : RS_ROWS <= 8 ? RS_BOUNDS8 : 3))
 os_sort_all_kernel(unsigned long long *keys_a, unsigned long long *keys_b, unsigned *vals_a, unsigned *vals_b, size_t n,
                    const unsigned *__restrict__ n_dev, int pass0, int npasses, int lazy_passes, const unsigned *__restrict__ hist,
                    unsigned *__restrict__ misc, unsigned long long *status)
