@@ -15,6 +15,15 @@
  *   NBODY_PEER_TIMEOUT_S   seconds a rank waits for a peer's positions in the cross-process exchange before the
  *                          context fails with NBODY_ESTATE instead of spinning for ever (default 120)
  *   NBODY_BH_WALK_WINDOW   lane window of the warp-cooperative Barnes-Hut walk (default 256; 1 = lock-step lanes)
+ *   NBODY_BH_NODE_FACTOR   Barnes-Hut cells reserved per body (default 4, at most 33)
+ * A/B switches of the execution (read once per process; every setting gives the same bits, tests/test_gpu_bh.py):
+ *   NBODY_SORT_LAZY=0      radix sort over all eight digits instead of the leading ones + run repair
+ *   NBODY_SORT_COOP=0      one launch per digit pass instead of the all-passes cooperative kernel
+ *   NBODY_BH_LOCAL=0       round-1 emit + climb-from-the-leaves instead of the window-local build
+ *   NBODY_BH_CTA_CLIMB=0   atomic climb over the top of the tree at every size (default: one CTA's shared memory up to 32,768 bodies)
+ *   NBODY_BH_FUSE_INSERT=0 collision grid filled by its own kernel instead of the Barnes-Hut walk
+ *   NBODY_COL_STRIP=W      width of the collision grid's x strips (default 37.5; 0 = whole cells)
+ *   NBODY_BH_TRACE=1       per-phase clocks of the local build kernels on stderr (tuning; synchronises)
  *
  * Plain C: pointers and sizes only, no C++/torch types.  All functions return 0 on success or a
  * negative NBODY_E* code; they never throw, never call exit().  A context is used by one host
