@@ -192,7 +192,7 @@ struct BhWorkspace {
     int dims = 2;                // 2 = the reference's quadtree, 3 = octree
     unsigned *status = nullptr;  // host-visible sticky flags ([0] = more cells than reserved), owned by the context
     // cleared by one memset at the start of every build: box | sort scratch | scan scratch | arrival counters
-    void *zero_region = nullptr, *sort_temp = nullptr, *scan_temp = nullptr;
+    void *zero_region = nullptr, *sort_temp = nullptr, *scan_temp = nullptr, *shard_scan = nullptr;
     size_t zero_bytes = 0;
     bool count_valid = false;
     bool warp_walk = false;      // warp-cooperative walk, or (default) one independent walk per thread
