@@ -75,14 +75,21 @@ __global__ void __launch_bounds__(256) bh_bbox_kernel(const float *__restrict__ 
             mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
         }
     }
+    // warp, then CTA (shared-memory atomics), then one global atomic per CTA and word: the six words are the same for
+    // everybody, and same-address atomics queue up in L2
+    __shared__ unsigned sbox[6];
+    if (threadIdx.x < 6) sbox[threadIdx.x] = 0u;
+    __syncthreads();
 #pragma unroll
     for (int c = 0; c < DIMS; ++c) {
         for (int o = 16; o > 0; o >>= 1) {
             mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
             mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
         }
-        if ((threadIdx.x & 31) == 0) { atomicMax(&box[c], ~f2ord(mn[c])); atomicMax(&box[3 + c], f2ord(mx[c])); }
+        if ((threadIdx.x & 31) == 0) { atomicMax(&sbox[c], ~f2ord(mn[c])); atomicMax(&sbox[3 + c], f2ord(mx[c])); }
     }
+    __syncthreads();
+    if (threadIdx.x < 6 && (threadIdx.x % 3) < DIMS) atomicMax(&box[threadIdx.x], sbox[threadIdx.x]);
 }
 
 // Quad::new_containing, Quad.hpp:40-44: center = (min+max)*0.5f ; size = max over the axes of the extent.

@@ -36,3 +36,15 @@ def test_c_driver_links_against_the_library(tmp_path):
         subprocess.check_call(["make", "-s", "-C", ROOT, "host"])
     r = subprocess.run([exe, "--help"], capture_output=True, text=True)
     assert r.returncode == 2 and "usage:" in r.stderr
+
+
+def test_radix_sort_scratch_holds_every_smaller_input(tmp_path):
+    """tests/cpp/sort_sizing.cu: host-side sizing rules of csrc/radix_sort.cuh (tile tiers, scratch layout), run on the CPU"""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    exe = str(tmp_path / "sort_sizing")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "sort_sizing.cu")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
