@@ -20,6 +20,7 @@
  *   NBODY_SORT_LAZY=0      radix sort over all eight digits instead of the leading ones + run repair
  *   NBODY_SORT_COOP=0      one launch per digit pass instead of the all-passes cooperative kernel
  *   NBODY_BH_LOCAL=0       round-1 emit + climb-from-the-leaves instead of the window-local build
+ *   NBODY_PDL=0            plain kernel launches instead of programmatic dependent launches along the Barnes-Hut step
  *   NBODY_BH_CTA_CLIMB=0   atomic climb over the top of the tree at every size (default: one CTA's shared memory up to 32,768 bodies)
  *   NBODY_BH_FUSE_INSERT=0 collision grid filled by its own kernel instead of the Barnes-Hut walk
  *   NBODY_COL_STRIP=W      width of the collision grid's x strips (default 37.5; 0 = whole cells)

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256)
 bh_keys_kernel(const float *__restrict__ posm, size_t n, const unsigned *__restrict__ box, BhRoot *__restrict__ root_out,
                unsigned long long *__restrict__ keys, unsigned *__restrict__ idx, unsigned *__restrict__ sort_hist)
 {
+    pdl_enter();
     __shared__ unsigned sh[FOLD_HIST ? RS_MAX_PASSES : 1][256];
     if (FOLD_HIST) rs_hist_clear(sh);
     const BhRoot root = bh_root_from_box<DIMS>(box);
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256)
 bh_count_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned *__restrict__ count,
                 unsigned char *__restrict__ first, unsigned char *__restrict__ leaf)
 {
+    pdl_enter();
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     if (s == 0) count[n] = 0;                                // terminates the exclusive scan over count[0..n]
@@ -444,6 +446,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
                      BhNodes nodes, unsigned *__restrict__ arrive, unsigned cap, unsigned *status, unsigned *__restrict__ gstart,
                      uint4 *__restrict__ edge_list, unsigned *__restrict__ edge_count, unsigned edge_cap, unsigned long long *trace)
 {
+    pdl_enter();
     // tuning aid (NBODY_BH_TRACE): per phase, the largest number of SM cycles any thread needed to get there
     const long long trace_t0 = TRACE ? clock64() : 0;
     const unsigned exp_ = TRACE ? (unsigned)trace[15] : 0u;      // timing experiments (results invalid): 1 no stores, 2 no rcp, 4 no marks
@@ -733,6 +736,7 @@ __global__ void __launch_bounds__(256)
 bh_climb_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, const unsigned *__restrict__ count,
                 const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive, unsigned cap, unsigned long long *trace)
 {
+    pdl_enter();
     const long long trace_t0 = TRACE ? clock64() : 0;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n || count[s] == 0) return;
@@ -772,6 +776,7 @@ bh_top_cta_kernel(BhNodes nodes, size_t n, const unsigned *__restrict__ offs, co
                   const unsigned *__restrict__ nedges, unsigned edge_cap, const unsigned *__restrict__ gstart, unsigned *__restrict__ arrive,
                   unsigned cap, unsigned edge_limit, unsigned long long *trace)
 {
+    pdl_enter();
     constexpr unsigned NCHILD = BhT<DIMS>::NCHILD;
     extern __shared__ __align__(16) unsigned char btc_raw[];
     BtcSmem<DIMS> &sm = *reinterpret_cast<BtcSmem<DIMS> *>(btc_raw);
@@ -1257,6 +1262,7 @@ bh_walk_direct_kernel(const float *__restrict__ posm, const unsigned *__restrict
                       float *__restrict__ accp, unsigned cap, unsigned long long *visits, const BhFuse fz,
                       const unsigned *__restrict__ n_dev)
 {
+    pdl_enter();
     if (n_dev) n = min(n, (size_t)*n_dev);                  // sharded: `idx` is the compacted list of this GPU's targets
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned body = s < n ? idx[s] : 0u;              // targets in Z-order: neighbouring threads walk alike
@@ -1489,15 +1495,17 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
     if ((e = cudaMemsetAsync(w.zero_region, 0, w.zero_bytes, st)) != cudaSuccess) return e;
     bh_bbox_kernel<DIMS><<<std::min(g256, 4u * 148u), 256, 0, st>>>(posm, n, (unsigned *)w.box);
     // stable LSD sort; the result lands back in the first buffer pair -> swap roles
-    bh_keys_kernel<DIMS, true><<<g256, 256, 0, st>>>(posm, n, (const unsigned *)w.box, (BhRoot *)w.root, (unsigned long long *)w.keys_in,
-                                                     (unsigned *)w.idx_in, (unsigned *)w.sort_temp);
+    // (from here on a kernel may become resident while its predecessor still runs: launch_pdl / pdl_enter, common.cuh)
+    if ((e = launch_pdl(bh_keys_kernel<DIMS, true>, dim3(g256), dim3(256), 0, st, posm, n, (const unsigned *)w.box, (BhRoot *)w.root,
+                        (unsigned long long *)w.keys_in, (unsigned *)w.idx_in, (unsigned *)w.sort_temp)) != cudaSuccess) return e;
     // high digits first: the leading 32 bits (16 quadtree levels; 48 bits = 16 octree levels) order all bodies but the few
     // that share a deeper cell, which the sort's run repair puts right (radix_sort.cuh)
     if ((e = radix_sort_u64((unsigned long long *)w.keys_in, (unsigned long long *)w.keys, (unsigned *)w.idx_in, (unsigned *)w.idx,
                             n, w.sort_temp, st, 0, 64, launches, nullptr, true, DIMS == 3 ? 16 : 32)) != cudaSuccess) return e;
     std::swap(w.keys_in, w.keys);
     std::swap(w.idx_in, w.idx);
-    bh_count_kernel<DIMS><<<g256, 256, 0, st>>>((const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first, (unsigned char *)w.leaf);
+    if ((e = launch_pdl(bh_count_kernel<DIMS>, dim3(g256), dim3(256), 0, st, (const unsigned long long *)w.keys, n, cnt, (unsigned char *)w.first,
+                        (unsigned char *)w.leaf)) != cudaSuccess) return e;
     if ((e = exclusive_scan_u32((const unsigned *)w.count, (unsigned *)w.offs, n + 1, w.scan_temp, st, launches, true)) != cudaSuccess) return e;
     // cells, centres of mass and skip pointers: the local kernel + the climb over the few long cells (default), or the
     // round-1/2 pair emit + climb-from-the-leaves (NBODY_BH_LOCAL=0; bit-identical trees, kept for comparison)
@@ -1520,7 +1528,8 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
 #define BHL_ARGS posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root, (const unsigned *)w.offs,      \
                  (const unsigned *)w.count, (const unsigned char *)w.first, (const unsigned char *)w.leaf, bh_nodes(w), (unsigned *)w.node_arrive, \
                  w.node_cap, w.status, (unsigned *)w.climb_start, cta_climb ? (uint4 *)w.node_owner : nullptr, (unsigned *)w.box + 8, w.node_cap / 4
-#define BHL_LAUNCH(T, M, H, TR) bh_emit_local_kernel<DIMS, T, M, H><<<(unsigned)((n + (M) - 1) / (M)), (M) + (H), 0, st>>>(BHL_ARGS, TR)
+#define BHL_LAUNCH(T, M, H, TR) do { if ((e = launch_pdl(bh_emit_local_kernel<DIMS, T, M, H>, dim3((unsigned)((n + (M) - 1) / (M))), dim3((M) + (H)), 0, st, \
+                                                                 BHL_ARGS, TR)) != cudaSuccess) return e; } while (0)
         if (want_trace) {
             const unsigned lgrid_trace = (unsigned)((n + 255) / 256);
             if (!w.trace && cudaMalloc(&w.trace, 2048 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
@@ -1552,7 +1561,7 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
         if (want_trace) {
             unsigned long long *tr = (unsigned long long *)w.trace + 32;
             cudaMemsetAsync(tr, 0, 4 * sizeof(long long), st);
-            if (cta_climb) bh_top_cta_kernel<DIMS, true><<<1, BTC_THREADS, sizeof(BtcSmem<DIMS>), st>>>(BCC_ARGS, tr);
+            if (cta_climb) e = launch_pdl(bh_top_cta_kernel<DIMS, true>, dim3(1), dim3(BTC_THREADS), sizeof(BtcSmem<DIMS>), st, BCC_ARGS, tr);
             else bh_climb_kernel<DIMS, true><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
                                                                    (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap, tr);
             unsigned long long h[4];
@@ -1560,11 +1569,12 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
                 fprintf(stderr, cta_climb ? "[top of the tree, one CTA, n=%zu] edges %llu, deepest %llu, (%llu), cycles %llu\n"
                                           : "[climb n=%zu] chains %llu, most cells finished by one thread %llu (%llu with several children), max cycles %llu\n", n, h[0], h[1], h[2], h[3]);
         } else if (cta_climb)
-            bh_top_cta_kernel<DIMS, false><<<1, BTC_THREADS, sizeof(BtcSmem<DIMS>), st>>>(BCC_ARGS, nullptr);
+            e = launch_pdl(bh_top_cta_kernel<DIMS, false>, dim3(1), dim3(BTC_THREADS), sizeof(BtcSmem<DIMS>), st, BCC_ARGS, (unsigned long long *)nullptr);
         else
-            bh_climb_kernel<DIMS, false><<<g256, 256, 0, st>>>(bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
-                                                               (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap, nullptr);
+            e = launch_pdl(bh_climb_kernel<DIMS, false>, dim3(g256), dim3(256), 0, st, bh_nodes(w), n, (const unsigned *)w.offs, (const unsigned *)w.count,
+                           (const unsigned *)w.climb_start, (unsigned *)w.node_arrive, w.node_cap, (unsigned long long *)nullptr);
 #undef BCC_ARGS
+        if (e != cudaSuccess) return e;
     } else {
         bh_emit_kernel<DIMS><<<g128, 128, 0, st>>>(posm, (const unsigned long long *)w.keys, (const unsigned *)w.idx, n, (const BhRoot *)w.root,
                                                    (const unsigned *)w.offs, (const unsigned *)w.count, (const unsigned char *)w.first,
@@ -1694,8 +1704,8 @@ static void bh_walk_t(const BhWorkspace &w, const float *posm, size_t n, float t
         else bh_walk_warp_kernel<DIMS, false><<<g, 128, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, w.walk_window, visits, n_dev);
         return;
     }
-    if (refcompat) bh_walk_direct_kernel<DIMS, true, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz, n_dev);
-    else bh_walk_direct_kernel<DIMS, false, FUSE><<<g, WALK_THREADS, 0, st>>>(posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz, n_dev);
+    if (refcompat) launch_pdl(bh_walk_direct_kernel<DIMS, true, FUSE>, dim3(g), dim3(WALK_THREADS), 0, st, posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz, n_dev);
+    else launch_pdl(bh_walk_direct_kernel<DIMS, false, FUSE>, dim3(g), dim3(WALK_THREADS), 0, st, posm, idx, n, nd, t_sq, e_sq, fix, shard_start, shard_count, accp, w.node_cap, visits, fz, n_dev);
 }
 
 // `fuse` != nullptr: the walk threads also integrate their targets (kick-drift; one GPU, whole array = one shard)

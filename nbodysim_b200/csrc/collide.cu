@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) col_grid_detect_kernel(ColArgs a, ColGrid
 
 __global__ void __launch_bounds__(256) col_grid_pairs_kernel(ColArgs a, ColGrid g)
 {
+    pdl_enter();
     col_grid_pairs(a, g, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
 col_finish_kernel(ColArgs a, ColGrid g, unsigned long long *pairs_b, unsigned *ranks, int key_bits)
 {
     __shared__ ClSmem sm;
+    pdl_enter();
     const unsigned tid = threadIdx.x;
     if (tid < 8) a.counters[tid] = 0;                                     // the statistics of a pass that found nothing
     const unsigned P = min(__ldcg(g.flags + 2), a.pair_cap);
@@ -228,15 +230,17 @@ cudaError_t CollideWorkspace::run(float *posm, float *vel, size_t n, cudaStream_
         if (launches) *launches += 1;
     }
     if (single_cta) {   // small scene: sweep pairs straight from the grid, everything else in one CTA
-        col_grid_pairs_kernel<<<gb, 256, 0, st>>>(a, g);
+        if ((e = launch_pdl(col_grid_pairs_kernel, dim3(gb), dim3(256), 0, st, a, g)) != cudaSuccess) return e;
         // an explicit cluster of ONE CTA: its sort uses the cluster primitives of cluster_prims.cuh
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(1); cfg.blockDim = dim3(CL_THREADS); cfg.stream = st;
-        cudaLaunchAttribute at;
-        at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = 1; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-        cfg.attrs = &at; cfg.numAttrs = 1;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // may become resident while the pair kernel runs (pdl_enter)
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         if ((e = cudaLaunchKernelEx(&cfg, col_finish_kernel, a, g, (unsigned long long *)pairs, (unsigned *)ranks, key_bits)) != cudaSuccess) return e;
         if (launches) *launches += 2;
         return cudaGetLastError();

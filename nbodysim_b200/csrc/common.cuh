@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace nb {
 
@@ -25,6 +27,36 @@ constexpr float PAD_POS = 1.0e18f;       // coordinates of the zero-mass padding
 __host__ __device__ inline size_t blk_index(size_t body, int comp)
 {
     return (body >> 8) * (size_t)BLK_ELEMS + (size_t)comp * BLK + (body & 255);
+}
+
+// ---- programmatic dependent launch (griddepcontrol) -------------------------------------------------------------------------
+// The Barnes-Hut step is ten short kernels in a row; a kernel launched with launch_pdl() may become RESIDENT while its
+// predecessor is still running and waits in pdl_enter() until that one has completed (and its writes are visible), so the
+// ~1.5 us a kernel boundary costs inside a graph overlaps with the predecessor's tail.  pdl_enter() is the first statement
+// of every kernel on that path: wait for the predecessor, THEN allow the successor to be made resident (at most one kernel
+// ahead).  In a kernel that was launched normally both instructions do nothing.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+}
+// NBODY_PDL=0: plain launches
+inline bool pdl_enabled()
+{
+    static const bool on = !(getenv("NBODY_PDL") && atoi(getenv("NBODY_PDL")) == 0);
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- sm_100a PTX helpers: mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----------

@@ -409,22 +409,25 @@ int enqueue_step(nbody_ctx *ctx, float dt, bool acc_only, bool profile)
         if (ctx->bh) {
             if (d.gathered_pending) { CU(wait_remote(d)); waited = true; }
             int nl = 0;
+            // small scenes on one GPU: the walk threads integrate their own targets (no separate integrator launch)
+            bh_fused = ctx->world == 1 && !acc_only && !d.bh.warp_walk && ctx->n_padded <= 131072 && ctx->p.fuse_integrator != 0;
+            static const bool fuse_insert_off = getenv("NBODY_BH_FUSE_INSERT") && atoi(getenv("NBODY_BH_FUSE_INSERT")) == 0;   // A/B switch
+            // ... and fill the collision pass's screening grid (Simulation::step()); the grid is cleared HERE, ahead of the
+            // build, so that nothing but kernels lies between the tree's last kernel and the walk (programmatic launches)
+            const bool fill_grid = bh_fused && ctx->p.collide && !fuse_insert_off;
+            if (fill_grid) CU(d.col.prepare(d.stream));
             CU(d.bh.build((const float *)d.posm[d.cur], ctx->n, d.stream, &nl));
             if (prof) {
                 CU(cudaEventRecord(d.ev_t[3], d.stream));
                 CU(cudaMemsetAsync(d.walk_visits, 0, 2 * sizeof(unsigned long long), d.stream));
             }
-            // small scenes on one GPU: the walk threads integrate their own targets (no separate integrator launch)
-            bh_fused = ctx->world == 1 && !acc_only && !d.bh.warp_walk && ctx->n_padded <= 131072 && ctx->p.fuse_integrator != 0;
             BhFuseArgs fa;
             ColArgs col_a;
             ColGrid col_g;
             if (bh_fused) {
                 fa.posm_next = (float *)d.posm[d.cur ^ 1]; fa.vel = (float *)d.vel; fa.acc = (float *)d.acc;
                 fa.G = ctx->p.G; fa.ip = make_ip(ctx, dt);
-                static const bool fuse_insert_off = getenv("NBODY_BH_FUSE_INSERT") && atoi(getenv("NBODY_BH_FUSE_INSERT")) == 0;   // A/B switch
-                if (ctx->p.collide && !fuse_insert_off) {   // Simulation::step(): the walk threads also fill the collision pass's screening grid
-                    CU(d.col.prepare(d.stream));
+                if (fill_grid) {
                     col_a = d.col.args((float *)d.posm[d.cur ^ 1], (float *)d.vel, ctx->n);
                     col_g = d.col.grid_view();
                     fa.col_args = &col_a; fa.col_grid = &col_g;

@@ -17,6 +17,7 @@
 // :56-60) depends on it.  Ping-pong between two buffers; the result always ends in the FIRST buffer.
 #pragma once
 #include <cuda_runtime.h>
+#include "common.cuh"                      // pdl_enter / launch_pdl
 #include <cstdint>
 #include <cstdlib>
 #include <algorithm>
@@ -597,6 +598,7 @@ static __global__ void __launch_bounds__(RS_THREADS)
 scan_excl_kernel(const unsigned *__restrict__ in, unsigned *__restrict__ out, size_t n, unsigned *__restrict__ ticket,
                  unsigned long long *status)
 {
+    pdl_enter();
     __shared__ unsigned warp_sums[RS_WARPS];
     __shared__ unsigned s_tile, s_excl;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -666,8 +668,8 @@ static inline cudaError_t exclusive_scan_u32(const unsigned *in, unsigned *out, 
     if (n == 0) return cudaSuccess;
     cudaError_t e = cudaSuccess;
     if (!temp_zeroed && (e = cudaMemsetAsync(temp, 0, exclusive_scan_temp_bytes(n), st)) != cudaSuccess) return e;
-    scan_excl_kernel<<<(unsigned)((n + SC_TILE - 1) / SC_TILE), RS_THREADS, 0, st>>>(in, out, n, (unsigned *)temp,
-                                                                                    (unsigned long long *)((char *)temp + 64));
+    if ((e = launch_pdl(scan_excl_kernel, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(RS_THREADS), 0, st, in, out, n, (unsigned *)temp,
+                        (unsigned long long *)((char *)temp + 64))) != cudaSuccess) return e;
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -351,7 +351,7 @@ def test_execution_variants_bit_identical(n):
 
     tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "step_checksum.py")
     variants = [{}, {"NBODY_BH_LOCAL": "0"}, {"NBODY_SORT_LAZY": "0"}, {"NBODY_BH_CTA_CLIMB": "0"}, {"NBODY_COL_STRIP": "0"},
-                {"NBODY_BH_FUSE_INSERT": "0"}, {"NBODY_SORT_COOP": "0"}, {"NBODY_BHL_GEOM": "2"}, {"NBODY_BHL_GEOM": "6"}, {"NBODY_BH_TOP_MAX_EDGES": "100"}]
+                {"NBODY_BH_FUSE_INSERT": "0"}, {"NBODY_SORT_COOP": "0"}, {"NBODY_BHL_GEOM": "2"}, {"NBODY_BHL_GEOM": "6"}, {"NBODY_BH_TOP_MAX_EDGES": "100"}, {"NBODY_PDL": "0"}]
     lines = []
     for v in variants:
         env = dict(os.environ, **v)
