@@ -449,7 +449,6 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
     pdl_enter();
     // tuning aid (NBODY_BH_TRACE): per phase, the largest number of SM cycles any thread needed to get there
     const long long trace_t0 = TRACE ? clock64() : 0;
-    const unsigned exp_ = TRACE ? (unsigned)trace[15] : 0u;      // timing experiments (results invalid): 1 no stores, 2 no rcp, 4 no marks
     int trace_k = 0;
 #define BHL_TRACE() do { if (TRACE) { const unsigned am = __activemask();                                                          \
                                       const unsigned cyc = __reduce_max_sync(am, (unsigned)(clock64() - trace_t0));                  \
@@ -580,9 +579,9 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
             }
             if (ok && span_ok(t)) {
 #pragma unroll
-                for (int c = 0; c < (int)NCHILD - 1; ++c) if (c < nk && !(exp_ & 4u)) spulled[kids[c]] = 1;
+                for (int c = 0; c < (int)NCHILD - 1; ++c) if (c < nk) spulled[kids[c]] = 1;
                 if (ms > 0.f) { // Vec2::operator/=: inv = 1/scalar ; x *= inv ; y *= inv   (1/m correctly rounded: rcp.rn)
-                    const float inv = (exp_ & 2u) ? 0.5f : __frcp_rn(ms);
+                    const float inv = __frcp_rn(ms);
                     px = __fmul_rn(px, inv);
                     py = __fmul_rn(py, inv);
                     if (DIMS == 3) pz = __fmul_rn(pz, inv);
@@ -591,7 +590,7 @@ bh_emit_local_kernel(const float *__restrict__ posm, const unsigned long long *_
                 tp = t; dcur = d;
                 if (d == firstd) { sval[i] = make_float4(px, py, pz, ms); spk[i] = myA | (t << 8); }
                 const unsigned c = off + (unsigned)(d - firstd);
-                if (main_thread && c < cap && !(exp_ & 1u)) {
+                if (main_thread && c < cap) {
                     *reinterpret_cast<float2 *>(nodes.data(c)) = make_float2(px, py);
                     reinterpret_cast<float *>(nodes.data(c))[2] = ms;
                     if (DIMS == 3) reinterpret_cast<float *>(nodes.aux(c))[0] = pz;
@@ -1534,8 +1533,6 @@ static cudaError_t bh_build_t(BhWorkspace &w, const float *posm, size_t n, cudaS
             const unsigned lgrid_trace = (unsigned)((n + 255) / 256);
             if (!w.trace && cudaMalloc(&w.trace, 2048 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
             cudaMemsetAsync(w.trace, 0, 2048 * sizeof(long long), st);
-            const unsigned long long expv = getenv("NBODY_BHL_EXP") ? strtoull(getenv("NBODY_BHL_EXP"), nullptr, 10) : 0ull;
-            cudaMemcpyAsync((unsigned long long *)w.trace + 15, &expv, 8, cudaMemcpyHostToDevice, st);
             BHL_LAUNCH(true, 256, 128, (unsigned long long *)w.trace);
             unsigned long long h[2048];
             if (cudaMemcpyAsync(h, w.trace, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
