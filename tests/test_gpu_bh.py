@@ -358,4 +358,9 @@ def test_execution_variants_bit_identical(n):
         r = subprocess.run([sys.executable, tool, str(n), "6"], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (v, r.stderr[-2000:])
         lines.append(r.stdout.strip().splitlines()[-1])
+    if n == 6000:     # sort_impl = 1: one kernel per phase, in the build and in the collision pass (its large-scene pipeline)
+        r = subprocess.run([sys.executable, tool, str(n), "6", "1"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        variants.append({"sort_impl": "1"})
+        lines.append(r.stdout.strip().splitlines()[-1])
     assert all(l == lines[0] for l in lines), list(zip(variants, lines))
