@@ -131,8 +131,6 @@ cudaError_t launch_unpack_f64(double *pos3, double *vel3, double *acc3, size_t n
 cudaError_t launch_energy(const void *posm, const void *vel, size_t n_padded, size_t shard_start,
                           size_t shard_count, double eps2, bool f64, double *out5, cudaStream_t st);
 
-// fused kick-drift epilogue of the Barnes-Hut walk (small scenes on one GPU): where the walk threads find velocities
-// and store the new state
 // ---- collision pass (collide.cu / collide.cuh): the arguments of a pass and its screening hash grid
 // counters: [0] cell entries, [1] pairs kept (hot components), [2] overflow flag, [3] pairs resolved (narrow test
 // passed), [4] sweep pairs that overlap now
@@ -165,6 +163,8 @@ struct ColGrid {
     unsigned tmask, ecap;
 };
 
+// fused kick-drift epilogue of the Barnes-Hut walk (small scenes on one GPU): where the walk threads find velocities
+// and store the new state
 struct BhFuseArgs {
     float *posm_next, *vel, *acc;
     float G;
